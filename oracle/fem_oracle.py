@@ -1,0 +1,220 @@
+'''CPU restatement (numpy) of the reference's element-integration hot path.
+
+TEST INFRASTRUCTURE ONLY -- may be imported from tests/, from
+__graft_entry__.smoke() and from bench.py's cpu_baseline / --impl reference
+legs, as the checker or the reported CPU baseline; never from nutils_b200/.
+
+Reference: evalf/nutils @ 37d1cc5 (version 10a8), /root/reference/src/nutils.
+The reference generates a Python element loop (evaluable.compile,
+evaluable.py:6532-6838; a listing is in SURVEY.md appendix A).  This module
+restates that loop step by step for structured tensor-product spline spaces on
+a multilinear nodal geometry, and the sparse post-processing exactly:
+
+  element index -> (ix,iy,iz)            transformseq.py:563-579 (C-order ravel)
+  coefficient rows per dimension         function.py:3080-3100 (StructuredBasis.f_dofs_coeffs)
+  N, dN/dxi at the quadrature points     evaluable.py:4328-4374 (Polyval), :4584-4634 (PolyGrad)
+                                         -- evaluated as products of the 1-D factors, which is the
+                                         same polynomial the reference expands with nutils_poly.MulPlan
+  dofs of the element                    function.py:3087-3093 (C-order ravel of per-dim ranges, modulo ndofs)
+  geometry x = sum_v phi_v X_v, J        mesh.py:55-57 (degree-1 spline times nodal coordinates),
+                                         function.py:1266-1295 (_Jacobian.lower)
+  J^-1, det J                            evaluable.py:1403 (Inverse) -> numeric.py:221-242, evaluable.py:1463
+  physical gradient dN J^-1              function.py:1207-1231 (_Gradient.lower)
+  integrand contractions + weights       sample.py:951-956 (_Integral.lower), generated einsums
+  COO append of block, rows, cols        evaluable.py:5383-5501 (LoopConcatenate), :5322-5343, :3474-3487
+  vector dofs ibasis*ncomp+comp          function.py:2623-2626 (field)
+  flat=row*ncols+col, stable argsort,
+  unique, accumulate, rowptr             evaluable.py:588-616, :5646-5652, :3570-3577 -> numeric.py:434-460,
+                                         evaluable.py:5655-5676 -> numeric.py:687-711
+  RHS scatter-add                        evaluable.py:3582-3620 (numpy.add.at)
+
+Parity pin: tests/test_oracle_golden.py checks this module against the
+golden vectors in tests/golden/*.npz, which were produced by the unmodified
+reference itself (oracle/make_golden.py) -- CSR pattern bit-exact, values to
+1e-13 relative.  The same tests pin the C restatement (oracle/fem_oracle.c).
+'''
+
+import itertools
+import numpy
+
+
+class Problem:
+    '''Plain-array description of one structured assembly problem.
+
+    ndims      : int
+    nelems     : int[ndims]
+    degree     : int[ndims]
+    coeffs     : list of float64[nsets_d, p_d+1, p_d+1]   (highest power first, local xi in [0,1])
+    setidx     : list of int[nelems_d]
+    start      : list of int[nelems_d]
+    ndofs_d    : int[ndims]
+    ncomp      : int (vector-valued fields: dof = ibasis*ncomp + comp)
+    qpts, qwts : list of float64[nq_d]  (tensor quadrature, C order)
+    nodes      : float64[ndims, nelems_0+1, ...]  nodal coordinates of the multilinear geometry
+    '''
+
+    def __init__(self, nelems, degree, coeffs, setidx, start, ndofs_d, qpts, qwts, nodes, ncomp=1):
+        self.ndims = len(nelems)
+        self.nelems = tuple(int(n) for n in nelems)
+        self.degree = tuple(int(p) for p in degree)
+        self.coeffs = [numpy.asarray(c, dtype=float) for c in coeffs]
+        self.setidx = [numpy.asarray(s, dtype=numpy.int64) for s in setidx]
+        self.start = [numpy.asarray(s, dtype=numpy.int64) for s in start]
+        self.ndofs_d = tuple(int(n) for n in ndofs_d)
+        self.qpts = [numpy.asarray(x, dtype=float) for x in qpts]
+        self.qwts = [numpy.asarray(w, dtype=float) for w in qwts]
+        self.nodes = numpy.asarray(nodes, dtype=float)
+        self.ncomp = int(ncomp)
+        assert self.nodes.shape == (self.ndims,) + tuple(n + 1 for n in self.nelems)
+
+    @property
+    def nbasis(self):
+        return int(numpy.prod(self.ndofs_d))
+
+    @property
+    def ndofs(self):
+        return self.nbasis * self.ncomp
+
+    @property
+    def ntotal(self):
+        return int(numpy.prod(self.nelems))
+
+
+def _polyval_rows(c, x):
+    'rows of c are polynomials (highest power first); returns [nrows, len(x)] values and derivatives'
+    p = c.shape[1] - 1
+    val = numpy.stack([numpy.polyval(row, x) for row in c])
+    if p:
+        der = numpy.stack([numpy.polyval(row[:-1] * numpy.arange(p, 0, -1.), x) for row in c])
+    else:
+        der = numpy.zeros_like(val)
+    return val, der
+
+
+def _tensor(factors):
+    'C-order tensor product of per-dim [n_d, q_d] tables -> [prod q, prod n]'
+    out = numpy.ones((1, 1))
+    for f in factors:
+        out = (out[:, None, :, None] * f.T[None, :, None, :]).reshape(out.shape[0] * f.shape[1], out.shape[1] * f.shape[0])
+    return out
+
+
+def element_data(prob, ielem):
+    '''Everything the generated loop computes for one element before the integrand:
+    dofs[n_e], N[nq,n_e], grad[nq,n_e,ndims] (physical), wdet[nq].'''
+    nd = prob.ndims
+    idx = numpy.unravel_index(ielem, prob.nelems)
+    vals, ders, ranges = [], [], []
+    for d in range(nd):
+        c = prob.coeffs[d][prob.setidx[d][idx[d]]]
+        v, g = _polyval_rows(c, prob.qpts[d])
+        vals.append(v)
+        ders.append(g)
+        ranges.append((prob.start[d][idx[d]] + numpy.arange(prob.degree[d] + 1)) % prob.ndofs_d[d])
+    N = _tensor(vals)
+    dN = numpy.stack([_tensor([ders[k] if k == d else vals[k] for k in range(nd)]) for d in range(nd)], axis=-1)
+    dofs = ranges[0]
+    for d in range(1, nd):
+        dofs = (dofs[:, None] * prob.ndofs_d[d] + ranges[d][None, :]).ravel()
+    # multilinear geometry: shape functions of the degree-1 spline on this element are (1-xi, xi) per dim
+    lin_v = [numpy.stack([1 - x, x]) for x in prob.qpts]
+    lin_d = [numpy.stack([-numpy.ones_like(x), numpy.ones_like(x)]) for x in prob.qpts]
+    X = prob.nodes[(slice(None),) + tuple(slice(i, i + 2) for i in idx)].reshape(nd, -1)  # [ndims, 2^nd] C-order vertices
+    J = numpy.stack([_tensor([lin_d[k] if k == d else lin_v[k] for k in range(nd)]) @ X.T for d in range(nd)], axis=-1)  # [nq, i, k] = dx_i/dxi_k
+    Jinv = numpy.linalg.inv(J)
+    det = numpy.linalg.det(J)
+    w = _tensor([wq[None, :] for wq in prob.qwts])[:, 0]
+    grad = numpy.einsum('qak,qki->qai', dN, Jinv)
+    return dofs, N, grad, w * abs(det)
+
+
+def _vector_dofs(dofs, ncomp):
+    return (dofs[:, None] * ncomp + numpy.arange(ncomp)[None, :]).ravel()
+
+
+def element_matrix(form, N, grad, wdet, ncomp=1):
+    '''Dense element block for a bilinear form.
+
+    form = ('mass',) | ('stiffness',) | ('elasticity', lmbda, mu) | ('generic', D)
+    with D[ncomp, ndims+1, ncomp, ndims+1] acting on (value, gradient) of test and trial.'''
+    kind = form[0]
+    nd = grad.shape[-1]
+    if kind == 'mass':
+        assert ncomp == 1
+        return numpy.einsum('qa,qb,q->ab', N, N, wdet)
+    if kind == 'stiffness':
+        assert ncomp == 1
+        return numpy.einsum('qai,qbi,q->ab', grad, grad, wdet)
+    if kind == 'elasticity':
+        # second derivative of the energy  eps_ij sigma_ij,  sigma = lmbda tr(eps) I + 2 mu eps  (examples/elasticity.py:50-58)
+        assert ncomp == nd
+        lmbda, mu = form[1], form[2]
+        n_e = N.shape[1]
+        eye = numpy.eye(nd)
+        # du_i/dx_j for basis (a, c): grad[q,a,j] delta_ic
+        G = numpy.einsum('qaj,ic->qacij', grad, eye)
+        eps = .5 * (G + G.swapaxes(-1, -2))
+        sig = lmbda * numpy.einsum('qackk,ij->qacij', eps, eye) + 2 * mu * eps
+        blk = 2 * numpy.einsum('qacij,qbdij,q->acbd', eps, sig, wdet)
+        return blk.reshape(n_e * ncomp, n_e * ncomp)
+    if kind == 'generic':
+        D = numpy.asarray(form[1], dtype=float)
+        B = numpy.concatenate([N[:, :, None], grad], axis=-1)  # [q, a, alpha]
+        n_e = N.shape[1]
+        blk = numpy.einsum('qax,cxdy,qby,q->acbd', B, D, B, wdet)
+        return blk.reshape(n_e * ncomp, n_e * ncomp)
+    raise ValueError(kind)
+
+
+def element_vector(form, N, grad, wdet, ncomp=1):
+    '''Element load vector.  form = ('load',) for int N_a, or ('generic', c) with c[ncomp, ndims+1].'''
+    kind = form[0]
+    if kind == 'load':
+        assert ncomp == 1
+        return numpy.einsum('qa,q->a', N, wdet)
+    if kind == 'generic':
+        c = numpy.asarray(form[1], dtype=float)
+        B = numpy.concatenate([N[:, :, None], grad], axis=-1)
+        return numpy.einsum('qax,cx,q->ac', B, c, wdet).ravel()
+    raise ValueError(kind)
+
+
+def coo_to_csr(values, rows, cols, nrows, ncols):
+    '''evaluable.py:588-616 + :5646-5682: sorted unique CSR with structural zeros kept.'''
+    flat = rows.astype(numpy.int64) * ncols + cols.astype(numpy.int64)
+    order = numpy.argsort(flat, kind='stable')                      # ArgSort, evaluable.py:5577-5581
+    sflat = flat[order]
+    mask = numpy.ones(len(sflat), dtype=bool)                       # UniqueMask, :5604-5612
+    mask[1:] = sflat[1:] != sflat[:-1]
+    inverse = numpy.empty(len(flat), dtype=numpy.int64)             # UniqueInverse, :5632-5640
+    inverse[order] = numpy.cumsum(mask) - 1
+    nnz = int(mask.sum())
+    data = numpy.bincount(inverse, weights=values, minlength=nnz)   # numeric.accumulate, numeric.py:448-455
+    ukeys = sflat[mask]
+    urows, ucols = numpy.divmod(ukeys, ncols)
+    rowptr = numpy.searchsorted(urows, numpy.arange(nrows + 1)).astype(numpy.int64)  # numeric.compress_indices, numeric.py:687-711
+    return data, rowptr, ucols.astype(numpy.int64)
+
+
+def assemble(prob, matrix_forms=(), vector_forms=()):
+    '''Run the element loop and the sparse post-processing.
+
+    Returns ([(values, rowptr, colidx), ...], [rhs, ...]).'''
+    nc = prob.ncomp
+    n_e = int(numpy.prod([p + 1 for p in prob.degree])) * nc
+    nel = prob.ntotal
+    vals = [numpy.empty((nel, n_e, n_e)) for _ in matrix_forms]
+    rows = numpy.empty((nel, n_e, n_e), dtype=numpy.int64)
+    cols = numpy.empty((nel, n_e, n_e), dtype=numpy.int64)
+    rhs = [numpy.zeros(prob.ndofs) for _ in vector_forms]
+    for ielem in range(nel):
+        dofs, N, grad, wdet = element_data(prob, ielem)
+        vdofs = _vector_dofs(dofs, nc)
+        rows[ielem] = vdofs[:, None]
+        cols[ielem] = vdofs[None, :]
+        for k, form in enumerate(matrix_forms):
+            vals[k][ielem] = element_matrix(form, N, grad, wdet, nc)
+        for k, form in enumerate(vector_forms):
+            numpy.add.at(rhs[k], vdofs, element_vector(form, N, grad, wdet, nc))
+    mats = [coo_to_csr(v.ravel(), rows.ravel(), cols.ravel(), prob.ndofs, prob.ndofs) for v in vals]
+    return mats, rhs
