@@ -1,0 +1,163 @@
+/*
+ * b200fem.h -- C ABI of the B200-native element-integration engine.
+ *
+ * Scope: the hot path behind nutils' Sample.integrate / Sample.integral /
+ * Topology.integral -> sparse assembly (reference: evalf/nutils @ 37d1cc5).
+ * The reference has NO native interface on this path (it is pure Python and
+ * its only extension points are Python-level), so every
+ * entry point below cites the reference code whose work it replaces; the
+ * conventions follow the reference's one ctypes boundary, the MKL backend
+ * (src/nutils/matrix/_mkl.py:10-97): plain C, caller-owned C-contiguous
+ * buffers, integer status return, no callbacks, no exceptions.
+ *
+ * All functions return B2_OK (0) or a negative B2_E* code; b2_strerror()
+ * gives a message, b2_last_error(ctx) the detail of the last failure.
+ * A context is bound to one CUDA device and is not fork-safe (the reference
+ * forks in nutils.parallel: create contexts after forking).
+ * Pointers named *_host are host memory, *_dev are device memory on the
+ * context's device.  Index arrays on the ABI are int64 like the reference's
+ * (function.as_csr returns int64 rowptr/colidx), values are float64.
+ */
+#ifndef B200FEM_H
+#define B200FEM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define B2_OK 0
+#define B2_EINVAL -1      /* invalid argument */
+#define B2_ENOMEM -2      /* host or device allocation failed */
+#define B2_ECUDA -3       /* CUDA runtime error (see b2_last_error) */
+#define B2_ENODEV -4      /* no usable sm_100 device */
+#define B2_EUNSUPPORTED -5 /* valid request outside the implemented path */
+
+#define B2_MAX_DIMS 3
+#define B2_MAX_DEGREE 4
+#define B2_MAX_FORMS 4
+
+typedef struct b2_ctx b2_ctx;
+typedef struct b2_basis b2_basis;
+typedef struct b2_quad b2_quad;
+typedef struct b2_geom b2_geom;
+typedef struct b2_pattern b2_pattern;
+
+const char* b2_strerror(int code);
+const char* b2_last_error(const b2_ctx* ctx);
+int b2_version(void);
+
+/* ---- context ---------------------------------------------------------------------------------
+ * Replaces the process-level state of the reference's loop runner: nutils.parallel.fork /
+ * ctxrange (src/nutils/parallel.py:27-154) -- one context per process and GPU. */
+int b2_device_count(int* count);
+int b2_ctx_create(int device, b2_ctx** out);
+int b2_ctx_destroy(b2_ctx* ctx);
+/* run on an externally owned CUDA stream (cudaStream_t as void*; NULL = the context's own stream) */
+int b2_ctx_set_stream(b2_ctx* ctx, void* cuda_stream);
+int b2_ctx_synchronize(b2_ctx* ctx);
+/* CUDA-event timing on the context's stream (used by bench.py for the roofline figure) */
+int b2_ctx_timer_start(b2_ctx* ctx);
+int b2_ctx_timer_stop(b2_ctx* ctx, float* milliseconds);
+/* number of kernels launched by this context since creation */
+int64_t b2_ctx_launch_count(const b2_ctx* ctx);
+/* pinned host memory for the end-to-end path */
+int b2_host_alloc(b2_ctx* ctx, int64_t nbytes, void** out_host);
+int b2_host_free(b2_ctx* ctx, void* host);
+int b2_device_alloc(b2_ctx* ctx, int64_t nbytes, void** out_dev);
+int b2_device_free(b2_ctx* ctx, void* dev);
+int b2_memcpy_d2h(b2_ctx* ctx, void* dst_host, const void* src_dev, int64_t nbytes);
+int b2_memcpy_h2d(b2_ctx* ctx, void* dst_dev, const void* src_host, int64_t nbytes);
+int b2_memset_zero(b2_ctx* ctx, void* dev, int64_t nbytes);
+/* write `nbytes` of scratch larger than L2 (bench.py: flush L2 between timed iterations) */
+int b2_flush_l2(b2_ctx* ctx);
+
+/* ---- basis -----------------------------------------------------------------------------------
+ * Tensor-product spline space on a structured topology.  Replaces function.StructuredBasis
+ * (src/nutils/function.py:3040-3100: _coeffs, _start_dofs, _stop_dofs, _dofs_shape) as produced by
+ * StructuredTopology.basis_spline (src/nutils/topology.py:2209-2324).  Per dimension d:
+ *   coeffs[d]  float64[nsets[d]][degree[d]+1][degree[d]+1]  local polynomials, HIGHEST power first,
+ *              in the element coordinate xi in [0,1]   (topology.py:2327-2361)
+ *   setidx[d]  int32[nelems[d]]   coefficient set of each element
+ *   start[d]   int64[nelems[d]]   first dof of each element; element dofs are start..start+degree
+ *   ndofs[d]   number of dofs along d
+ * Global dof = C-order ravel of the per-dimension dofs (function.py:3087-3093); vector-valued
+ * fields with ncomp components use dof = ibasis*ncomp + comp (function.py:2623-2626). */
+int b2_basis_create(b2_ctx* ctx, int ndims, const int64_t* nelems, const int32_t* degree, const int32_t* nsets,
+                    const double* const* coeffs, const int32_t* const* setidx, const int64_t* const* start,
+                    const int64_t* ndofs, int ncomp, b2_basis** out);
+int b2_basis_destroy(b2_basis* basis);
+int64_t b2_basis_ndofs(const b2_basis* basis);
+
+/* ---- quadrature ------------------------------------------------------------------------------
+ * Uniform tensor rule, the same for every element: replaces PointsSequence._Uniform over
+ * TensorPoints of gauss1 rules (src/nutils/pointsseq.py:420-428, points.py:144-164, 342-355).
+ * pts[d], wts[d]: float64[nq[d]] on [0,1]; tensor points are the C-order outer product. */
+int b2_quad_create_tensor(b2_ctx* ctx, int ndims, const int32_t* nq, const double* const* pts, const double* const* wts, b2_quad** out);
+int b2_quad_destroy(b2_quad* quad);
+
+/* ---- geometry --------------------------------------------------------------------------------
+ * Multilinear nodal geometry x = sum_v phi_v X_v, the geometry mesh.rectilinear builds for
+ * non-integer vertices (src/nutils/mesh.py:55-57); J = dx/dxi, J^-1 and |det J| are evaluated per
+ * quadrature point in the kernel (function.py:1207-1231, 1266-1295; evaluable.py:1403, 1463).
+ * nodes_host: float64[ndims][nelems[0]+1][nelems[1]+1][nelems[2]+1]. */
+int b2_geom_create_nodal(b2_ctx* ctx, int ndims, const int64_t* nelems, const double* nodes_host, b2_geom** out);
+/* re-upload the coordinates (same shape); part of the end-to-end timed region in bench.py */
+int b2_geom_update_nodal(b2_geom* geom, const double* nodes_host);
+int b2_geom_destroy(b2_geom* geom);
+
+/* ---- CSR pattern -----------------------------------------------------------------------------
+ * The sorted, unique (row, col) set that the reference obtains after the element loop by
+ * argsort/unique/compress_indices (src/nutils/evaluable.py:588-616, 5646-5682;
+ * numeric.py:687-711) -- here built once, analytically, from the tensor structure of the basis;
+ * structural zeros are kept exactly like the reference does. */
+int b2_pattern_create(b2_ctx* ctx, const b2_basis* basis, b2_pattern** out);
+int b2_pattern_destroy(b2_pattern* pattern);
+int64_t b2_pattern_nnz(const b2_pattern* pattern);
+int64_t b2_pattern_nrows(const b2_pattern* pattern);
+/* rowptr int64[nrows+1], colidx int64[nnz]; bit-equal to function.as_csr of the reference */
+int b2_pattern_export_host(b2_pattern* pattern, int64_t* rowptr_host, int64_t* colidx_host);
+int b2_pattern_export_device(b2_pattern* pattern, int64_t* rowptr_dev, int64_t* colidx_dev);
+
+/* ---- assembly --------------------------------------------------------------------------------
+ * One pass of the element loop that evaluable.compile generates (src/nutils/evaluable.py:6532-6838,
+ * listing in SURVEY.md appendix A) for integrals lowered by sample._Integral.lower
+ * (src/nutils/sample.py:944-956): basis evaluation (Polyval/PolyGrad), geometry, the integrand
+ * einsums, the weighted sum over quadrature points and the scatter into CSR values
+ * (LoopConcatenate + Assemble, evaluable.py:5383-5501, 3552-3620) and load vectors.
+ *
+ * Matrix form m is the bilinear form
+ *     A[(i,c),(j,e)] = int sum_{x,y} D_m[c][x][e][y] d_x N_i d_y N_j |det J| dxi,   x,y in 0..ndims,
+ * d_0 = value, d_k = derivative to physical coordinate k-1;  D_m: float64[ncomp][ndims+1][ncomp][ndims+1].
+ * (mass: D[0][0][0][0]=1;  Laplace stiffness: D[0][k][0][k]=1, k>=1;  elasticity:
+ *  D[c][1+k][e][1+l] = lambda d_ck d_el + mu (d_ce d_kl + d_cl d_ek).)
+ * Vector form v:  b[(i,c)] = int sum_x C_v[c][x] d_x N_i |det J| dxi;  C_v: float64[ncomp][ndims+1].
+ *
+ * Elements [elem_begin, elem_end) of the C-order element numbering are integrated
+ * (transformseq.py:563-579); pass 0, -1 for all.  values[m] (float64[nnz]) and rhs[v]
+ * (float64[ndofs]) are ACCUMULATED INTO (zero them first, b2_memset_zero); this is what lets
+ * ranks of a multi-GPU run integrate element slabs into their own arrays. */
+int b2_assemble_device(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis* basis, const b2_quad* quad, const b2_geom* geom,
+                       int64_t elem_begin, int64_t elem_end,
+                       int nmat, const double* const* D_host, double* const* values_dev,
+                       int nvec, const double* const* C_host, double* const* rhs_dev);
+/* Host-buffer variant: zero-fills device scratch owned by the context, assembles, copies the
+ * results to the caller's host buffers (pinned memory from b2_host_alloc recommended). */
+int b2_assemble_host(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis* basis, const b2_quad* quad, const b2_geom* geom,
+                     int64_t elem_begin, int64_t elem_end,
+                     int nmat, const double* const* D_host, double* const* values_host,
+                     int nvec, const double* const* C_host, double* const* rhs_host);
+/* kernel selection for experiments and profiling: 0 = automatic, 1 = generic kernel only */
+int b2_ctx_set_option(b2_ctx* ctx, const char* name, int64_t value);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FEM_H */

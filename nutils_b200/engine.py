@@ -1,0 +1,258 @@
+'''Thin object layer over the C ABI: contexts, device-resident tables, assembly calls.
+
+This is the host-side glue between the Nutils-style API (topology.py, sample.py,
+function.py) and libb200fem.  It owns no numerics: tables are produced by
+bspline.py / points.py, the arithmetic happens in the CUDA kernels.
+'''
+
+import ctypes
+import weakref
+import numpy
+
+from . import _lib
+from ._lib import check, as_f64, c_vp, c_i64
+
+
+class Context:
+    '''One CUDA context wrapper per process and device (b2_ctx).'''
+
+    _instances = {}
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = c_vp()
+        check(self.lib.b2_ctx_create(int(device), ctypes.byref(h)))
+        self.handle = h
+        self.device = int(device)
+        self._finalizer = weakref.finalize(self, self.lib.b2_ctx_destroy, h)
+
+    @classmethod
+    def get(cls, device=0):
+        'shared context of a device'
+        ctx = cls._instances.get(device)
+        if ctx is None:
+            ctx = cls._instances[device] = cls(device)
+        return ctx
+
+    def check(self, status):
+        check(status, self.handle)
+
+    def synchronize(self):
+        self.check(self.lib.b2_ctx_synchronize(self.handle))
+
+    def set_stream(self, cuda_stream):
+        'run on an external stream (int handle, e.g. torch.cuda.current_stream().cuda_stream); None restores the own stream'
+        self.check(self.lib.b2_ctx_set_stream(self.handle, c_vp(cuda_stream or 0)))
+
+    def set_option(self, name, value):
+        self.check(self.lib.b2_ctx_set_option(self.handle, name.encode(), int(value)))
+
+    def timer_start(self):
+        self.check(self.lib.b2_ctx_timer_start(self.handle))
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        self.check(self.lib.b2_ctx_timer_stop(self.handle, ctypes.byref(ms)))
+        return float(ms.value)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.b2_ctx_launch_count(self.handle))
+
+    def flush_l2(self):
+        self.check(self.lib.b2_flush_l2(self.handle))
+
+    # raw memory -----------------------------------------------------------------------------------
+
+    def host_empty(self, shape, dtype=numpy.float64):
+        'pinned host array (freed when garbage collected)'
+        dtype = numpy.dtype(dtype)
+        n = int(numpy.prod(shape)) * dtype.itemsize
+        p = c_vp()
+        self.check(self.lib.b2_host_alloc(self.handle, n, ctypes.byref(p)))
+        buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
+        arr = numpy.frombuffer(buf, dtype=dtype, count=int(numpy.prod(shape))).reshape(shape)
+        weakref.finalize(buf, self.lib.b2_host_free, self.handle, p)
+        return arr
+
+    def device_alloc(self, nbytes):
+        p = c_vp()
+        self.check(self.lib.b2_device_alloc(self.handle, int(nbytes), ctypes.byref(p)))
+        return DeviceBuffer(self, p, int(nbytes))
+
+
+class DeviceBuffer:
+    'device memory owned through the C ABI (used when torch is not wanted)'
+
+    def __init__(self, ctx, ptr, nbytes):
+        self.ctx = ctx
+        self.ptr = ptr
+        self.nbytes = nbytes
+        self._finalizer = weakref.finalize(self, ctx.lib.b2_device_free, ctx.handle, ptr)
+
+    def zero(self):
+        self.ctx.check(self.ctx.lib.b2_memset_zero(self.ctx.handle, self.ptr, self.nbytes))
+
+    def to_host(self, dtype=numpy.float64, out=None):
+        dtype = numpy.dtype(dtype)
+        if out is None:
+            out = numpy.empty(self.nbytes // dtype.itemsize, dtype=dtype)
+        self.ctx.check(self.ctx.lib.b2_memcpy_d2h(self.ctx.handle, out.ctypes.data_as(c_vp), self.ptr, self.nbytes))
+        return out
+
+    def from_host(self, arr):
+        arr = numpy.ascontiguousarray(arr)
+        assert arr.nbytes == self.nbytes
+        self.ctx.check(self.ctx.lib.b2_memcpy_h2d(self.ctx.handle, self.ptr, arr.ctypes.data_as(c_vp), self.nbytes))
+
+
+def _devptr(x):
+    'device pointer of a DeviceBuffer, a torch tensor or an int'
+    if isinstance(x, DeviceBuffer):
+        return x.ptr
+    if hasattr(x, 'data_ptr'):
+        return c_vp(x.data_ptr())
+    return c_vp(int(x))
+
+
+class Plan:
+    '''Device-resident description of one structured assembly problem:
+    spline space (b2_basis) + tensor quadrature (b2_quad) + nodal geometry (b2_geom)
+    + analytic CSR pattern (b2_pattern).
+
+    bases : sequence of bspline.Basis1D, one per dimension
+    rules : sequence of (points, weights), one per dimension
+    nodes : float64[ndims, n0+1, n1+1, ...]
+    '''
+
+    def __init__(self, ctx, bases, rules, nodes, ncomp=1):
+        self.ctx = ctx
+        lib = ctx.lib
+        self.ndims = nd = len(bases)
+        self.ncomp = int(ncomp)
+        self.bases = list(bases)
+        self.rules = [(as_f64(x), as_f64(w)) for x, w in rules]
+        self.nelems = tuple(b.nelems for b in bases)
+        self.ntotal = int(numpy.prod(self.nelems))
+        nodes = as_f64(nodes)
+        if nodes.shape != (nd,) + tuple(n + 1 for n in self.nelems):
+            raise ValueError('nodes must have shape (ndims, nelems_0+1, ...), got {}'.format(nodes.shape))
+        self.nodes = nodes
+        nelems = numpy.array(self.nelems, dtype=numpy.int64)
+        degree = numpy.array([b.degree for b in bases], dtype=numpy.int32)
+        nsets = numpy.array([len(b.coeffs) for b in bases], dtype=numpy.int32)
+        ndofs = numpy.array([b.ndofs for b in bases], dtype=numpy.int64)
+        coeffs = [as_f64(b.coeffs) for b in bases]
+        setidx = [numpy.ascontiguousarray(b.setidx, dtype=numpy.int32) for b in bases]
+        start = [numpy.ascontiguousarray(b.start, dtype=numpy.int64) for b in bases]
+        if any(b.periodic for b in bases):
+            raise _lib.B200Error('unsupported configuration: periodic bases')
+        h = c_vp()
+        ctx.check(lib.b2_basis_create(ctx.handle, nd, nelems.ctypes.data_as(_lib.p_i64), degree.ctypes.data_as(_lib.p_i32), nsets.ctypes.data_as(_lib.p_i32),
+                                      _lib.ptr_array(coeffs, _lib.p_f64), _lib.ptr_array(setidx, _lib.p_i32), _lib.ptr_array(start, _lib.p_i64),
+                                      ndofs.ctypes.data_as(_lib.p_i64), self.ncomp, ctypes.byref(h)))
+        self.basis = h
+        self._fin = [weakref.finalize(self, lib.b2_basis_destroy, h)]
+        nq = numpy.array([len(x) for x, w in self.rules], dtype=numpy.int32)
+        h = c_vp()
+        ctx.check(lib.b2_quad_create_tensor(ctx.handle, nd, nq.ctypes.data_as(_lib.p_i32), _lib.ptr_array([x for x, w in self.rules], _lib.p_f64),
+                                            _lib.ptr_array([w for x, w in self.rules], _lib.p_f64), ctypes.byref(h)))
+        self.quad = h
+        self._fin.append(weakref.finalize(self, lib.b2_quad_destroy, h))
+        h = c_vp()
+        ctx.check(lib.b2_geom_create_nodal(ctx.handle, nd, nelems.ctypes.data_as(_lib.p_i64), nodes.ctypes.data_as(c_vp), ctypes.byref(h)))
+        self.geom = h
+        self._fin.append(weakref.finalize(self, lib.b2_geom_destroy, h))
+        h = c_vp()
+        ctx.check(lib.b2_pattern_create(ctx.handle, self.basis, ctypes.byref(h)))
+        self.pattern = h
+        self._fin.append(weakref.finalize(self, lib.b2_pattern_destroy, h))
+        self.nnz = int(lib.b2_pattern_nnz(h))
+        self.ndofs = int(lib.b2_pattern_nrows(h))
+        self._csr = None
+
+    # pattern --------------------------------------------------------------------------------------
+
+    def csr_pattern(self):
+        '(rowptr int64[ndofs+1], colidx int64[nnz]) on the host, cached'
+        if self._csr is None:
+            rowptr = numpy.empty(self.ndofs + 1, dtype=numpy.int64)
+            colidx = numpy.empty(self.nnz, dtype=numpy.int64)
+            self.ctx.check(self.ctx.lib.b2_pattern_export_host(self.pattern, rowptr.ctypes.data_as(c_vp), colidx.ctypes.data_as(c_vp)))
+            self._csr = rowptr, colidx
+        return self._csr
+
+    def csr_pattern_device(self, rowptr_dev, colidx_dev):
+        self.ctx.check(self.ctx.lib.b2_pattern_export_device(self.pattern, _devptr(rowptr_dev), _devptr(colidx_dev)))
+
+    def update_nodes(self, nodes):
+        nodes = as_f64(nodes)
+        assert nodes.shape == self.nodes.shape
+        self.nodes = nodes
+        self.ctx.check(self.ctx.lib.b2_geom_update_nodal(self.geom, nodes.ctypes.data_as(c_vp)))
+
+    # assembly -------------------------------------------------------------------------------------
+
+    def _form_args(self, Ds, Cs):
+        na = self.ndims + 1
+        nc = self.ncomp
+        Ds = [as_f64(D).reshape(nc, na, nc, na) for D in Ds]
+        Cs = [as_f64(C).reshape(nc, na) for C in Cs]
+        return Ds, Cs, _lib.ptr_array(Ds, _lib.p_f64), _lib.ptr_array(Cs, _lib.p_f64)
+
+    def assemble_host(self, Ds=(), Cs=(), elem_range=None, out_values=None, out_rhs=None):
+        '''Assemble into host arrays through b2_assemble_host: returns ([values...], [rhs...]).'''
+        Ds, Cs, pD, pC = self._form_args(Ds, Cs)
+        vals = out_values if out_values is not None else [numpy.empty(self.nnz) for _ in Ds]
+        rhs = out_rhs if out_rhs is not None else [numpy.empty(self.ndofs) for _ in Cs]
+        e0, e1 = elem_range if elem_range is not None else (0, -1)
+        pv = (c_vp * max(len(vals), 1))(*[v.ctypes.data_as(c_vp) for v in vals])
+        pr = (c_vp * max(len(rhs), 1))(*[r.ctypes.data_as(c_vp) for r in rhs])
+        self.ctx.check(self.ctx.lib.b2_assemble_host(self.ctx.handle, self.pattern, self.basis, self.quad, self.geom, c_i64(e0), c_i64(e1),
+                                                     len(Ds), pD, pv, len(Cs), pC, pr))
+        return vals, rhs
+
+    def assemble_device(self, Ds=(), Cs=(), values=(), rhs=(), elem_range=None):
+        '''Accumulate into device arrays (DeviceBuffer / torch tensors / raw pointers); asynchronous on the context stream.'''
+        Ds, Cs, pD, pC = self._form_args(Ds, Cs)
+        assert len(values) == len(Ds) and len(rhs) == len(Cs)
+        e0, e1 = elem_range if elem_range is not None else (0, -1)
+        pv = (c_vp * max(len(values), 1))(*[_devptr(v) for v in values])
+        pr = (c_vp * max(len(rhs), 1))(*[_devptr(r) for r in rhs])
+        self.ctx.check(self.ctx.lib.b2_assemble_device(self.ctx.handle, self.pattern, self.basis, self.quad, self.geom, c_i64(e0), c_i64(e1),
+                                                       len(Ds), pD, pv, len(Cs), pC, pr))
+
+
+# ---- coefficient tensors of the north-star forms -------------------------------------------------------
+
+def form_mass(ndims, ncomp=1):
+    'D for int N_i N_j (per component)'
+    D = numpy.zeros((ncomp, ndims + 1, ncomp, ndims + 1))
+    for c in range(ncomp):
+        D[c, 0, c, 0] = 1.
+    return D
+
+
+def form_stiffness(ndims, ncomp=1, conductivity=None):
+    'D for int grad N_i . K grad N_j (K = identity by default)'
+    K = numpy.eye(ndims) if conductivity is None else numpy.asarray(conductivity, dtype=float)
+    D = numpy.zeros((ncomp, ndims + 1, ncomp, ndims + 1))
+    for c in range(ncomp):
+        D[c, 1:, c, 1:] = K
+    return D
+
+
+def form_elasticity(ndims, lmbda, mu, scale=1.):
+    '''D for scale * int eps(v):sigma(u), sigma = lmbda tr(eps) I + 2 mu eps:
+    D[c,1+k,e,1+l] = scale (lmbda d_ck d_el + mu (d_ce d_kl + d_cl d_ek)).'''
+    eye = numpy.eye(ndims)
+    D = numpy.zeros((ndims, ndims + 1, ndims, ndims + 1))
+    D[:, 1:, :, 1:] = scale * (lmbda * numpy.einsum('ck,el->ckel', eye, eye) + mu * (numpy.einsum('ce,kl->ckel', eye, eye) + numpy.einsum('cl,ek->ckel', eye, eye)))
+    return D
+
+
+def form_load(ndims, ncomp=1, f=None):
+    'C for int f_c N_i (f = ones by default)'
+    C = numpy.zeros((ncomp, ndims + 1))
+    C[:, 0] = 1. if f is None else numpy.asarray(f, dtype=float)
+    return C
