@@ -65,6 +65,10 @@ int b2_ctx_timer_start(b2_ctx* ctx);
 int b2_ctx_timer_stop(b2_ctx* ctx, float* milliseconds);
 /* number of kernels launched by this context since creation */
 int64_t b2_ctx_launch_count(const b2_ctx* ctx);
+/* per-kernel device time: after b2_ctx_set_option(ctx, "time_kernels", 1) every assembly kernel launch is
+ * bracketed by CUDA events on the context's stream; this call synchronises, returns the summed duration and
+ * the number of launches since the last call, and resets both (bench.py: roofline.achieved) */
+int b2_ctx_kernel_time(b2_ctx* ctx, double* milliseconds, int64_t* launches);
 /* pinned host memory for the end-to-end path */
 int b2_host_alloc(b2_ctx* ctx, int64_t nbytes, void** out_host);
 int b2_host_free(b2_ctx* ctx, void* host);
@@ -119,6 +123,9 @@ int b2_pattern_create(b2_ctx* ctx, const b2_basis* basis, b2_pattern** out);
 int b2_pattern_destroy(b2_pattern* pattern);
 int64_t b2_pattern_nnz(const b2_pattern* pattern);
 int64_t b2_pattern_nrows(const b2_pattern* pattern);
+/* offset of the first stored entry of `row` (0 <= row <= nrows), i.e. rowptr[row], computed analytically on the
+ * host; lets a rank of a multi-GPU run allocate only its window of rows (see b2_assemble_device) */
+int64_t b2_pattern_row_offset(const b2_pattern* pattern, int64_t row);
 /* rowptr int64[nrows+1], colidx int64[nnz]; bit-equal to function.as_csr of the reference */
 int b2_pattern_export_host(b2_pattern* pattern, int64_t* rowptr_host, int64_t* colidx_host);
 int b2_pattern_export_device(b2_pattern* pattern, int64_t* rowptr_dev, int64_t* colidx_dev);
@@ -140,7 +147,9 @@ int b2_pattern_export_device(b2_pattern* pattern, int64_t* rowptr_dev, int64_t* 
  * Elements [elem_begin, elem_end) of the C-order element numbering are integrated
  * (transformseq.py:563-579); pass 0, -1 for all.  values[m] (float64[nnz]) and rhs[v]
  * (float64[ndofs]) are ACCUMULATED INTO (zero them first, b2_memset_zero); this is what lets
- * ranks of a multi-GPU run integrate element slabs into their own arrays. */
+ * ranks of a multi-GPU run integrate element slabs into their own arrays.  A rank that stores only the
+ * rows [r0, r1) its slab touches passes values_dev[m] = window - b2_pattern_row_offset(pattern, r0) and
+ * rhs_dev[v] = window - r0 (in elements): only addresses inside the window are accessed. */
 int b2_assemble_device(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis* basis, const b2_quad* quad, const b2_geom* geom,
                        int64_t elem_begin, int64_t elem_end,
                        int nmat, const double* const* D_host, double* const* values_dev,

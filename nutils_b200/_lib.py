@@ -47,6 +47,8 @@ SIGNATURES = {
     'b2_ctx_timer_start': (ctypes.c_int, [c_vp]),
     'b2_ctx_timer_stop': (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float)]),
     'b2_ctx_launch_count': (c_i64, [c_vp]),
+    'b2_ctx_kernel_time': (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_double), p_i64]),
+    'b2_pattern_row_offset': (c_i64, [c_vp, c_i64]),
     'b2_ctx_set_option': (ctypes.c_int, [c_vp, ctypes.c_char_p, c_i64]),
     'b2_host_alloc': (ctypes.c_int, [c_vp, c_i64, p_vp]),
     'b2_host_free': (ctypes.c_int, [c_vp, c_vp]),

@@ -86,6 +86,8 @@ extern "C" int b2_ctx_destroy(b2_ctx* ctx) {
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->formbuf) cudaFree(ctx->formbuf);
+  for (auto* v : {&ctx->kernel_events, &ctx->event_pool})
+    for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->own_stream);
@@ -121,6 +123,43 @@ extern "C" int b2_ctx_timer_stop(b2_ctx* ctx, float* ms) {
 }
 
 extern "C" int64_t b2_ctx_launch_count(const b2_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+KernelTimer::KernelTimer(b2_ctx* c) : ctx(c) {
+  auto it = ctx->opts.find("time_kernels");
+  if (it == ctx->opts.end() || !it->second) return;
+  if (!ctx->event_pool.empty()) {
+    e0 = ctx->event_pool.back().first;
+    e1 = ctx->event_pool.back().second;
+    ctx->event_pool.pop_back();
+  } else if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+    cudaGetLastError();
+    e0 = e1 = nullptr;
+    return;
+  }
+  cudaEventRecord(e0, ctx->stream);
+}
+
+KernelTimer::~KernelTimer() {
+  if (!e0) return;
+  cudaEventRecord(e1, ctx->stream);
+  ctx->kernel_events.emplace_back(e0, e1);
+}
+
+extern "C" int b2_ctx_kernel_time(b2_ctx* ctx, double* ms, int64_t* launches) {
+  if (!ctx || !ms || !launches) return B2_EINVAL;
+  B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  double total = 0.;
+  for (auto& ev : ctx->kernel_events) {
+    float t = 0.f;
+    B2_CUDA(ctx, cudaEventElapsedTime(&t, ev.first, ev.second));
+    total += t;
+  }
+  *ms = total;
+  *launches = (int64_t)ctx->kernel_events.size();
+  ctx->event_pool.insert(ctx->event_pool.end(), ctx->kernel_events.begin(), ctx->kernel_events.end());
+  ctx->kernel_events.clear();
+  return B2_OK;
+}
 
 extern "C" int b2_ctx_set_option(b2_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return B2_EINVAL;
@@ -415,6 +454,23 @@ extern "C" int b2_pattern_destroy(b2_pattern* p) {
 
 extern "C" int64_t b2_pattern_nnz(const b2_pattern* p) { return p ? p->nnz : 0; }
 extern "C" int64_t b2_pattern_nrows(const b2_pattern* p) { return p ? p->nrows : 0; }
+
+extern "C" int64_t b2_pattern_row_offset(const b2_pattern* p, int64_t row) {
+  if (!p || row < 0 || row > p->nrows) return -1;
+  if (row == p->nrows) return p->nnz;
+  const b2_basis* b = p->basis;
+  const int nc = b->ncomp;
+  int64_t I = row / nc;
+  const int c = (int)(row % nc);
+  int i[B2_MAXD] = {0, 0, 0};
+  for (int d = b->ndims - 1; d >= 0; d--) { i[d] = (int)(I % b->ndofs_d[d]); I /= b->ndofs_d[d]; }
+  long long r = b->cum[0][i[0]], w = b->wid[0][i[0]];
+  for (int d = 1; d < b->ndims; d++) {
+    r = r * b->W[d] + w * b->cum[d][i[d]];
+    w *= b->wid[d][i[d]];
+  }
+  return (r * nc + (long long)c * w) * nc;
+}
 
 extern "C" int b2_pattern_export_device(b2_pattern* p, int64_t* rowptr_dev, int64_t* colidx_dev) {
   if (!p || !rowptr_dev || !colidx_dev) return B2_EINVAL;

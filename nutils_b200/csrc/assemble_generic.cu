@@ -322,7 +322,10 @@ int launch_dim(b2_ctx* ctx, GenericParams& P) {
   per_sm = std::max(per_sm, 1);
   const long long nel = P.elem_end - P.elem_begin;
   const int blocks = (int)std::min<long long>(nel, (long long)ctx->sm_count * per_sm * 4);
-  k_assemble_generic<DIM><<<blocks, threads, smem, ctx->stream>>>(P);
+  {
+    KernelTimer timer(ctx);
+    k_assemble_generic<DIM><<<blocks, threads, smem, ctx->stream>>>(P);
+  }
   ctx->launches++;
   B2_CUDA(ctx, cudaGetLastError());
   return B2_OK;

@@ -6,6 +6,7 @@
 
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200fem.h"
@@ -76,6 +77,17 @@ struct b2_ctx {
   void* formbuf = nullptr;
   size_t formbuf_bytes = 0;
   int64_t serial = 0;
+  // optional per-kernel timing (option "time_kernels")
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
+};
+
+// brackets one kernel launch with events when the context option "time_kernels" is set
+struct KernelTimer {
+  b2_ctx* ctx;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  explicit KernelTimer(b2_ctx* c);
+  ~KernelTimer();
 };
 
 struct TabDev {

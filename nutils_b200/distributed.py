@@ -1,0 +1,85 @@
+'''Multi-GPU assembly: element slabs per rank, one neighbour exchange on the shared dof rows.
+
+The reference's only parallelism is a fork-parallel element loop with shared-memory outputs
+(src/nutils/parallel.py:27-154).  Here elements are partitioned into contiguous slabs along the
+slowest element index (C-order numbering, transformseq.py:563-579); a rank integrates its slab
+into a window of the GLOBAL CSR -- the rows its elements touch -- and adjacent ranks then exchange
+and add the `p` dof planes they share (one batched NCCL send/recv over NVLink; gloo in the CPU
+tests).  No other collective is on the data path.
+
+``torch.distributed`` is plumbing: process group, send/recv.
+'''
+
+import numpy
+
+
+def slab_ranges(n0, world):
+    'balanced contiguous ranges of the slowest element index'
+    cuts = [(n0 * r) // world for r in range(world + 1)]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+class SlabLayout:
+    '''Index arithmetic of one rank's slab.
+
+    bases1d    : per-dimension bspline.Basis1D of the GLOBAL space
+    ncomp      : components per basis function
+    row_offset : callable row -> rowptr[row] of the global pattern (engine.Plan.row_offset on the GPU path)
+    '''
+
+    def __init__(self, bases1d, ncomp, rank, world, row_offset):
+        b0 = bases1d[0]
+        p = b0.degree
+        self.rank, self.world = rank, world
+        ranges = slab_ranges(b0.nelems, world)
+        if any(e1 <= e0 for e0, e1 in ranges):
+            raise ValueError('more ranks than element layers')
+        nrest_e = int(numpy.prod([b.nelems for b in bases1d[1:]]))
+        nrest_d = int(numpy.prod([b.ndofs for b in bases1d[1:]])) * ncomp  # dof rows per plane of dimension 0
+        e0, e1 = ranges[rank]
+        self.elem_range = e0 * nrest_e, e1 * nrest_e
+        planes = [(int(b0.start[a]), int(b0.start[b - 1]) + p + 1) for a, b in ranges]
+        lo, hi = planes[rank]
+        self.row_lo, self.row_hi = lo * nrest_d, hi * nrest_d
+        self.off_lo, self.off_hi = row_offset(self.row_lo), row_offset(self.row_hi)
+        self.nvalues = self.off_hi - self.off_lo
+        self.nrows = self.row_hi - self.row_lo
+        # shared planes with the neighbours: [planes[r+1].lo, planes[r].hi)
+        self.neighbours = []  # (peer, value slice, row slice) in window coordinates
+        for peer in (rank - 1, rank + 1):
+            if not 0 <= peer < world:
+                continue
+            a = max(planes[rank][0], planes[peer][0])
+            b = min(planes[rank][1], planes[peer][1])
+            if b <= a:
+                continue
+            r0, r1 = a * nrest_d, b * nrest_d
+            self.neighbours.append((peer, slice(row_offset(r0) - self.off_lo, row_offset(r1) - self.off_lo), slice(r0 - self.row_lo, r1 - self.row_lo)))
+        if world > 2 and any(planes[r][1] > planes[r + 2][0] for r in range(world - 2)):
+            raise ValueError('slabs thinner than the basis support: a dof plane would be shared by three ranks')
+        # rows this rank owns after the exchange (lower rank owns the shared planes)
+        own_hi = planes[rank + 1][0] if rank + 1 < world else hi
+        self.own_rows = slice(0, (min(own_hi, hi) - lo) * nrest_d) if rank + 1 < world else slice(0, self.nrows)
+
+
+def exchange_interfaces(layout, matrices, vectors, group=None):
+    '''Add the neighbours' contributions on the shared rows, in place.
+
+    matrices / vectors: torch tensors holding this rank's window of the values / rhs arrays.
+    One batch of point-to-point operations; both sides end up with the complete rows.'''
+    import torch
+    import torch.distributed as dist
+    if not layout.neighbours:
+        return
+    ops, pending = [], []
+    for peer, vs, rs in layout.neighbours:
+        for t, sl in [(m, vs) for m in matrices] + [(v, rs) for v in vectors]:
+            send = t[sl]
+            recv = torch.empty_like(send)
+            ops.append(dist.P2POp(dist.isend, send, peer, group=group))
+            ops.append(dist.P2POp(dist.irecv, recv, peer, group=group))
+            pending.append((t, sl, recv))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    for t, sl, recv in pending:
+        t[sl] += recv

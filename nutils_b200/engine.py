@@ -42,7 +42,13 @@ class Context:
 
     def set_stream(self, cuda_stream):
         'run on an external stream (int handle, e.g. torch.cuda.current_stream().cuda_stream); None restores the own stream'
-        self.check(self.lib.b2_ctx_set_stream(self.handle, c_vp(cuda_stream or 0)))
+        if cuda_stream is None:
+            handle = 0           # the context's own stream
+        elif int(cuda_stream) == 0:
+            handle = 1           # cudaStreamLegacy: the default stream torch hands out as 0
+        else:
+            handle = int(cuda_stream)
+        self.check(self.lib.b2_ctx_set_stream(self.handle, c_vp(handle)))
 
     def set_option(self, name, value):
         self.check(self.lib.b2_ctx_set_option(self.handle, name.encode(), int(value)))
@@ -54,6 +60,13 @@ class Context:
         ms = ctypes.c_float()
         self.check(self.lib.b2_ctx_timer_stop(self.handle, ctypes.byref(ms)))
         return float(ms.value)
+
+    def kernel_time(self):
+        '(summed device milliseconds, launches) of the assembly kernels since the last call; needs set_option("time_kernels", 1)'
+        ms = ctypes.c_double()
+        n = ctypes.c_int64()
+        self.check(self.lib.b2_ctx_kernel_time(self.handle, ctypes.byref(ms), ctypes.byref(n)))
+        return float(ms.value), int(n.value)
 
     @property
     def launch_count(self):
@@ -184,6 +197,13 @@ class Plan:
 
     def csr_pattern_device(self, rowptr_dev, colidx_dev):
         self.ctx.check(self.ctx.lib.b2_pattern_export_device(self.pattern, _devptr(rowptr_dev), _devptr(colidx_dev)))
+
+    def row_offset(self, row):
+        'rowptr[row], computed analytically on the host'
+        off = int(self.ctx.lib.b2_pattern_row_offset(self.pattern, int(row)))
+        if off < 0:
+            raise ValueError('row out of range')
+        return off
 
     def update_nodes(self, nodes):
         nodes = as_f64(nodes)
