@@ -252,6 +252,7 @@ BasisView b2_basis::view() const {
     v.wid[d] = d_wid[d];
     v.cum[d] = d_cum[d];
     v.W[d] = W[d];
+    v.nsets[d] = nsets[d];
     v.nb *= p[d] + 1;
   }
   return v;

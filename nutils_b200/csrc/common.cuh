@@ -29,6 +29,7 @@ struct BasisView {
   const int* cum[B2_MAXD];     // [ndofs+1] exclusive prefix sum of wid
   long long W[B2_MAXD];        // sum of wid over the dimension
   int nb;                      // prod (p+1): basis functions per element
+  int nsets[B2_MAXD];          // number of coefficient sets per dimension
 };
 
 struct QuadView {
