@@ -154,13 +154,27 @@ int b2_assemble_device(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis* b
                        int64_t elem_begin, int64_t elem_end,
                        int nmat, const double* const* D_host, double* const* values_dev,
                        int nvec, const double* const* C_host, double* const* rhs_dev);
+/* Owner-computes variant of the same integrals: every stored CSR value (and load-vector entry) of the dof rows whose
+ * index along dimension 0 lies in [plane_begin, plane_end) is WRITTEN exactly once -- the sum over the elements in
+ * the common support of N_i and N_j, which the reference forms after its loop by argsort/unique/accumulate
+ * (src/nutils/evaluable.py:588-616, 5646-5682; numeric.py:434-460), is folded into the integration itself.  No
+ * zero-fill is needed and rows outside the planes are not touched, so the ranks of a multi-GPU run that own disjoint
+ * plane ranges need NO exchange step (each integrates the <= degree element layers below its first plane again).
+ * Pass 0, -1 for all planes.  values_dev / rhs_dev follow the windowing convention of b2_assemble_device. */
+int b2_assemble_rows_device(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis* basis, const b2_quad* quad, const b2_geom* geom,
+                            int64_t plane_begin, int64_t plane_end,
+                            int nmat, const double* const* D_host, double* const* values_dev,
+                            int nvec, const double* const* C_host, double* const* rhs_dev);
 /* Host-buffer variant: zero-fills device scratch owned by the context, assembles, copies the
  * results to the caller's host buffers (pinned memory from b2_host_alloc recommended). */
 int b2_assemble_host(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis* basis, const b2_quad* quad, const b2_geom* geom,
                      int64_t elem_begin, int64_t elem_end,
                      int nmat, const double* const* D_host, double* const* values_host,
                      int nvec, const double* const* C_host, double* const* rhs_host);
-/* kernel selection for experiments and profiling: 0 = automatic, 1 = generic kernel only */
+/* Experiments and profiling.  "kernel": 0 = automatic, 1 = generic (coverage) kernel only, 2 = specialised kernel or
+ * B2_EUNSUPPORTED.  "path": 0 = b2_assemble_host uses the owner-computes rows path for the whole topology, 1 = always
+ * the element-scatter path.  "rows_nseg": force the number of marching segments of the rows kernel (0 = automatic).
+ * "time_kernels": see b2_ctx_kernel_time. */
 int b2_ctx_set_option(b2_ctx* ctx, const char* name, int64_t value);
 
 #if defined(__GNUC__)

@@ -73,6 +73,7 @@ SIGNATURES = {
     'b2_pattern_export_host': (ctypes.c_int, [c_vp, c_vp, c_vp]),
     'b2_pattern_export_device': (ctypes.c_int, [c_vp, c_vp, c_vp]),
     'b2_assemble_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
+    'b2_assemble_rows_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
     'b2_assemble_host': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
 }
 

@@ -530,9 +530,11 @@ static int get_tabs(b2_ctx* ctx, const b2_basis* cb, const b2_quad* q, TabDev* o
   return B2_OK;
 }
 
+// rows == false: integrate elements [elem_begin, elem_end) and ACCUMULATE into the outputs.
+// rows == true:  elem_begin/elem_end are dof planes of dimension 0; every stored value of those planes is WRITTEN.
 static int assemble_impl(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis* basis, const b2_quad* quad, const b2_geom* geom,
                          int64_t elem_begin, int64_t elem_end, int nmat, const double* const* D_host, double* const* values_dev,
-                         int nvec, const double* const* C_host, double* const* rhs_dev) {
+                         int nvec, const double* const* C_host, double* const* rhs_dev, bool rows = false) {
   if (!ctx || !pattern || !basis || !quad || !geom) return b2_fail(ctx, B2_EINVAL, "null argument");
   if (nmat < 0 || nmat > B2_MAX_FORMS || nvec < 0 || nvec > B2_MAX_FORMS) return b2_fail(ctx, B2_EINVAL, "0..4 matrix and vector forms per call");
   if ((nmat && (!D_host || !values_dev)) || (nvec && (!C_host || !rhs_dev))) return b2_fail(ctx, B2_EINVAL, "null form argument");
@@ -543,9 +545,25 @@ static int assemble_impl(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis*
     if (geom->nel[d] != basis->nel[d]) return b2_fail(ctx, B2_EINVAL, "geometry and basis live on different topologies");
     ntot *= basis->nel[d];
   }
-  if (elem_end < 0) elem_end = ntot;
-  if (elem_begin < 0 || elem_begin > elem_end || elem_end > ntot) return b2_fail(ctx, B2_EINVAL, "invalid element range");
-  if (elem_begin == elem_end || (nmat == 0 && nvec == 0)) return B2_OK;
+  int64_t plane_begin = 0, plane_end = basis->ndofs_d[0];
+  if (rows) {
+    plane_begin = elem_begin;
+    plane_end = elem_end < 0 ? basis->ndofs_d[0] : elem_end;
+    if (plane_begin < 0 || plane_begin > plane_end || plane_end > basis->ndofs_d[0]) return b2_fail(ctx, B2_EINVAL, "invalid dof-plane range");
+    if (plane_begin == plane_end || (nmat == 0 && nvec == 0)) return B2_OK;
+    // elements of dimension 0 whose dofs touch the planes (start is non-decreasing)
+    int64_t e_lo = basis->nel[0], e_hi = -1;
+    for (int64_t e = 0; e < basis->nel[0]; e++)
+      if (basis->start[0][e] < plane_end && basis->start[0][e] + basis->p[0] >= plane_begin) { e_lo = std::min(e_lo, e); e_hi = std::max(e_hi, e); }
+    const int64_t per_layer = ntot / basis->nel[0];
+    elem_begin = e_lo * per_layer;
+    elem_end = (e_hi + 1) * per_layer;
+    if (e_hi < e_lo) elem_begin = elem_end = 0;
+  } else {
+    if (elem_end < 0) elem_end = ntot;
+    if (elem_begin < 0 || elem_begin > elem_end || elem_end > ntot) return b2_fail(ctx, B2_EINVAL, "invalid element range");
+    if (elem_begin == elem_end || (nmat == 0 && nvec == 0)) return B2_OK;
+  }
   B2_CUDA(ctx, cudaSetDevice(ctx->device));
 
   const int nd = basis->ndims, nc = basis->ncomp, na = nd + 1;
@@ -625,18 +643,38 @@ static int assemble_impl(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis*
   for (int v = 0; v < nvec; v++) F.rhs[v] = rhs_dev[v];
 
   const int64_t kernel_opt = ctx->opts.count("kernel") ? ctx->opts["kernel"] : 0;
+  if (rows) {
+    if (kernel_opt != 1) {
+      rc = launch_assemble_rows(ctx, basis, B, Q, G, F, D_host, C_host, plane_begin, plane_end);
+      if (rc != B2_EUNSUPPORTED) return rc;
+      if (kernel_opt >= 2) return b2_fail(ctx, B2_EUNSUPPORTED, "requested specialised kernel does not cover this configuration");
+    }
+    // coverage path: zero the planes' slots, then scatter only the rows inside the planes
+    const int64_t nb_plane = basis->nbasis / basis->ndofs_d[0] * nc;
+    const int64_t s0 = b2_pattern_row_offset(pattern, plane_begin * nb_plane), s1 = b2_pattern_row_offset(pattern, plane_end * nb_plane);
+    for (int m = 0; m < nmat; m++) B2_CUDA(ctx, cudaMemsetAsync(values_dev[m] + s0, 0, sizeof(double) * (size_t)(s1 - s0), ctx->stream));
+    for (int v = 0; v < nvec; v++) B2_CUDA(ctx, cudaMemsetAsync(rhs_dev[v] + plane_begin * nb_plane, 0, sizeof(double) * (size_t)((plane_end - plane_begin) * nb_plane), ctx->stream));
+    if (elem_begin == elem_end) return B2_OK;
+    return launch_assemble_generic(ctx, B, Q, G, F, elem_begin, elem_end, (int)plane_begin, (int)plane_end);
+  }
   if (kernel_opt != 1) {
     rc = launch_assemble_fast(ctx, B, Q, G, F, D_host, C_host, elem_begin, elem_end);
     if (rc != B2_EUNSUPPORTED) return rc;
     if (kernel_opt >= 2) return b2_fail(ctx, B2_EUNSUPPORTED, "requested specialised kernel does not cover this configuration");
   }
-  return launch_assemble_generic(ctx, B, Q, G, F, elem_begin, elem_end);
+  return launch_assemble_generic(ctx, B, Q, G, F, elem_begin, elem_end, 0, 0x7fffffff);
 }
 
 extern "C" int b2_assemble_device(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis* basis, const b2_quad* quad, const b2_geom* geom,
                                   int64_t elem_begin, int64_t elem_end, int nmat, const double* const* D_host, double* const* values_dev,
                                   int nvec, const double* const* C_host, double* const* rhs_dev) {
   return assemble_impl(ctx, pattern, basis, quad, geom, elem_begin, elem_end, nmat, D_host, values_dev, nvec, C_host, rhs_dev);
+}
+
+extern "C" int b2_assemble_rows_device(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis* basis, const b2_quad* quad, const b2_geom* geom,
+                                       int64_t plane_begin, int64_t plane_end, int nmat, const double* const* D_host, double* const* values_dev,
+                                       int nvec, const double* const* C_host, double* const* rhs_dev) {
+  return assemble_impl(ctx, pattern, basis, quad, geom, plane_begin, plane_end, nmat, D_host, values_dev, nvec, C_host, rhs_dev, true);
 }
 
 extern "C" int b2_assemble_host(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis* basis, const b2_quad* quad, const b2_geom* geom,
@@ -655,13 +693,19 @@ extern "C" int b2_assemble_host(b2_ctx* ctx, const b2_pattern* pattern, const b2
     B2_CUDA(ctx, cudaMalloc(&ctx->scratch, need));
     ctx->scratch_bytes = need;
   }
-  B2_CUDA(ctx, cudaMemsetAsync(ctx->scratch, 0, need, ctx->stream));
+  int64_t ntot = 1;
+  if (basis) for (int d = 0; d < basis->ndims; d++) ntot *= basis->nel[d];
+  // option "path" = 1 forces the element-scatter (accumulate) kernels also for the whole topology
+  const bool whole = basis && elem_begin == 0 && (elem_end < 0 || elem_end == ntot) && !(ctx->opts.count("path") && ctx->opts["path"] == 1);
+  if (!whole) B2_CUDA(ctx, cudaMemsetAsync(ctx->scratch, 0, need, ctx->stream));
   double* vals[B2_MAX_FORMS];
   double* rhs[B2_MAX_FORMS];
   unsigned char* base = (unsigned char*)ctx->scratch;
   for (int m = 0; m < nmat; m++) vals[m] = (double*)(base + bm * m);
   for (int v = 0; v < nvec; v++) rhs[v] = (double*)(base + bm * nmat + bv * v);
-  int rc = assemble_impl(ctx, pattern, pattern->basis == nullptr ? nullptr : basis, quad, geom, elem_begin, elem_end, nmat, D_host, vals, nvec, C_host, rhs);
+  // the whole topology: owner-computes rows (every value written once, no zero fill); a slab: accumulate
+  int rc = whole ? assemble_impl(ctx, pattern, basis, quad, geom, 0, -1, nmat, D_host, vals, nvec, C_host, rhs, true)
+                 : assemble_impl(ctx, pattern, basis, quad, geom, elem_begin, elem_end, nmat, D_host, vals, nvec, C_host, rhs);
   if (rc != B2_OK) return rc;
   for (int m = 0; m < nmat; m++) {
     if (!values_host[m]) return b2_fail(ctx, B2_EINVAL, "null output buffer");

@@ -30,6 +30,7 @@ struct GenericParams {
   GeomView G;
   FormView F;
   long long elem_begin, elem_end;
+  int plane_lo, plane_hi;  // only rows whose dimension-0 dof index lies in [plane_lo, plane_hi) are scattered
   int qchunk;   // quadrature points per chunk
   int pm1;      // max(p)+1
   int nqm;      // max(nq)
@@ -285,9 +286,11 @@ __global__ void __launch_bounds__(512) k_assemble_generic(const GenericParams P)
           }
           const long long w = (long long)wa[0] * wa[1] * wa[2];
           const long long slot = (sR[a] * nc + (long long)ci * w) * nc + pos * nc + cj;
+          if (sI[a * DIM] >= P.plane_lo && sI[a * DIM] < P.plane_hi) {
 #pragma unroll
-          for (int m = 0; m < B2_MAX_FORMS; m++)
-            if (m < P.F.nmat) atomicAdd(P.F.values[m] + slot, acc[m][e]);
+            for (int m = 0; m < B2_MAX_FORMS; m++)
+              if (m < P.F.nmat) atomicAdd(P.F.values[m] + slot, acc[m][e]);
+          }
         }
       }
     }
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(512) k_assemble_generic(const GenericParams P)
       const int a = r / nc, ci = r % nc;
       long long I = 0;
       for (int d = 0; d < DIM; d++) I = I * B.ndofs[d] + sI[a * DIM + d];
-      atomicAdd(P.F.rhs[v] + I * nc + ci, sV[t]);
+      if (sI[a * DIM] >= P.plane_lo && sI[a * DIM] < P.plane_hi) atomicAdd(P.F.rhs[v] + I * nc + ci, sV[t]);
     }
   }
 }
@@ -334,7 +337,7 @@ int launch_dim(b2_ctx* ctx, GenericParams& P) {
 }  // namespace
 
 int launch_assemble_generic(b2_ctx* ctx, const BasisView& B, const QuadView& Q, const GeomView& G, const FormView& F,
-                            long long elem_begin, long long elem_end) {
+                            long long elem_begin, long long elem_end, int plane_lo, int plane_hi) {
   GenericParams P;
   P.B = B;
   P.Q = Q;
@@ -342,6 +345,8 @@ int launch_assemble_generic(b2_ctx* ctx, const BasisView& B, const QuadView& Q, 
   P.F = F;
   P.elem_begin = elem_begin;
   P.elem_end = elem_end;
+  P.plane_lo = plane_lo;
+  P.plane_hi = plane_hi;
   P.pm1 = 1;
   P.nqm = 1;
   for (int d = 0; d < B.ndims; d++) {

@@ -1,0 +1,542 @@
+// Owner-computes ("row-sum") integration kernel for scalar forms on 3-D maximal-smoothness
+// tensor-product splines: every stored CSR value is produced by exactly ONE thread and written
+// once with a plain store -- no atomics, no zero-fill, no cross-GPU exchange.
+//
+// What it replaces in the reference: the whole generated element loop (SURVEY.md appendix A;
+// src/nutils/evaluable.py:6773-6787) PLUS the post-loop argsort/unique/accumulate that sums the
+// element blocks into CSR values (evaluable.py:588-616, 5646-5682; numeric.py:434-460).  Instead of
+// forming 27x27 element blocks and scattering them (1.5 G scatter-adds per matrix at 128^3, which
+// is what bounds assemble_fast.cu: the LSU retires ~280 G fp64 RED/s chip-wide), the sum over the
+// elements in supp(N_i) n supp(N_j) is folded into a GLOBAL sum factorisation:
+//
+//   A[i,j] = sum_{Q0} W0[i0,j0](Q0) sum_{Q1} W1[i1,j1](Q1) sum_{Q2} W2[i2,j2](Q2) Ghat(Q0,Q1,Q2)
+//
+// with Q_d running over the quadrature points of ALL elements in the common support along d.
+//
+// Mapping.  A CTA owns a tile of T1 x T2 dofs in dimensions 1 and 2 and MARCHES along dimension 0
+// over the element layers e0 that support its dof planes [r0, r1).  Per layer and chunk of QC
+// points q0 it runs four barrier-separated stages through shared memory:
+//   G   geometry at the halo points (T1+P)(P+1) x (T2+P)(P+1): trilinear J, adj(J), det ->
+//       Ghat = w/|det| adj Kc adj^T (6 values) and w|det|                        [~115 flop/pt]
+//   S1  contract Q2: lanes = (q0, Q1), warp-uniform i2 -> T1[Q1][9 terms][q0][pair2]
+//   S2  contract Q1: lanes = (q0, pair2), warp-uniform i1 -> T2[q0][5 groups][pair1 x pair2]
+//   S3  contract q0 into register accumulators acc[(P+1)^2] per dof pair and matrix.
+// After a layer the entries with min(a0,b0)=0 are complete (dof e0 has no further support) and are
+// stored; the other P^2 are carried into the next layer (register shift).  Flop count ~10 kFMA per
+// element-equivalent for K+M at p=2 versus ~20 k for the per-element sum factorisation; the bound
+// is the FP64 pipe (64 DFMA/clk/SM), then shared-memory bandwidth -- see DESIGN.md.
+//
+// Dimension names inside this file: 0 = marching (slowest dof index), 1, 2 = tile dimensions.
+
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+struct RowParams {
+  BasisView B;
+  QuadView Q;
+  GeomView G;
+  int plane_begin, plane_end;  // dof planes of dimension 0 written by this launch
+  int nseg, tiles1, tiles2;
+  int has_f, iso;
+  double kc[6];  // symmetric conductivity (00,01,02,11,12,22)
+  double rho, vcoef;
+  double* valK;
+  double* valM;
+  double* rhs;
+};
+
+template <int P_, int T1_, int T2_, int QC_, int NT_>
+struct RCfg {
+  static constexpr int P = P_, NB = P + 1, NQ = P + 1, WD = 2 * P + 1;
+  static constexpr int T1 = T1_, T2 = T2_, QC = QC_, NT = NT_, NW = NT / 32;
+  static constexpr int H1 = T1 + P, H2 = T2 + P;          // halo elements per tile dimension
+  static constexpr int NQ1 = H1 * NQ, NQ2 = H2 * NQ;      // halo points
+  static constexpr int NP1 = T1 * WD, NP2 = T2 * WD;      // dof pairs (i, i-P..i+P)
+  static constexpr int LS = QC * NQ1;                     // S1 lane items (q0, Q1)
+  static constexpr int NP2P = NP2 | 1;                    // odd -> conflict-free T1 stores
+  static constexpr int L2S = QC * NP2P;                   // S2 lane items (q0, pair2)
+  static constexpr int T1QS = (9 * L2S) | 1;              // T1 stride per Q1
+  static constexpr int N12 = NP1 * NP2;                   // S3 items
+  static constexpr int N12P = N12 + 4;
+  static constexpr int IPT = (N12 + NT - 1) / NT;
+  static constexpr int WPI1 = (LS + 31) / 32, WPI2 = (L2S + 31) / 32;
+  // shared memory, in doubles
+  static constexpr int SZ_G = 7 * NQ2 * LS;
+  static constexpr int SZ_T2 = QC * 5 * N12P;
+  static constexpr int SZ_GT = SZ_G > SZ_T2 ? SZ_G : SZ_T2;  // T2 aliases G
+  static constexpr int OFF_T1 = SZ_GT, SZ_T1 = NQ1 * T1QS;
+  static constexpr int OFF_L1 = OFF_T1 + SZ_T1, SZ_L1 = NQ1 * QC * T2;
+  static constexpr int OFF_L2 = OFF_L1 + SZ_L1, SZ_L2 = QC * T1 * T2;
+  static constexpr int OFF_NOD = OFF_L2 + SZ_L2, SZ_NOD = 3 * 2 * (H1 + 1) * (H2 + 1);
+  static constexpr int OFF_TB1 = OFF_NOD + SZ_NOD, SZ_TB1 = H1 * NQ * NB * 2;
+  static constexpr int OFF_TB2 = OFF_TB1 + SZ_TB1, SZ_TB2 = H2 * NQ * NB * 2;
+  static constexpr int OFF_TB0 = OFF_TB2 + SZ_TB2, SZ_TB0 = NQ * NB * 2;
+  static constexpr int OFF_PW = OFF_TB0 + SZ_TB0, SZ_PW = 6 * NQ;
+  static constexpr int TOTAL = OFF_PW + SZ_PW;
+};
+
+template <class C, bool FK, bool FM>
+__global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
+  constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, QC = C::QC, NT = C::NT, NW = C::NW;
+  constexpr int T1 = C::T1, T2 = C::T2, H1 = C::H1, H2 = C::H2, NQ1 = C::NQ1, NQ2 = C::NQ2;
+  constexpr int NP1 = C::NP1, NP2 = C::NP2, NP2P = C::NP2P, LS = C::LS, L2S = C::L2S, T1QS = C::T1QS;
+  constexpr int N12 = C::N12, N12P = C::N12P, IPT = C::IPT;
+  constexpr int NTK = FK ? 8 : 0, NTERM = NTK + (FM ? 1 : 0);  // S1 output terms
+  constexpr int NGK = FK ? 4 : 0, NG = NGK + (FM ? 1 : 0);      // S2 output groups
+  const BasisView& B = prm.B;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  extern __shared__ __align__(16) double smem[];
+  double* sG = smem;                  // [7][NQ2][LS]
+  double* sT2 = smem;                 // [QC][NG][N12P]   (aliases sG)
+  double* sT1 = smem + C::OFF_T1;     // [NQ1][T1QS] = [NQ1][term][q0 NP2P + pair2]
+  double* sL1 = smem + C::OFF_L1;     // [NQ1][QC][T2]
+  double* sL2 = smem + C::OFF_L2;     // [QC][T1][T2]
+  double* sNod = smem + C::OFF_NOD;   // [3][2][H1+1][H2+1]
+  double* sTb1 = smem + C::OFF_TB1;   // [H1][NQ][NB][2]  (value, derivative) of local function a at point q of halo element
+  double* sTb2 = smem + C::OFF_TB2;   // [H2][NQ][NB][2]
+  double* sTb0 = smem + C::OFF_TB0;   // [NQ][NB][2]      current layer
+  double* sPt = smem + C::OFF_PW;     // [3][NQ]
+  double* sWt = sPt + 3 * NQ;         // [3][NQ]
+
+  // ---- work unit ----
+  const int t2 = blockIdx.x % prm.tiles2, t1 = (blockIdx.x / prm.tiles2) % prm.tiles1, seg = blockIdx.x / (prm.tiles2 * prm.tiles1);
+  const int i1lo = t1 * T1, i2lo = t2 * T2, e1base = i1lo - P, e2base = i2lo - P;
+  const int n0 = B.nel[0], n1 = B.nel[1], n2 = B.nel[2], nd1 = B.ndofs[1], nd2 = B.ndofs[2];
+  const long long npl = prm.plane_end - prm.plane_begin;
+  const int r0 = prm.plane_begin + (int)(npl * seg / prm.nseg), r1 = prm.plane_begin + (int)(npl * (seg + 1) / prm.nseg);
+  if (r0 >= r1) return;
+  const int ebeg = max(0, r0 - P), eend = min(n0 - 1, r1 - 1);
+
+  // ---- per-unit tables ----
+  for (int t = tid; t < C::SZ_TB1; t += NT) {
+    const int k = t & 1, a = (t >> 1) % NB, q = (t / (2 * NB)) % NQ, el = t / (2 * NB * NQ);
+    const int e = e1base + el;
+    sTb1[t] = (e >= 0 && e < n1) ? prm.Q.tab[1][((B.setidx[1][e] * 2 + k) * NB + a) * NQ + q] : 0.;
+  }
+  for (int t = tid; t < C::SZ_TB2; t += NT) {
+    const int k = t & 1, a = (t >> 1) % NB, q = (t / (2 * NB)) % NQ, el = t / (2 * NB * NQ);
+    const int e = e2base + el;
+    sTb2[t] = (e >= 0 && e < n2) ? prm.Q.tab[2][((B.setidx[2][e] * 2 + k) * NB + a) * NQ + q] : 0.;
+  }
+  for (int t = tid; t < 3 * NQ; t += NT) {
+    sPt[t] = prm.Q.x[t / NQ][t % NQ];
+    sWt[t] = prm.Q.w[t / NQ][t % NQ];
+  }
+
+  // ---- S3 items owned by this thread: dof pairs (i1, j1) x (i2, j2) ----
+  bool ivalid[IPT], idiag[IPT];
+  long long ic12[IPT];
+  int iw12[IPT], io12[IPT], if12[IPT], il12[IPT];
+#pragma unroll
+  for (int it = 0; it < IPT; it++) {
+    const int item = tid + it * NT;
+    const int pair1 = item / NP2, pair2 = item % NP2;
+    const int i1l = pair1 / WD, d1 = pair1 % WD, i2l = pair2 / WD, d2 = pair2 % WD;
+    const int i1 = i1lo + i1l, j1 = i1 + d1 - P, i2 = i2lo + i2l, j2 = i2 + d2 - P;
+    const bool v = item < N12 && i1 < nd1 && i2 < nd2 && j1 >= 0 && j1 < nd1 && j2 >= 0 && j2 < nd2;
+    ivalid[it] = v;
+    idiag[it] = v && d1 == P && d2 == P;
+    ic12[it] = 0; iw12[it] = 0; io12[it] = 0; if12[it] = 0; il12[it] = i1l * T2 + i2l;
+    if (v) {
+      const int w1 = B.wid[1][i1], w2 = B.wid[2][i2];
+      ic12[it] = (long long)B.cum[1][i1] * B.W[2] + (long long)w1 * B.cum[2][i2];
+      iw12[it] = w1 * w2;
+      io12[it] = (j1 - B.lo[1][i1]) * w2 + (j2 - B.lo[2][i2]);
+      if12[it] = i1 * nd2 + i2;
+    }
+  }
+  const long long W12 = B.W[1] * B.W[2];
+
+  double accK[IPT][NB][NB], accM[IPT][NB][NB], accF[IPT][NB];
+#pragma unroll
+  for (int it = 0; it < IPT; it++)
+#pragma unroll
+    for (int a = 0; a < NB; a++) {
+      accF[it][a] = 0.;
+#pragma unroll
+      for (int b = 0; b < NB; b++) accK[it][a][b] = accM[it][a][b] = 0.;
+    }
+
+  for (int e0 = ebeg; e0 <= eend; e0++) {
+    // ---- layer tables: nodes of planes e0, e0+1 over the halo, 1-D table of dimension 0 ----
+    for (int t = tid; t < C::SZ_NOD; t += NT) {
+      const int c2 = t % (H2 + 1), c1 = (t / (H2 + 1)) % (H1 + 1), pl = (t / ((H2 + 1) * (H1 + 1))) % 2, i = t / (2 * (H2 + 1) * (H1 + 1));
+      const int v1 = min(max(e1base + c1, 0), n1), v2 = min(max(e2base + c2, 0), n2);
+      sNod[t] = __ldg(prm.G.nodes + i * prm.G.nnodes + (long long)(e0 + pl) * prm.G.stride[0] + (long long)v1 * prm.G.stride[1] + v2);
+    }
+    for (int t = tid; t < C::SZ_TB0; t += NT) {
+      const int k = t & 1, a = (t >> 1) % NB, q = t / (2 * NB);
+      sTb0[t] = prm.Q.tab[0][((B.setidx[0][e0] * 2 + k) * NB + a) * NQ + q];
+    }
+    __syncthreads();
+
+    for (int qc = 0; qc < NQ; qc += QC) {
+      // ================= G: geometry at the halo points of QC point-planes =================
+      for (int pt = tid; pt < NQ2 * LS; pt += NT) {
+        const int Q2 = pt / LS, L = pt % LS, q0 = qc + L / NQ1, Q1 = L % NQ1;
+        const int e1l = Q1 / NQ, q1 = Q1 % NQ, e2l = Q2 / NQ, q2 = Q2 % NQ;
+        const int e1 = e1base + e1l, e2 = e2base + e2l;
+        if (e1 < 0 || e1 >= n1 || e2 < 0 || e2 >= n2) continue;
+        const double x1 = sPt[q0], x2 = sPt[NQ + q1], x3 = sPt[2 * NQ + q2];
+        const double w = sWt[q0] * sWt[NQ + q1] * sWt[2 * NQ + q2];
+        double J[9];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          const double* X = sNod + (i * 2 * (H1 + 1) + e1l) * (H2 + 1) + e2l;
+          constexpr int SP = (H1 + 1) * (H2 + 1), S1 = H2 + 1;
+          const double c000 = X[0], c001 = X[1], c010 = X[S1], c011 = X[S1 + 1];
+          const double c100 = X[SP], c101 = X[SP + 1], c110 = X[SP + S1], c111 = X[SP + S1 + 1];
+          const double d00 = c001 - c000, d01 = c011 - c010, d10 = c101 - c100, d11 = c111 - c110;
+          const double m00 = fma(x3, d00, c000), m01 = fma(x3, d01, c010), m10 = fma(x3, d10, c100), m11 = fma(x3, d11, c110);
+          const double g0 = fma(x2, d01 - d00, d00), g1 = fma(x2, d11 - d10, d10);
+          J[i * 3 + 2] = fma(x1, g1 - g0, g0);
+          const double f0 = m01 - m00, f1 = m11 - m10;
+          const double h0 = fma(x2, f0, m00), h1 = fma(x2, f1, m10);
+          J[i * 3 + 1] = fma(x1, f1 - f0, f0);
+          J[i * 3 + 0] = h1 - h0;
+        }
+        // adjugate rows A[k][i] (J^-1 = A / det)
+        double A[9];
+        A[0] = J[4] * J[8] - J[5] * J[7]; A[1] = J[2] * J[7] - J[1] * J[8]; A[2] = J[1] * J[5] - J[2] * J[4];
+        A[3] = J[5] * J[6] - J[3] * J[8]; A[4] = J[0] * J[8] - J[2] * J[6]; A[5] = J[2] * J[3] - J[0] * J[5];
+        A[6] = J[3] * J[7] - J[4] * J[6]; A[7] = J[1] * J[6] - J[0] * J[7]; A[8] = J[0] * J[4] - J[1] * J[3];
+        const double det = J[0] * A[0] + J[1] * A[3] + J[2] * A[6];
+        const double adet = fabs(det);
+        double* g = sG + Q2 * LS + L;
+        constexpr int GS = NQ2 * LS;
+        if (FK) {
+          const double s = w / adet;
+          if (prm.iso) {
+            const double sk = s * prm.kc[0];
+            g[0 * GS] = sk * (A[0] * A[0] + A[1] * A[1] + A[2] * A[2]);
+            g[1 * GS] = sk * (A[0] * A[3] + A[1] * A[4] + A[2] * A[5]);
+            g[2 * GS] = sk * (A[0] * A[6] + A[1] * A[7] + A[2] * A[8]);
+            g[3 * GS] = sk * (A[3] * A[3] + A[4] * A[4] + A[5] * A[5]);
+            g[4 * GS] = sk * (A[3] * A[6] + A[4] * A[7] + A[5] * A[8]);
+            g[5 * GS] = sk * (A[6] * A[6] + A[7] * A[7] + A[8] * A[8]);
+          } else {
+            double T[9];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              T[k * 3 + 0] = A[k * 3] * prm.kc[0] + A[k * 3 + 1] * prm.kc[1] + A[k * 3 + 2] * prm.kc[2];
+              T[k * 3 + 1] = A[k * 3] * prm.kc[1] + A[k * 3 + 1] * prm.kc[3] + A[k * 3 + 2] * prm.kc[4];
+              T[k * 3 + 2] = A[k * 3] * prm.kc[2] + A[k * 3 + 1] * prm.kc[4] + A[k * 3 + 2] * prm.kc[5];
+            }
+            int t = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+              for (int l = k; l < 3; l++) g[(t++) * GS] = s * (T[k * 3] * A[l * 3] + T[k * 3 + 1] * A[l * 3 + 1] + T[k * 3 + 2] * A[l * 3 + 2]);
+          }
+        }
+        g[6 * GS] = w * adet;
+      }
+      __syncthreads();
+
+      // ================= S1: contract Q2 =================
+      for (int wi = warp; wi < T2 * C::WPI1; wi += NW) {
+        const int i2l = wi / C::WPI1, L = (wi % C::WPI1) * 32 + lane, i2 = i2lo + i2l;
+        if (i2 >= nd2) continue;
+        const int q0l = L / NQ1, Q1 = L % NQ1, e1 = e1base + Q1 / NQ;
+        if (L >= LS || e1 < 0 || e1 >= n1) continue;
+        double t[WD][NTERM > 0 ? NTERM : 1];
+#pragma unroll
+        for (int d = 0; d < WD; d++)
+#pragma unroll
+          for (int m = 0; m < NTERM; m++) t[d][m] = 0.;
+        double l1 = 0.;
+#pragma unroll
+        for (int k = 0; k <= P; k++) {
+          const int e2 = i2 - P + k;
+          if (e2 < 0 || e2 >= n2) continue;
+          constexpr int GS = NQ2 * LS;
+          const int a = P - k, e2l = i2l + k;
+#pragma unroll
+          for (int q2 = 0; q2 < NQ; q2++) {
+            const double* g = sG + (e2l * NQ + q2) * LS + L;
+            const double* tb = sTb2 + (e2l * NQ + q2) * NB * 2;
+            const double va = tb[a * 2], da = tb[a * 2 + 1];
+            const double gm = g[6 * GS];
+            double pa[9];
+            if (FK) {
+              const double g00 = g[0], g01 = g[GS], g02 = g[2 * GS], g11 = g[3 * GS], g12 = g[4 * GS], g22 = g[5 * GS];
+              pa[0] = va * g00; pa[1] = va * g01; pa[2] = va * g11;
+              pa[3] = va * g02; pa[4] = va * g12;
+              pa[5] = da * g02; pa[6] = da * g12;
+              pa[7] = da * g22;
+            }
+            pa[8] = va * gm;
+            l1 += pa[8];
+#pragma unroll
+            for (int b = 0; b <= P; b++) {
+              const double vb = tb[b * 2], db = tb[b * 2 + 1];
+              const int d = b + k;
+              if (FK) {
+                t[d][0] = fma(pa[0], vb, t[d][0]);
+                t[d][1] = fma(pa[1], vb, t[d][1]);
+                t[d][2] = fma(pa[2], vb, t[d][2]);
+                t[d][3] = fma(pa[3], db, t[d][3]);
+                t[d][4] = fma(pa[4], db, t[d][4]);
+                t[d][5] = fma(pa[5], vb, t[d][5]);
+                t[d][6] = fma(pa[6], vb, t[d][6]);
+                t[d][7] = fma(pa[7], db, t[d][7]);
+              }
+              if (FM) t[d][NTK] = fma(pa[8], vb, t[d][NTK]);
+            }
+          }
+        }
+        double* o = sT1 + Q1 * T1QS + q0l * NP2P + i2l * WD;
+#pragma unroll
+        for (int d = 0; d < WD; d++)
+#pragma unroll
+          for (int m = 0; m < NTERM; m++) o[m * L2S + d] = t[d][m];
+        sL1[(Q1 * QC + q0l) * T2 + i2l] = l1;
+      }
+      __syncthreads();
+
+      // ================= S2: contract Q1 =================
+      for (int wi = warp; wi < T1 * C::WPI2; wi += NW) {
+        const int i1l = wi / C::WPI2, L = (wi % C::WPI2) * 32 + lane, i1 = i1lo + i1l;
+        if (i1 >= nd1) continue;
+        const int q0l = L / NP2P, pair2 = L % NP2P;
+        if (L >= L2S || pair2 >= NP2) continue;
+        const int i2l = pair2 / WD;
+        const bool diag = (pair2 % WD) == P;
+        double u[WD][NG > 0 ? NG : 1];
+#pragma unroll
+        for (int d = 0; d < WD; d++)
+#pragma unroll
+          for (int m = 0; m < NG; m++) u[d][m] = 0.;
+        double l2 = 0.;
+#pragma unroll
+        for (int k = 0; k <= P; k++) {
+          const int e1 = i1 - P + k;
+          if (e1 < 0 || e1 >= n1) continue;
+          const int a = P - k, e1l = i1l + k;
+#pragma unroll
+          for (int q1 = 0; q1 < NQ; q1++) {
+            const int Q1 = e1l * NQ + q1;
+            const double* x = sT1 + Q1 * T1QS + L;
+            const double* tb = sTb1 + Q1 * NB * 2;
+            const double va = tb[a * 2], da = tb[a * 2 + 1];
+            double X[7];
+            if (FK) {
+              const double A0 = x[0], A1 = x[L2S], A2 = x[2 * L2S], B0 = x[3 * L2S], B1 = x[4 * L2S], C0 = x[5 * L2S], C1 = x[6 * L2S], D = x[7 * L2S];
+              X[0] = va * A0;
+              X[1] = va * A1;
+              X[2] = va * B0;
+              X[3] = fma(da, A1, va * C0);
+              X[4] = fma(da, A2, va * C1);
+              X[5] = fma(da, B1, va * D);
+            }
+            if (FM) X[6] = va * x[NTK * L2S];
+            if (diag) l2 = fma(va, sL1[(Q1 * QC + q0l) * T2 + i2l], l2);
+#pragma unroll
+            for (int b = 0; b <= P; b++) {
+              const double vb = tb[b * 2], db = tb[b * 2 + 1];
+              const int d = b + k;
+              if (FK) {
+                u[d][0] = fma(X[0], vb, u[d][0]);                      // DD
+                u[d][1] = fma(X[1], db, fma(X[2], vb, u[d][1]));       // DV
+                u[d][2] = fma(X[3], vb, u[d][2]);                      // VD
+                u[d][3] = fma(X[4], db, fma(X[5], vb, u[d][3]));       // VV
+              }
+              if (FM) u[d][NGK] = fma(X[6], vb, u[d][NGK]);
+            }
+          }
+        }
+        double* o = sT2 + q0l * NG * N12P + (i1l * WD) * NP2 + pair2;
+#pragma unroll
+        for (int d = 0; d < WD; d++)
+#pragma unroll
+          for (int m = 0; m < NG; m++) o[m * N12P + d * NP2] = u[d][m];
+        if (diag) sL2[(q0l * T1 + i1l) * T2 + i2l] = l2;
+      }
+      __syncthreads();
+
+      // ================= S3: contract q0 into the marching accumulators =================
+#pragma unroll
+      for (int q0l = 0; q0l < QC; q0l++) {
+        double va[NB], da[NB];
+#pragma unroll
+        for (int a = 0; a < NB; a++) {
+          va[a] = sTb0[((qc + q0l) * NB + a) * 2];
+          da[a] = sTb0[((qc + q0l) * NB + a) * 2 + 1];
+        }
+#pragma unroll
+        for (int it = 0; it < IPT; it++) {
+          const int item = tid + it * NT;
+          if (item < N12) {
+            const double* x = sT2 + q0l * NG * N12P + item;
+            double gDD = 0., gDV = 0., gVD = 0., gVV = 0., gM = 0.;
+            if (FK) { gDD = x[0]; gDV = x[N12P]; gVD = x[2 * N12P]; gVV = x[3 * N12P]; }
+            if (FM) gM = x[NGK * N12P];
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+              const double ud = fma(da[b], gDD, va[b] * gDV), uv = fma(da[b], gVD, va[b] * gVV), um = va[b] * gM;
+#pragma unroll
+              for (int a = 0; a < NB; a++) {
+                if (FK) accK[it][a][b] = fma(da[a], ud, fma(va[a], uv, accK[it][a][b]));
+                if (FM) accM[it][a][b] = fma(va[a], um, accM[it][a][b]);
+              }
+            }
+            if (prm.has_f && idiag[it]) {
+              const double l2 = sL2[q0l * T1 * T2 + il12[it]];
+#pragma unroll
+              for (int a = 0; a < NB; a++) accF[it][a] = fma(va[a], l2, accF[it][a]);
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- store the completed entries of this layer, carry the rest ----
+    const bool last = e0 == n0 - 1;
+    int rlo[NB], rwid[NB];
+    long long rbase[NB];
+#pragma unroll
+    for (int a = 0; a < NB; a++) {
+      const int i0 = e0 + a;
+      rlo[a] = B.lo[0][i0];
+      rwid[a] = B.wid[0][i0];
+      rbase[a] = (long long)B.cum[0][i0] * W12;
+    }
+#pragma unroll
+    for (int it = 0; it < IPT; it++) {
+      if (ivalid[it]) {
+#pragma unroll
+        for (int a = 0; a < NB; a++) {
+          const int i0 = e0 + a;
+          if (i0 < r0 || i0 >= r1) continue;
+          const long long rowslot = rbase[a] + (long long)rwid[a] * ic12[it] + io12[it];
+#pragma unroll
+          for (int b = 0; b < NB; b++) {
+            if (a == 0 || b == 0 || last) {
+              const long long slot = rowslot + (long long)(e0 + b - rlo[a]) * iw12[it];
+              if (FK) prm.valK[slot] = accK[it][a][b];
+              if (FM && prm.valM) prm.valM[slot] = accM[it][a][b] * prm.rho;
+            }
+          }
+          if (prm.has_f && idiag[it] && (a == 0 || last)) prm.rhs[(long long)i0 * nd1 * nd2 + if12[it]] = accF[it][a] * prm.vcoef;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NB; a++) {
+        accF[it][a] = a < P ? accF[it][a + 1] : 0.;
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+          if (FK) accK[it][a][b] = (a < P && b < P) ? accK[it][a + 1][b + 1] : 0.;
+          if (FM) accM[it][a][b] = (a < P && b < P) ? accM[it][a + 1][b + 1] : 0.;
+        }
+      }
+    }
+  }
+}
+
+template <class C, bool FK, bool FM>
+int launch_rows_cfg(b2_ctx* ctx, RowParams& prm) {
+  auto kern = k_rows3d<C, FK, FM>;
+  const size_t smem = sizeof(double) * C::TOTAL;
+  static_assert(sizeof(double) * C::TOTAL <= 227 * 1024, "tile does not fit in shared memory");
+  B2_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prm.tiles1 = (prm.B.ndofs[1] + C::T1 - 1) / C::T1;
+  prm.tiles2 = (prm.B.ndofs[2] + C::T2 - 1) / C::T2;
+  // segments along the marching direction: trade redundant layers (P per segment) against wave quantisation
+  const long long tiles = (long long)prm.tiles1 * prm.tiles2, npl = prm.plane_end - prm.plane_begin;
+  const int slots = ctx->sm_count;  // one CTA per SM
+  int best = 1;
+  double bestcost = 1e300;
+  const int64_t forced = ctx->opts.count("rows_nseg") ? ctx->opts["rows_nseg"] : 0;
+  for (int s = 1; s <= 64 && s <= npl; s++) {
+    const long long waves = (tiles * s + slots - 1) / slots;
+    const double cost = (double)waves * ((double)(npl + s - 1) / s + C::P + 1.5);  // +1.5: per-CTA set-up in layer units
+    if (cost < bestcost) { bestcost = cost; best = s; }
+  }
+  prm.nseg = forced > 0 ? (int)std::min<int64_t>(forced, npl) : best;
+  const long long blocks = tiles * prm.nseg;
+  if (blocks > 0x7fffffffLL) return B2_EUNSUPPORTED;
+  {
+    KernelTimer timer(ctx);
+    kern<<<(unsigned)blocks, C::NT, smem, ctx->stream>>>(prm);
+  }
+  ctx->launches++;
+  B2_CUDA(ctx, cudaGetLastError());
+  return B2_OK;
+}
+
+template <class C>
+int launch_rows_forms(b2_ctx* ctx, RowParams& prm, bool fk, bool fm) {
+  if (fk && fm) return launch_rows_cfg<C, true, true>(ctx, prm);
+  if (fk) return launch_rows_cfg<C, true, false>(ctx, prm);
+  return launch_rows_cfg<C, false, true>(ctx, prm);
+}
+
+}  // namespace
+
+// Owner-computes assembly of the dof planes [plane_begin, plane_end) of dimension 0.  Returns
+// B2_EUNSUPPORTED when the configuration is outside the specialised kernel (caller falls back).
+int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const BasisView& B, const QuadView& Q, const GeomView& G, const FormView& F,
+                         const double* const* D_host, const double* const* C_host, long long plane_begin, long long plane_end) {
+  if (B.ndims != 3 || B.ncomp != 1) return B2_EUNSUPPORTED;
+  const int P = B.p[0];
+  if (B.p[1] != P || B.p[2] != P || (P != 1 && P != 2)) return B2_EUNSUPPORTED;
+  for (int d = 0; d < 3; d++) {
+    if (Q.nq[d] != P + 1) return B2_EUNSUPPORTED;
+    // maximal smoothness: element e carries dofs e..e+P
+    if (B.ndofs[d] != B.nel[d] + P) return B2_EUNSUPPORTED;
+    for (int e = 0; e < B.nel[d]; e++)
+      if (basis->start[d][e] != e) return B2_EUNSUPPORTED;
+  }
+  if (F.nmat > 2 || F.nvec > 1 || (F.nmat == 0 && F.nvec == 0)) return B2_EUNSUPPORTED;
+  RowParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.B = B;
+  prm.Q = Q;
+  prm.G = G;
+  prm.plane_begin = (int)plane_begin;
+  prm.plane_end = (int)plane_end;
+  prm.rho = 1.;
+  prm.kc[0] = prm.kc[3] = prm.kc[5] = 1.;
+  bool fk = false, fm = false;
+  for (int m = 0; m < F.nmat; m++) {
+    const double* D = D_host[m];  // [4][4]
+    bool gradgrad = false, mass = D[0] != 0., mixed = false, symmetric = true;
+    for (int x = 1; x < 4; x++) {
+      if (D[x] != 0. || D[x * 4] != 0.) mixed = true;
+      for (int y = 1; y < 4; y++) {
+        if (D[x * 4 + y] != 0.) gradgrad = true;
+        if (D[x * 4 + y] != D[y * 4 + x]) symmetric = false;
+      }
+    }
+    if (mixed || !symmetric || (gradgrad && mass) || (!gradgrad && !mass)) return B2_EUNSUPPORTED;
+    if (gradgrad) {
+      if (fk) return B2_EUNSUPPORTED;
+      fk = true;
+      const double kc[6] = {D[5], D[6], D[7], D[10], D[11], D[15]};
+      for (int t = 0; t < 6; t++) prm.kc[t] = kc[t];
+      prm.valK = F.values[m];
+    } else {
+      if (fm) return B2_EUNSUPPORTED;
+      fm = true;
+      prm.rho = D[0];
+      prm.valM = F.values[m];
+    }
+  }
+  prm.iso = prm.kc[1] == 0. && prm.kc[2] == 0. && prm.kc[4] == 0. && prm.kc[0] == prm.kc[3] && prm.kc[0] == prm.kc[5];
+  if (F.nvec) {
+    const double* Cv = C_host[0];  // [4]
+    if (Cv[1] != 0. || Cv[2] != 0. || Cv[3] != 0.) return B2_EUNSUPPORTED;
+    prm.has_f = 1;
+    prm.vcoef = Cv[0];
+    prm.rhs = F.rhs[0];
+    if (!fk && !fm) fm = true, prm.valM = nullptr;  // load vector only: run the mass chain without storing it
+  }
+  if (P == 1) return launch_rows_forms<RCfg<1, 6, 6, 2, 256>>(ctx, prm, fk, fm);
+  return launch_rows_forms<RCfg<2, 4, 4, 3, 256>>(ctx, prm, fk, fm);
+}

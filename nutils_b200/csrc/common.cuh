@@ -155,11 +155,16 @@ int b2_cuda_fail(b2_ctx* ctx, cudaError_t e, const char* what);
 // ---- kernel launchers (defined in the .cu files) -------------------------------------------------
 
 int launch_pattern_export(b2_ctx* ctx, const BasisView& B, long long* rowptr, long long* colidx);
+// only rows whose dimension-0 dof index lies in [plane_lo, plane_hi) are scattered (0, INT_MAX = all)
 int launch_assemble_generic(b2_ctx* ctx, const BasisView& B, const QuadView& Q, const GeomView& G, const FormView& F,
-                            long long elem_begin, long long elem_end);
+                            long long elem_begin, long long elem_end, int plane_lo, int plane_hi);
 // returns B2_EUNSUPPORTED when no specialised kernel covers the request
 int launch_assemble_fast(b2_ctx* ctx, const BasisView& B, const QuadView& Q, const GeomView& G, const FormView& F,
                          const double* const* D_host, const double* const* C_host, long long elem_begin, long long elem_end);
+
+// owner-computes kernel: WRITES every stored value of the dof planes [plane_begin, plane_end) of dimension 0
+int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const BasisView& B, const QuadView& Q, const GeomView& G, const FormView& F,
+                         const double* const* D_host, const double* const* C_host, long long plane_begin, long long plane_end);
 
 // ---- device helpers ------------------------------------------------------------------------------
 

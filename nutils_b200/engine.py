@@ -242,6 +242,17 @@ class Plan:
         self.ctx.check(self.ctx.lib.b2_assemble_device(self.ctx.handle, self.pattern, self.basis, self.quad, self.geom, c_i64(e0), c_i64(e1),
                                                        len(Ds), pD, pv, len(Cs), pC, pr))
 
+    def assemble_rows_device(self, Ds=(), Cs=(), values=(), rhs=(), plane_range=None):
+        '''Owner-computes assembly (b2_assemble_rows_device): WRITES every stored value of the dof rows whose index along
+        dimension 0 lies in plane_range (default: all); no zero-fill needed, rows outside the range are untouched.'''
+        Ds, Cs, pD, pC = self._form_args(Ds, Cs)
+        assert len(values) == len(Ds) and len(rhs) == len(Cs)
+        p0, p1 = plane_range if plane_range is not None else (0, -1)
+        pv = (c_vp * max(len(values), 1))(*[_devptr(v) for v in values])
+        pr = (c_vp * max(len(rhs), 1))(*[_devptr(r) for r in rhs])
+        self.ctx.check(self.ctx.lib.b2_assemble_rows_device(self.ctx.handle, self.pattern, self.basis, self.quad, self.geom, c_i64(p0), c_i64(p1),
+                                                            len(Ds), pD, pv, len(Cs), pC, pr))
+
 
 # ---- coefficient tensors of the north-star forms -------------------------------------------------------
 

@@ -31,13 +31,19 @@ def _forms(g, nd):
     return [engine.form_elasticity(nd, float(g['lmbda']), float(g['mu']), scale=2.)], [C], [g['K_values']]
 
 
-@pytest.mark.parametrize('kernel', [0, 1])
+# (kernel, path): owner-computes rows kernel / its coverage fallback / element-scatter specialised / element-scatter generic
+MODES = [(0, 0), (1, 0), (0, 1), (1, 1)]
+MODE_IDS = ['rows', 'rows-generic', 'scatter', 'scatter-generic']
+
+
+@pytest.mark.parametrize('mode', MODES, ids=MODE_IDS)
 @pytest.mark.parametrize('name', util.golden_names())
-def test_golden(ctx, name, kernel):
+def test_golden(ctx, name, mode):
     g = util.load_golden(name)
     prob = util.problem_from_golden(g)
     plan = _plan(ctx, prob)
-    ctx.set_option('kernel', kernel)
+    ctx.set_option('kernel', mode[0])
+    ctx.set_option('path', mode[1])
     try:
         rowptr, colidx = plan.csr_pattern()
         assert rowptr.dtype == numpy.int64 and colidx.dtype == numpy.int64
@@ -52,6 +58,7 @@ def test_golden(ctx, name, kernel):
         assert util.relerr(rhs[0], g['F']) <= TOL
     finally:
         ctx.set_option('kernel', 0)
+        ctx.set_option('path', 0)
 
 
 def _random_problem(seed, nelems, degree, ncomp=1, btype='spline', warp=.25, qdegree=None):
@@ -73,13 +80,13 @@ CASES = [
     dict(nelems=(9, 8, 7), degree=1), dict(nelems=(10, 9, 11), degree=2), dict(nelems=(5, 4, 6), degree=3), dict(nelems=(3, 2, 3), degree=4),
     dict(nelems=(6, 5, 4), degree=2, btype='std'), dict(nelems=(6, 5, 4), degree=2, qdegree=6),
     dict(nelems=(9, 7), degree=2, ncomp=2), dict(nelems=(5, 4, 5), degree=2, ncomp=3), dict(nelems=(4, 3, 3), degree=3, ncomp=3),
-    dict(nelems=(1, 1, 1), degree=2),
+    dict(nelems=(1, 1, 1), degree=2), dict(nelems=(3, 13, 18), degree=2), dict(nelems=(7, 11, 5), degree=1), dict(nelems=(1, 2, 9), degree=2),
 ]
 
 
-@pytest.mark.parametrize('kernel', [0, 1])
+@pytest.mark.parametrize('mode', MODES, ids=MODE_IDS)
 @pytest.mark.parametrize('case', CASES, ids=lambda c: 'x'.join(map(str, c['nelems'])) + 'p{}c{}'.format(c['degree'], c.get('ncomp', 1)) + c.get('btype', '') + str(c.get('qdegree', '')))
-def test_oracle_seeded(ctx, case, kernel):
+def test_oracle_seeded(ctx, case, mode):
     prob = _random_problem(seed=hash(str(case)) % 2**31, **case)
     nd, nc = prob.ndims, prob.ncomp
     rng = numpy.random.RandomState(5)
@@ -91,7 +98,8 @@ def test_oracle_seeded(ctx, case, kernel):
         Cs = [rng.rand(nc, nd + 1)]
     mats, vecs = c_oracle.assemble(prob, [('generic', D) for D in Ds], [('generic', C) for C in Cs])
     plan = _plan(ctx, prob)
-    ctx.set_option('kernel', kernel)
+    ctx.set_option('kernel', mode[0])
+    ctx.set_option('path', mode[1])
     try:
         rowptr, colidx = plan.csr_pattern()
         assert numpy.array_equal(rowptr, mats[0][1])
@@ -99,6 +107,7 @@ def test_oracle_seeded(ctx, case, kernel):
         vals, rhs = plan.assemble_host(Ds, Cs)
     finally:
         ctx.set_option('kernel', 0)
+        ctx.set_option('path', 0)
     for v, (ref, _, _) in zip(vals, mats):
         assert util.relerr(v, ref) <= TOL
         assert util.rowsum_relerr(v, ref, rowptr) <= TOL
@@ -116,6 +125,77 @@ def test_element_ranges_accumulate(ctx):
     parts = [plan.assemble_host(D, C, elem_range=r) for r in ((0, n // 3), (n // 3, n // 3), (n // 3, n))]
     assert util.relerr(sum(p[0][0] for p in parts), full_v[0]) <= 1e-14
     assert util.relerr(sum(p[1][0] for p in parts), full_r[0]) <= 1e-14
+
+
+ROWS_CASES = [
+    dict(nelems=(10, 9, 11), degree=2), dict(nelems=(9, 8, 7), degree=1), dict(nelems=(3, 13, 18), degree=2), dict(nelems=(1, 1, 1), degree=2),
+    dict(nelems=(2, 1, 1), degree=1), dict(nelems=(6, 5, 4), degree=2, btype='std'), dict(nelems=(5, 4, 6), degree=3), dict(nelems=(12, 15), degree=2),
+    dict(nelems=(5, 4, 5), degree=2, ncomp=3),
+]
+
+
+@pytest.mark.parametrize('nseg', [0, 1, 3])
+@pytest.mark.parametrize('case', ROWS_CASES, ids=lambda c: 'x'.join(map(str, c['nelems'])) + 'p{}c{}'.format(c['degree'], c.get('ncomp', 1)) + c.get('btype', ''))
+def test_rows_plane_ranges(ctx, case, nseg):
+    '''b2_assemble_rows_device: physical coefficients (anisotropic conductivity, density, load) against the oracle; disjoint
+    plane ranges written into one poisoned array give the full result (the multi-GPU decomposition: no exchange, no zero-fill),
+    and rows outside a range are not touched.  Covers the specialised owner-computes kernel (3-D scalar p=1,2 splines) and the
+    coverage path (everything else).'''
+    import torch
+    prob = _random_problem(seed=hash(str(case)) % 2**31, **case)
+    nd, nc = prob.ndims, prob.ncomp
+    rng = numpy.random.RandomState(11)
+    A = rng.rand(nd, nd)
+    Ds = [engine.form_stiffness(nd, nc, conductivity=A @ A.T + numpy.eye(nd)), 2.5 * engine.form_mass(nd, nc)]
+    Cs = [-.75 * engine.form_load(nd, nc)]
+    mats, vecs = c_oracle.assemble(prob, [('generic', D) for D in Ds], [('generic', C) for C in Cs])
+    plan = _plan(ctx, prob)
+    rowptr, _ = plan.csr_pattern()
+    ndof0 = prob.ndofs_d[0]
+    dev = torch.device('cuda', 0)
+    poison = -7.25
+    vals = [torch.full((plan.nnz,), poison, dtype=torch.float64, device=dev) for _ in Ds]
+    rhs = [torch.full((plan.ndofs,), poison, dtype=torch.float64, device=dev) for _ in Cs]
+    cuts = sorted(set([0, ndof0 // 3, ndof0 // 3 + 1, ndof0]))
+    ctx.set_option('rows_nseg', nseg)
+    try:
+        per_plane = plan.ndofs // ndof0
+        for i, (p0, p1) in enumerate(zip(cuts[:-1], cuts[1:])):
+            plan.assemble_rows_device(Ds, Cs, vals, rhs, plane_range=(p0, p1))
+            ctx.synchronize()
+            if i == 0 and p1 < ndof0:
+                # nothing outside the planes [p0, p1) was written
+                assert bool((vals[0][int(rowptr[p1 * per_plane]):] == poison).all())
+                assert bool((rhs[0][p1 * per_plane:] == poison).all())
+    finally:
+        ctx.set_option('rows_nseg', 0)
+    for v, (ref, _, _) in zip(vals, mats):
+        v = v.cpu().numpy()
+        assert util.relerr(v, ref) <= TOL
+        assert util.rowsum_relerr(v, ref, rowptr) <= TOL
+    assert util.relerr(rhs[0].cpu().numpy(), vecs[0]) <= TOL
+
+
+def test_rows_single_forms(ctx):
+    # K only, M only, f only through the owner-computes kernel
+    import torch
+    prob = _random_problem(21, (7, 6, 9), 2)
+    plan = _plan(ctx, prob)
+    Ds = [engine.form_stiffness(3), engine.form_mass(3)]
+    Cs = [engine.form_load(3)]
+    mats, vecs = c_oracle.assemble(prob, [('generic', D) for D in Ds], [('generic', C) for C in Cs])
+    dev = torch.device('cuda', 0)
+    ctx.set_option('kernel', 2)  # specialised kernel or error
+    try:
+        for m in range(2):
+            v = torch.full((plan.nnz,), 3., dtype=torch.float64, device=dev)
+            plan.assemble_rows_device([Ds[m]], [], [v], [])
+            assert util.relerr(v.cpu().numpy(), mats[m][0]) <= TOL
+        r = torch.full((plan.ndofs,), 3., dtype=torch.float64, device=dev)
+        plan.assemble_rows_device([], Cs, [], [r])
+        assert util.relerr(r.cpu().numpy(), vecs[0]) <= TOL
+    finally:
+        ctx.set_option('kernel', 0)
 
 
 def test_properties_large(ctx):
