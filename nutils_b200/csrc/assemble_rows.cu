@@ -49,10 +49,11 @@ struct RowParams {
   double* rhs;
 };
 
-template <int P_, int T1_, int T2_, int QC_, int NT_>
+template <int P_, int T1_, int T2_, int QC_, int NT_, bool SPLIT_>
 struct RCfg {
   static constexpr int P = P_, NB = P + 1, NQ = P + 1, WD = 2 * P + 1;
   static constexpr int T1 = T1_, T2 = T2_, QC = QC_, NT = NT_, NW = NT / 32;
+  static constexpr bool SPLIT = SPLIT_;                   // S1/S2 warp items split in two term groups (more warps, fewer registers)
   static constexpr int H1 = T1 + P, H2 = T2 + P;          // halo elements per tile dimension
   static constexpr int NQ1 = H1 * NQ, NQ2 = H2 * NQ;      // halo points
   static constexpr int NP1 = T1 * WD, NP2 = T2 * WD;      // dof pairs (i, i-P..i+P)
@@ -71,22 +72,150 @@ struct RCfg {
   static constexpr int OFF_T1 = SZ_GT, SZ_T1 = NQ1 * T1QS;
   static constexpr int OFF_L1 = OFF_T1 + SZ_T1, SZ_L1 = NQ1 * QC * T2;
   static constexpr int OFF_L2 = OFF_L1 + SZ_L1, SZ_L2 = QC * T1 * T2;
-  static constexpr int OFF_NOD = OFF_L2 + SZ_L2, SZ_NOD = 3 * 2 * (H1 + 1) * (H2 + 1);
-  static constexpr int OFF_TB1 = OFF_NOD + SZ_NOD, SZ_TB1 = H1 * NQ * NB * 2;
+  static constexpr int OFF_NOD = OFF_L2 + SZ_L2, SZ_NOD = 3 * 2 * (H1 + 1) * (H2 + 1);   // x2 (double buffer)
+  static constexpr int OFF_TB1 = OFF_NOD + 2 * SZ_NOD, SZ_TB1 = H1 * NQ * NB * 2;
   static constexpr int OFF_TB2 = OFF_TB1 + SZ_TB1, SZ_TB2 = H2 * NQ * NB * 2;
-  static constexpr int OFF_TB0 = OFF_TB2 + SZ_TB2, SZ_TB0 = NQ * NB * 2;
-  static constexpr int OFF_PW = OFF_TB0 + SZ_TB0, SZ_PW = 6 * NQ;
-  static constexpr int TOTAL = OFF_PW + SZ_PW;
+  static constexpr int OFF_TB0 = OFF_TB2 + SZ_TB2, SZ_TB0 = NQ * NB * 2;                 // x2 (double buffer)
+  static constexpr int OFF_PW = OFF_TB0 + 2 * SZ_TB0, SZ_PW = 6 * NQ;
+  static constexpr int OFF_ROW = OFF_PW + SZ_PW, SZ_ROW = 2 * NB;                        // ints [NB][lo, wid, cum, pad], x2
+  static constexpr int TOTAL = OFF_ROW + 2 * SZ_ROW;
+  static constexpr int NPF = (SZ_NOD + NT - 1) / NT;                                     // node values prefetched per thread
+  static_assert(SZ_TB0 <= NT && 4 * NB <= NT, "layer tables are prefetched by one pass of the CTA");
 };
+
+// ---- S1: contract Q2.  One warp item = (dof i2 of the tile, 32 lanes of (q0, Q1), term group PART) ----
+// terms: 0 A0=G00 v.v  1 A1=G01 v.v  2 A2=G11 v.v  3 B0=G02 v.d  4 B1=G12 v.d  5 C0=G02 d.v  6 C1=G12 d.v  7 D=G22 d.d  (a-side.b-side), NTK: M
+template <class C, bool FK, bool FM, int PART, int NPARTS>
+__device__ __forceinline__ void s1_item(const double* __restrict__ sG, const double* __restrict__ sTb2, double* __restrict__ sT1, double* __restrict__ sL1,
+                                        int i2, int i2l, int L, int n2) {
+  constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, QC = C::QC, T2 = C::T2, NQ1 = C::NQ1, NQ2 = C::NQ2, LS = C::LS;
+  constexpr int NTK = FK ? 8 : 0, GS = NQ2 * LS;
+  constexpr bool TA = FK && (NPARTS == 1 || PART == 0), TB = FK && (NPARTS == 1 || PART == 1), TM = NPARTS == 1 || PART == 0;
+  const int q0l = L / NQ1, Q1 = L % NQ1;
+  double t[WD][9];
+#pragma unroll
+  for (int d = 0; d < WD; d++)
+#pragma unroll
+    for (int m = 0; m < 9; m++) t[d][m] = 0.;
+  double l1 = 0.;
+#pragma unroll
+  for (int k = 0; k <= P; k++) {
+    const int e2 = i2 - P + k;
+    if (e2 < 0 || e2 >= n2) continue;
+    const int a = P - k, e2l = i2l + k;
+#pragma unroll
+    for (int q2 = 0; q2 < NQ; q2++) {
+      const double* g = sG + (e2l * NQ + q2) * LS + L;
+      const double* tb = sTb2 + (e2l * NQ + q2) * NB * 2;
+      const double va = tb[a * 2], da = tb[a * 2 + 1];
+      double pa[9];
+      if (TA) { pa[0] = va * g[0]; pa[1] = va * g[GS]; pa[2] = va * g[3 * GS]; }
+      if (TB) {
+        const double g02 = g[2 * GS], g12 = g[4 * GS], g22 = g[5 * GS];
+        pa[3] = va * g02; pa[4] = va * g12; pa[5] = da * g02; pa[6] = da * g12; pa[7] = da * g22;
+      }
+      if (TM) { pa[8] = va * g[6 * GS]; l1 += pa[8]; }
+#pragma unroll
+      for (int b = 0; b <= P; b++) {
+        const double vb = tb[b * 2], db = tb[b * 2 + 1];
+        const int d = b + k;
+        if (TA) {
+          t[d][0] = fma(pa[0], vb, t[d][0]);
+          t[d][1] = fma(pa[1], vb, t[d][1]);
+          t[d][2] = fma(pa[2], vb, t[d][2]);
+        }
+        if (TB) {
+          t[d][3] = fma(pa[3], db, t[d][3]);
+          t[d][4] = fma(pa[4], db, t[d][4]);
+          t[d][5] = fma(pa[5], vb, t[d][5]);
+          t[d][6] = fma(pa[6], vb, t[d][6]);
+          t[d][7] = fma(pa[7], db, t[d][7]);
+        }
+        if (TM && FM) t[d][8] = fma(pa[8], vb, t[d][8]);
+      }
+    }
+  }
+  double* o = sT1 + Q1 * C::T1QS + q0l * C::NP2P + i2l * WD;
+#pragma unroll
+  for (int d = 0; d < WD; d++) {
+    if (TA) { o[0 * C::L2S + d] = t[d][0]; o[1 * C::L2S + d] = t[d][1]; o[2 * C::L2S + d] = t[d][2]; }
+    if (TB) { o[3 * C::L2S + d] = t[d][3]; o[4 * C::L2S + d] = t[d][4]; o[5 * C::L2S + d] = t[d][5]; o[6 * C::L2S + d] = t[d][6]; o[7 * C::L2S + d] = t[d][7]; }
+    if (TM && FM) o[NTK * C::L2S + d] = t[d][8];
+  }
+  if (TM) sL1[(Q1 * QC + q0l) * T2 + i2l] = l1;
+}
+
+// ---- S2: contract Q1.  One warp item = (dof i1 of the tile, 32 lanes of (q0, pair2), group set PART) ----
+// groups by the dimension-0 factor still to be applied (a-side, b-side): 0 DD, 1 DV, 2 VD, 3 VV, NGK: M
+template <class C, bool FK, bool FM, int PART, int NPARTS>
+__device__ __forceinline__ void s2_item(const double* __restrict__ sT1, const double* __restrict__ sTb1, const double* __restrict__ sL1, double* __restrict__ sT2,
+                                        double* __restrict__ sL2, int i1, int i1l, int L, int n1, bool want_f) {
+  constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, QC = C::QC, T1 = C::T1, T2 = C::T2, NP2 = C::NP2, L2S = C::L2S, N12P = C::N12P;
+  constexpr int NTK = FK ? 8 : 0, NGK = FK ? 4 : 0, NG = NGK + (FM ? 1 : 0);
+  constexpr bool GA = FK && (NPARTS == 1 || PART == 0), GB = FK && (NPARTS == 1 || PART == 1), GM = FM && (NPARTS == 1 || PART == 1), GF = NPARTS == 1 || PART == 0;
+  const int q0l = L / C::NP2P, pair2 = L % C::NP2P;
+  const int i2l = pair2 / WD;
+  const bool diag = GF && want_f && (pair2 % WD) == P;
+  double u[WD][5];
+#pragma unroll
+  for (int d = 0; d < WD; d++)
+#pragma unroll
+    for (int m = 0; m < 5; m++) u[d][m] = 0.;
+  double l2 = 0.;
+#pragma unroll
+  for (int k = 0; k <= P; k++) {
+    const int e1 = i1 - P + k;
+    if (e1 < 0 || e1 >= n1) continue;
+    const int a = P - k, e1l = i1l + k;
+#pragma unroll
+    for (int q1 = 0; q1 < NQ; q1++) {
+      const int Q1 = e1l * NQ + q1;
+      const double* x = sT1 + Q1 * C::T1QS + L;
+      const double* tb = sTb1 + Q1 * NB * 2;
+      const double va = tb[a * 2], da = tb[a * 2 + 1];
+      double X[7];
+      if (GA) {
+        const double A0 = x[0], A1 = x[L2S], B0 = x[3 * L2S], C0 = x[5 * L2S];
+        X[0] = va * A0; X[1] = va * A1; X[2] = va * B0; X[3] = fma(da, A1, va * C0);
+      }
+      if (GB) {
+        const double A2 = x[2 * L2S], B1 = x[4 * L2S], C1 = x[6 * L2S], D = x[7 * L2S];
+        X[4] = fma(da, A2, va * C1); X[5] = fma(da, B1, va * D);
+      }
+      if (GM) X[6] = va * x[NTK * L2S];
+      if (diag) l2 = fma(va, sL1[(Q1 * QC + q0l) * T2 + i2l], l2);
+#pragma unroll
+      for (int b = 0; b <= P; b++) {
+        const double vb = tb[b * 2], db = tb[b * 2 + 1];
+        const int d = b + k;
+        if (GA) {
+          u[d][0] = fma(X[0], vb, u[d][0]);
+          u[d][1] = fma(X[1], db, fma(X[2], vb, u[d][1]));
+          u[d][2] = fma(X[3], vb, u[d][2]);
+        }
+        if (GB) u[d][3] = fma(X[4], db, fma(X[5], vb, u[d][3]));
+        if (GM) u[d][4] = fma(X[6], vb, u[d][4]);
+      }
+    }
+  }
+  double* o = sT2 + q0l * NG * N12P + (i1l * WD) * NP2 + pair2;
+#pragma unroll
+  for (int d = 0; d < WD; d++) {
+    if (GA) { o[0 * N12P + d * NP2] = u[d][0]; o[1 * N12P + d * NP2] = u[d][1]; o[2 * N12P + d * NP2] = u[d][2]; }
+    if (GB) o[3 * N12P + d * NP2] = u[d][3];
+    if (GM) o[NGK * N12P + d * NP2] = u[d][4];
+  }
+  if (diag) sL2[(q0l * T1 + i1l) * T2 + i2l] = l2;
+}
 
 template <class C, bool FK, bool FM>
 __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
   constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, QC = C::QC, NT = C::NT, NW = C::NW;
   constexpr int T1 = C::T1, T2 = C::T2, H1 = C::H1, H2 = C::H2, NQ1 = C::NQ1, NQ2 = C::NQ2;
-  constexpr int NP1 = C::NP1, NP2 = C::NP2, NP2P = C::NP2P, LS = C::LS, L2S = C::L2S, T1QS = C::T1QS;
+  constexpr int NP2 = C::NP2, LS = C::LS, L2S = C::L2S;
   constexpr int N12 = C::N12, N12P = C::N12P, IPT = C::IPT;
-  constexpr int NTK = FK ? 8 : 0, NTERM = NTK + (FM ? 1 : 0);  // S1 output terms
-  constexpr int NGK = FK ? 4 : 0, NG = NGK + (FM ? 1 : 0);      // S2 output groups
+  constexpr int NGK = FK ? 4 : 0, NG = NGK + (FM ? 1 : 0);  // S2 output groups
+  constexpr int NPARTS = (C::SPLIT && FK) ? 2 : 1;
   const BasisView& B = prm.B;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -96,12 +225,13 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
   double* sT1 = smem + C::OFF_T1;     // [NQ1][T1QS] = [NQ1][term][q0 NP2P + pair2]
   double* sL1 = smem + C::OFF_L1;     // [NQ1][QC][T2]
   double* sL2 = smem + C::OFF_L2;     // [QC][T1][T2]
-  double* sNod = smem + C::OFF_NOD;   // [3][2][H1+1][H2+1]
+  double* sNodB = smem + C::OFF_NOD;  // 2 x [3][2][H1+1][H2+1]
   double* sTb1 = smem + C::OFF_TB1;   // [H1][NQ][NB][2]  (value, derivative) of local function a at point q of halo element
   double* sTb2 = smem + C::OFF_TB2;   // [H2][NQ][NB][2]
-  double* sTb0 = smem + C::OFF_TB0;   // [NQ][NB][2]      current layer
+  double* sTb0B = smem + C::OFF_TB0;  // 2 x [NQ][NB][2]  layer tables of dimension 0
   double* sPt = smem + C::OFF_PW;     // [3][NQ]
   double* sWt = sPt + 3 * NQ;         // [3][NQ]
+  int* sRowB = reinterpret_cast<int*>(smem + C::OFF_ROW);  // 2 x [NB][4] = lo, wid, cum of dof e0+a along dimension 0
 
   // ---- work unit ----
   const int t2 = blockIdx.x % prm.tiles2, t1 = (blockIdx.x / prm.tiles2) % prm.tiles1, seg = blockIdx.x / (prm.tiles2 * prm.tiles1);
@@ -127,6 +257,49 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
     sPt[t] = prm.Q.x[t / NQ][t % NQ];
     sWt[t] = prm.Q.w[t / NQ][t % NQ];
   }
+
+  // ---- layer tables (nodes of planes e0, e0+1 over the halo; 1-D table and CSR row data of dimension 0): one value per
+  //      thread, fetched one layer ahead into registers and parked in the other half of a double buffer ----
+  constexpr int NPF = C::NPF;
+  const double* nod_src[NPF];
+  double pf_nod[NPF];
+#pragma unroll
+  for (int r = 0; r < NPF; r++) {
+    const int t = tid + r * NT;
+    nod_src[r] = nullptr;
+    pf_nod[r] = 0.;
+    if (t < C::SZ_NOD) {
+      const int c2 = t % (H2 + 1), c1 = (t / (H2 + 1)) % (H1 + 1), pl = (t / ((H2 + 1) * (H1 + 1))) % 2, i = t / (2 * (H2 + 1) * (H1 + 1));
+      const int v1 = min(max(e1base + c1, 0), n1), v2 = min(max(e2base + c2, 0), n2);
+      nod_src[r] = prm.G.nodes + i * prm.G.nnodes + (long long)pl * prm.G.stride[0] + (long long)v1 * prm.G.stride[1] + v2;
+    }
+  }
+  double pf_tb0 = 0.;
+  int pf_row = 0;
+  auto prefetch = [&](int e) {
+    if (e > eend) return;
+#pragma unroll
+    for (int r = 0; r < NPF; r++)
+      if (nod_src[r]) pf_nod[r] = __ldg(nod_src[r] + (long long)e * prm.G.stride[0]);
+    if (tid < C::SZ_TB0) {
+      const int k = tid & 1, a = (tid >> 1) % NB, q = tid / (2 * NB);
+      pf_tb0 = prm.Q.tab[0][((B.setidx[0][e] * 2 + k) * NB + a) * NQ + q];
+    }
+    if (tid < 4 * NB) {
+      const int a = tid >> 2, w = tid & 3, i0 = e + a;
+      pf_row = w == 0 ? B.lo[0][i0] : w == 1 ? B.wid[0][i0] : w == 2 ? B.cum[0][i0] : 0;
+    }
+  };
+  auto park = [&](int e) {
+    const int buf = e & 1;
+#pragma unroll
+    for (int r = 0; r < NPF; r++)
+      if (nod_src[r]) sNodB[buf * C::SZ_NOD + tid + r * NT] = pf_nod[r];
+    if (tid < C::SZ_TB0) sTb0B[buf * C::SZ_TB0 + tid] = pf_tb0;
+    if (tid < 4 * NB) sRowB[buf * 4 * NB + tid] = pf_row;
+  };
+  prefetch(ebeg);
+  park(ebeg);
 
   // ---- S3 items owned by this thread: dof pairs (i1, j1) x (i2, j2) ----
   bool ivalid[IPT], idiag[IPT];
@@ -163,17 +336,11 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
     }
 
   for (int e0 = ebeg; e0 <= eend; e0++) {
-    // ---- layer tables: nodes of planes e0, e0+1 over the halo, 1-D table of dimension 0 ----
-    for (int t = tid; t < C::SZ_NOD; t += NT) {
-      const int c2 = t % (H2 + 1), c1 = (t / (H2 + 1)) % (H1 + 1), pl = (t / ((H2 + 1) * (H1 + 1))) % 2, i = t / (2 * (H2 + 1) * (H1 + 1));
-      const int v1 = min(max(e1base + c1, 0), n1), v2 = min(max(e2base + c2, 0), n2);
-      sNod[t] = __ldg(prm.G.nodes + i * prm.G.nnodes + (long long)(e0 + pl) * prm.G.stride[0] + (long long)v1 * prm.G.stride[1] + v2);
-    }
-    for (int t = tid; t < C::SZ_TB0; t += NT) {
-      const int k = t & 1, a = (t >> 1) % NB, q = t / (2 * NB);
-      sTb0[t] = prm.Q.tab[0][((B.setidx[0][e0] * 2 + k) * NB + a) * NQ + q];
-    }
-    __syncthreads();
+    const double* sNod = sNodB + (e0 & 1) * C::SZ_NOD;
+    const double* sTb0 = sTb0B + (e0 & 1) * C::SZ_TB0;
+    const int* sRow = sRowB + (e0 & 1) * 4 * NB;
+    prefetch(e0 + 1);   // consumed by park() at the end of this layer
+    __syncthreads();    // tables of this layer parked by all threads; previous layer's stores issued
 
     for (int qc = 0; qc < NQ; qc += QC) {
       // ================= G: geometry at the halo points of QC point-planes =================
@@ -239,123 +406,27 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
       __syncthreads();
 
       // ================= S1: contract Q2 =================
-      for (int wi = warp; wi < T2 * C::WPI1; wi += NW) {
-        const int i2l = wi / C::WPI1, L = (wi % C::WPI1) * 32 + lane, i2 = i2lo + i2l;
+      for (int wi = warp; wi < T2 * C::WPI1 * NPARTS; wi += NW) {
+        const int part = wi % NPARTS, wj = wi / NPARTS;
+        const int i2l = wj / C::WPI1, L = (wj % C::WPI1) * 32 + lane, i2 = i2lo + i2l;
         if (i2 >= nd2) continue;
-        const int q0l = L / NQ1, Q1 = L % NQ1, e1 = e1base + Q1 / NQ;
+        const int e1 = e1base + (L % NQ1) / NQ;
         if (L >= LS || e1 < 0 || e1 >= n1) continue;
-        double t[WD][NTERM > 0 ? NTERM : 1];
-#pragma unroll
-        for (int d = 0; d < WD; d++)
-#pragma unroll
-          for (int m = 0; m < NTERM; m++) t[d][m] = 0.;
-        double l1 = 0.;
-#pragma unroll
-        for (int k = 0; k <= P; k++) {
-          const int e2 = i2 - P + k;
-          if (e2 < 0 || e2 >= n2) continue;
-          constexpr int GS = NQ2 * LS;
-          const int a = P - k, e2l = i2l + k;
-#pragma unroll
-          for (int q2 = 0; q2 < NQ; q2++) {
-            const double* g = sG + (e2l * NQ + q2) * LS + L;
-            const double* tb = sTb2 + (e2l * NQ + q2) * NB * 2;
-            const double va = tb[a * 2], da = tb[a * 2 + 1];
-            const double gm = g[6 * GS];
-            double pa[9];
-            if (FK) {
-              const double g00 = g[0], g01 = g[GS], g02 = g[2 * GS], g11 = g[3 * GS], g12 = g[4 * GS], g22 = g[5 * GS];
-              pa[0] = va * g00; pa[1] = va * g01; pa[2] = va * g11;
-              pa[3] = va * g02; pa[4] = va * g12;
-              pa[5] = da * g02; pa[6] = da * g12;
-              pa[7] = da * g22;
-            }
-            pa[8] = va * gm;
-            l1 += pa[8];
-#pragma unroll
-            for (int b = 0; b <= P; b++) {
-              const double vb = tb[b * 2], db = tb[b * 2 + 1];
-              const int d = b + k;
-              if (FK) {
-                t[d][0] = fma(pa[0], vb, t[d][0]);
-                t[d][1] = fma(pa[1], vb, t[d][1]);
-                t[d][2] = fma(pa[2], vb, t[d][2]);
-                t[d][3] = fma(pa[3], db, t[d][3]);
-                t[d][4] = fma(pa[4], db, t[d][4]);
-                t[d][5] = fma(pa[5], vb, t[d][5]);
-                t[d][6] = fma(pa[6], vb, t[d][6]);
-                t[d][7] = fma(pa[7], db, t[d][7]);
-              }
-              if (FM) t[d][NTK] = fma(pa[8], vb, t[d][NTK]);
-            }
-          }
-        }
-        double* o = sT1 + Q1 * T1QS + q0l * NP2P + i2l * WD;
-#pragma unroll
-        for (int d = 0; d < WD; d++)
-#pragma unroll
-          for (int m = 0; m < NTERM; m++) o[m * L2S + d] = t[d][m];
-        sL1[(Q1 * QC + q0l) * T2 + i2l] = l1;
+        if (NPARTS == 1) s1_item<C, FK, FM, 0, 1>(sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+        else if (part == 0) s1_item<C, FK, FM, 0, 2>(sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+        else s1_item<C, FK, FM, 1, 2>(sG, sTb2, sT1, sL1, i2, i2l, L, n2);
       }
       __syncthreads();
 
       // ================= S2: contract Q1 =================
-      for (int wi = warp; wi < T1 * C::WPI2; wi += NW) {
-        const int i1l = wi / C::WPI2, L = (wi % C::WPI2) * 32 + lane, i1 = i1lo + i1l;
+      for (int wi = warp; wi < T1 * C::WPI2 * NPARTS; wi += NW) {
+        const int part = wi % NPARTS, wj = wi / NPARTS;
+        const int i1l = wj / C::WPI2, L = (wj % C::WPI2) * 32 + lane, i1 = i1lo + i1l;
         if (i1 >= nd1) continue;
-        const int q0l = L / NP2P, pair2 = L % NP2P;
-        if (L >= L2S || pair2 >= NP2) continue;
-        const int i2l = pair2 / WD;
-        const bool diag = (pair2 % WD) == P;
-        double u[WD][NG > 0 ? NG : 1];
-#pragma unroll
-        for (int d = 0; d < WD; d++)
-#pragma unroll
-          for (int m = 0; m < NG; m++) u[d][m] = 0.;
-        double l2 = 0.;
-#pragma unroll
-        for (int k = 0; k <= P; k++) {
-          const int e1 = i1 - P + k;
-          if (e1 < 0 || e1 >= n1) continue;
-          const int a = P - k, e1l = i1l + k;
-#pragma unroll
-          for (int q1 = 0; q1 < NQ; q1++) {
-            const int Q1 = e1l * NQ + q1;
-            const double* x = sT1 + Q1 * T1QS + L;
-            const double* tb = sTb1 + Q1 * NB * 2;
-            const double va = tb[a * 2], da = tb[a * 2 + 1];
-            double X[7];
-            if (FK) {
-              const double A0 = x[0], A1 = x[L2S], A2 = x[2 * L2S], B0 = x[3 * L2S], B1 = x[4 * L2S], C0 = x[5 * L2S], C1 = x[6 * L2S], D = x[7 * L2S];
-              X[0] = va * A0;
-              X[1] = va * A1;
-              X[2] = va * B0;
-              X[3] = fma(da, A1, va * C0);
-              X[4] = fma(da, A2, va * C1);
-              X[5] = fma(da, B1, va * D);
-            }
-            if (FM) X[6] = va * x[NTK * L2S];
-            if (diag) l2 = fma(va, sL1[(Q1 * QC + q0l) * T2 + i2l], l2);
-#pragma unroll
-            for (int b = 0; b <= P; b++) {
-              const double vb = tb[b * 2], db = tb[b * 2 + 1];
-              const int d = b + k;
-              if (FK) {
-                u[d][0] = fma(X[0], vb, u[d][0]);                      // DD
-                u[d][1] = fma(X[1], db, fma(X[2], vb, u[d][1]));       // DV
-                u[d][2] = fma(X[3], vb, u[d][2]);                      // VD
-                u[d][3] = fma(X[4], db, fma(X[5], vb, u[d][3]));       // VV
-              }
-              if (FM) u[d][NGK] = fma(X[6], vb, u[d][NGK]);
-            }
-          }
-        }
-        double* o = sT2 + q0l * NG * N12P + (i1l * WD) * NP2 + pair2;
-#pragma unroll
-        for (int d = 0; d < WD; d++)
-#pragma unroll
-          for (int m = 0; m < NG; m++) o[m * N12P + d * NP2] = u[d][m];
-        if (diag) sL2[(q0l * T1 + i1l) * T2 + i2l] = l2;
+        if (L >= L2S || (L % C::NP2P) >= NP2) continue;
+        if (NPARTS == 1) s2_item<C, FK, FM, 0, 1>(sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+        else if (part == 0) s2_item<C, FK, FM, 0, 2>(sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+        else s2_item<C, FK, FM, 1, 2>(sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
       }
       __syncthreads();
 
@@ -397,16 +468,8 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
     }
 
     // ---- store the completed entries of this layer, carry the rest ----
+    park(e0 + 1);
     const bool last = e0 == n0 - 1;
-    int rlo[NB], rwid[NB];
-    long long rbase[NB];
-#pragma unroll
-    for (int a = 0; a < NB; a++) {
-      const int i0 = e0 + a;
-      rlo[a] = B.lo[0][i0];
-      rwid[a] = B.wid[0][i0];
-      rbase[a] = (long long)B.cum[0][i0] * W12;
-    }
 #pragma unroll
     for (int it = 0; it < IPT; it++) {
       if (ivalid[it]) {
@@ -414,11 +477,12 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
         for (int a = 0; a < NB; a++) {
           const int i0 = e0 + a;
           if (i0 < r0 || i0 >= r1) continue;
-          const long long rowslot = rbase[a] + (long long)rwid[a] * ic12[it] + io12[it];
+          const int rlo = sRow[a * 4], rwid = sRow[a * 4 + 1], rcum = sRow[a * 4 + 2];
+          const long long rowslot = (long long)rcum * W12 + (long long)rwid * ic12[it] + io12[it];
 #pragma unroll
           for (int b = 0; b < NB; b++) {
             if (a == 0 || b == 0 || last) {
-              const long long slot = rowslot + (long long)(e0 + b - rlo[a]) * iw12[it];
+              const long long slot = rowslot + (long long)(e0 + b - rlo) * iw12[it];
               if (FK) prm.valK[slot] = accK[it][a][b];
               if (FM && prm.valM) prm.valM[slot] = accM[it][a][b] * prm.rho;
             }
@@ -537,6 +601,8 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const BasisView& B,
     prm.rhs = F.rhs[0];
     if (!fk && !fm) fm = true, prm.valM = nullptr;  // load vector only: run the mass chain without storing it
   }
-  if (P == 1) return launch_rows_forms<RCfg<1, 6, 6, 2, 256>>(ctx, prm, fk, fm);
-  return launch_rows_forms<RCfg<2, 4, 4, 3, 256>>(ctx, prm, fk, fm);
+  const int64_t variant = ctx->opts.count("rows_variant") ? ctx->opts["rows_variant"] : 0;
+  if (P == 1) return launch_rows_forms<RCfg<1, 8, 8, 2, 512, true>>(ctx, prm, fk, fm);
+  if (variant == 1) return launch_rows_forms<RCfg<2, 4, 4, 3, 256, false>>(ctx, prm, fk, fm);
+  return launch_rows_forms<RCfg<2, 4, 4, 3, 512, true>>(ctx, prm, fk, fm);
 }

@@ -17,6 +17,8 @@ Cs = [engine.form_load(3)]
 dev = torch.device('cuda', 0)
 mats = [torch.empty(plan.nnz, dtype=torch.float64, device=dev) for _ in Ds]
 vecs = [torch.empty(plan.ndofs, dtype=torch.float64, device=dev) for _ in Cs]
+variant = int(os.environ.get('ROWS_VARIANT', 0))
+ctx.set_option('rows_variant', variant)
 for nseg in [int(a) for a in sys.argv[3:]] or [0]:
     ctx.set_option('rows_nseg', nseg)
     for _ in range(2):
@@ -29,4 +31,4 @@ for nseg in [int(a) for a in sys.argv[3:]] or [0]:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
-    print(json.dumps({'n': n, 'p': p, 'nseg': nseg, 'ms': ms, 'dof_per_s': plan.ndofs / ms * 1e3, 'sumM-sumf': float(mats[1].sum() - vecs[0].sum())}))
+    print(json.dumps({'n': n, 'p': p, 'nseg': nseg, 'variant': variant, 'ms': ms, 'dof_per_s': plan.ndofs / ms * 1e3, 'sumM-sumf': float(mats[1].sum() - vecs[0].sum())}))
