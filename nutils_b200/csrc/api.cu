@@ -645,7 +645,7 @@ static int assemble_impl(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis*
   const int64_t kernel_opt = ctx->opts.count("kernel") ? ctx->opts["kernel"] : 0;
   if (rows) {
     if (kernel_opt != 1) {
-      rc = launch_assemble_rows(ctx, basis, B, Q, G, F, D_host, C_host, plane_begin, plane_end);
+      rc = launch_assemble_rows(ctx, basis, quad, B, Q, G, F, D_host, C_host, plane_begin, plane_end);
       if (rc != B2_EUNSUPPORTED) return rc;
       if (kernel_opt >= 2) return b2_fail(ctx, B2_EUNSUPPORTED, "requested specialised kernel does not cover this configuration");
     }

@@ -44,6 +44,10 @@ struct RowParams {
   int has_f, iso;
   double kc[6];  // symmetric conductivity (00,01,02,11,12,22)
   double rho, vcoef;
+  // (value, derivative) of the local functions of the DOMINANT coefficient set of each dimension at the 1-D points,
+  // [dim][q][a][2]: kernel parameters live in the constant bank, so these are free FP64 operands
+  int cset[3];
+  double ctab[3][B2_MAX_DEGREE][B2_MAX_DEGREE][2];
   double* valK;
   double* valM;
   double* rhs;
@@ -58,16 +62,46 @@ struct RCfg {
   static constexpr int NQ1 = H1 * NQ, NQ2 = H2 * NQ;      // halo points
   static constexpr int NP1 = T1 * WD, NP2 = T2 * WD;      // dof pairs (i, i-P..i+P)
   static constexpr int LS = QC * NQ1;                     // S1 lane items (q0, Q1)
-  static constexpr int NP2P = NP2 | 1;                    // odd -> conflict-free T1 stores
+  // T1[Q1][term][q0][pair2] is stored by S1 lanes (q0, Q1) and loaded by S2 lanes (q0, pair2): the paddings NP2P (pairs per
+  // q0) and T1QS (stride per Q1) are chosen so that both are free of bank conflicts (banks = 8-byte index mod 16 per half warp)
+  static constexpr bool t1_ok(int np2p, int t1qs) {
+    for (int h = 0; h * 16 < QC * NQ1; h++) {
+      unsigned used = 0;
+      for (int l = h * 16; l < h * 16 + 16 && l < QC * NQ1; l++) {
+        const int b = ((l % NQ1) * t1qs + (l / NQ1) * np2p) % 16;
+        if (used >> b & 1) return false;
+        used |= 1u << b;
+      }
+    }
+    return true;
+  }
+  static constexpr int pick_np2p() {
+    for (int a = NP2; a < NP2 + 4; a++)
+      for (int b = 9 * QC * a; b < 9 * QC * a + 16; b++)
+        if (t1_ok(a, b)) return a;
+    return NP2 | 1;
+  }
+  static constexpr int NP2P = pick_np2p();
   static constexpr int L2S = QC * NP2P;                   // S2 lane items (q0, pair2)
-  static constexpr int T1QS = (9 * L2S) | 1;              // T1 stride per Q1
+  static constexpr int pick_t1qs() {
+    for (int b = 9 * L2S; b < 9 * L2S + 16; b++)
+      if (t1_ok(NP2P, b)) return b;
+    return (9 * L2S) | 1;
+  }
+  static constexpr int T1QS = pick_t1qs();                // T1 stride per Q1
   static constexpr int N12 = NP1 * NP2;                   // S3 items
   static constexpr int N12P = N12 + 4;
+  static constexpr int pick_t2qs() {                      // T2 stride per q0: lane (q0, pair2) -> consecutive banks
+    for (int b = 5 * N12P; b < 5 * N12P + 16; b++)
+      if (b % 16 == NP2P % 16) return b;
+    return 5 * N12P;
+  }
+  static constexpr int T2QS = pick_t2qs();
   static constexpr int IPT = (N12 + NT - 1) / NT;
   static constexpr int WPI1 = (LS + 31) / 32, WPI2 = (L2S + 31) / 32;
   // shared memory, in doubles
   static constexpr int SZ_G = 7 * NQ2 * LS;
-  static constexpr int SZ_T2 = QC * 5 * N12P;
+  static constexpr int SZ_T2 = QC * T2QS;
   static constexpr int SZ_GT = SZ_G > SZ_T2 ? SZ_G : SZ_T2;  // T2 aliases G
   static constexpr int OFF_T1 = SZ_GT, SZ_T1 = NQ1 * T1QS;
   static constexpr int OFF_L1 = OFF_T1 + SZ_T1, SZ_L1 = NQ1 * QC * T2;
@@ -78,17 +112,19 @@ struct RCfg {
   static constexpr int OFF_TB0 = OFF_TB2 + SZ_TB2, SZ_TB0 = NQ * NB * 2;                 // x2 (double buffer)
   static constexpr int OFF_PW = OFF_TB0 + 2 * SZ_TB0, SZ_PW = 6 * NQ;
   static constexpr int OFF_ROW = OFF_PW + SZ_PW, SZ_ROW = 2 * NB;                        // ints [NB][lo, wid, cum, pad], x2
-  static constexpr int TOTAL = OFF_ROW + 2 * SZ_ROW;
+  static constexpr int MAXL = 512;                                                       // layers per marching segment (sSet0)
+  static constexpr int OFF_SET = OFF_ROW + 2 * SZ_ROW;
+  static constexpr int TOTAL = OFF_SET + MAXL / 2;
   static constexpr int NPF = (SZ_NOD + NT - 1) / NT;                                     // node values prefetched per thread
   static_assert(SZ_TB0 <= NT && 4 * NB <= NT, "layer tables are prefetched by one pass of the CTA");
 };
 
 // ---- S1: contract Q2.  One warp item = (dof i2 of the tile, 32 lanes of (q0, Q1), term group PART) ----
 // terms: 0 A0=G00 v.v  1 A1=G01 v.v  2 A2=G11 v.v  3 B0=G02 v.d  4 B1=G12 v.d  5 C0=G02 d.v  6 C1=G12 d.v  7 D=G22 d.d  (a-side.b-side), NTK: M
-template <class C, bool FK, bool FM, int PART, int NPARTS>
-__device__ __forceinline__ void s1_item(const double* __restrict__ sG, const double* __restrict__ sTb2, double* __restrict__ sT1, double* __restrict__ sL1,
+template <class C, bool FK, bool FM, int PART, int NPARTS, bool CONST>
+__device__ __forceinline__ void s1_item(const RowParams& prm, const double* __restrict__ sG, const double* __restrict__ sTb2, double* __restrict__ sT1, double* __restrict__ sL1,
                                         int i2, int i2l, int L, int n2) {
-  constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, QC = C::QC, T2 = C::T2, NQ1 = C::NQ1, NQ2 = C::NQ2, LS = C::LS;
+  constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, NQ1 = C::NQ1, NQ2 = C::NQ2, LS = C::LS;
   constexpr int NTK = FK ? 8 : 0, GS = NQ2 * LS;
   constexpr bool TA = FK && (NPARTS == 1 || PART == 0), TB = FK && (NPARTS == 1 || PART == 1), TM = NPARTS == 1 || PART == 0;
   const int q0l = L / NQ1, Q1 = L % NQ1;
@@ -107,7 +143,7 @@ __device__ __forceinline__ void s1_item(const double* __restrict__ sG, const dou
     for (int q2 = 0; q2 < NQ; q2++) {
       const double* g = sG + (e2l * NQ + q2) * LS + L;
       const double* tb = sTb2 + (e2l * NQ + q2) * NB * 2;
-      const double va = tb[a * 2], da = tb[a * 2 + 1];
+      const double va = CONST ? prm.ctab[2][q2][a][0] : tb[a * 2], da = CONST ? prm.ctab[2][q2][a][1] : tb[a * 2 + 1];
       double pa[9];
       if (TA) { pa[0] = va * g[0]; pa[1] = va * g[GS]; pa[2] = va * g[3 * GS]; }
       if (TB) {
@@ -117,7 +153,7 @@ __device__ __forceinline__ void s1_item(const double* __restrict__ sG, const dou
       if (TM) { pa[8] = va * g[6 * GS]; l1 += pa[8]; }
 #pragma unroll
       for (int b = 0; b <= P; b++) {
-        const double vb = tb[b * 2], db = tb[b * 2 + 1];
+        const double vb = CONST ? prm.ctab[2][q2][b][0] : tb[b * 2], db = CONST ? prm.ctab[2][q2][b][1] : tb[b * 2 + 1];
         const int d = b + k;
         if (TA) {
           t[d][0] = fma(pa[0], vb, t[d][0]);
@@ -142,16 +178,16 @@ __device__ __forceinline__ void s1_item(const double* __restrict__ sG, const dou
     if (TB) { o[3 * C::L2S + d] = t[d][3]; o[4 * C::L2S + d] = t[d][4]; o[5 * C::L2S + d] = t[d][5]; o[6 * C::L2S + d] = t[d][6]; o[7 * C::L2S + d] = t[d][7]; }
     if (TM && FM) o[NTK * C::L2S + d] = t[d][8];
   }
-  if (TM) sL1[(Q1 * QC + q0l) * T2 + i2l] = l1;
+  if (TM) sL1[i2l * LS + L] = l1;
 }
 
 // ---- S2: contract Q1.  One warp item = (dof i1 of the tile, 32 lanes of (q0, pair2), group set PART) ----
 // groups by the dimension-0 factor still to be applied (a-side, b-side): 0 DD, 1 DV, 2 VD, 3 VV, NGK: M
-template <class C, bool FK, bool FM, int PART, int NPARTS>
-__device__ __forceinline__ void s2_item(const double* __restrict__ sT1, const double* __restrict__ sTb1, const double* __restrict__ sL1, double* __restrict__ sT2,
+template <class C, bool FK, bool FM, int PART, int NPARTS, bool CONST>
+__device__ __forceinline__ void s2_item(const RowParams& prm, const double* __restrict__ sT1, const double* __restrict__ sTb1, const double* __restrict__ sL1, double* __restrict__ sT2,
                                         double* __restrict__ sL2, int i1, int i1l, int L, int n1, bool want_f) {
-  constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, QC = C::QC, T1 = C::T1, T2 = C::T2, NP2 = C::NP2, L2S = C::L2S, N12P = C::N12P;
-  constexpr int NTK = FK ? 8 : 0, NGK = FK ? 4 : 0, NG = NGK + (FM ? 1 : 0);
+  constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, T1 = C::T1, T2 = C::T2, NP2 = C::NP2, L2S = C::L2S, N12P = C::N12P;
+  constexpr int NTK = FK ? 8 : 0, NGK = FK ? 4 : 0;
   constexpr bool GA = FK && (NPARTS == 1 || PART == 0), GB = FK && (NPARTS == 1 || PART == 1), GM = FM && (NPARTS == 1 || PART == 1), GF = NPARTS == 1 || PART == 0;
   const int q0l = L / C::NP2P, pair2 = L % C::NP2P;
   const int i2l = pair2 / WD;
@@ -172,7 +208,7 @@ __device__ __forceinline__ void s2_item(const double* __restrict__ sT1, const do
       const int Q1 = e1l * NQ + q1;
       const double* x = sT1 + Q1 * C::T1QS + L;
       const double* tb = sTb1 + Q1 * NB * 2;
-      const double va = tb[a * 2], da = tb[a * 2 + 1];
+      const double va = CONST ? prm.ctab[1][q1][a][0] : tb[a * 2], da = CONST ? prm.ctab[1][q1][a][1] : tb[a * 2 + 1];
       double X[7];
       if (GA) {
         const double A0 = x[0], A1 = x[L2S], B0 = x[3 * L2S], C0 = x[5 * L2S];
@@ -183,10 +219,10 @@ __device__ __forceinline__ void s2_item(const double* __restrict__ sT1, const do
         X[4] = fma(da, A2, va * C1); X[5] = fma(da, B1, va * D);
       }
       if (GM) X[6] = va * x[NTK * L2S];
-      if (diag) l2 = fma(va, sL1[(Q1 * QC + q0l) * T2 + i2l], l2);
+      if (diag) l2 = fma(va, sL1[i2l * C::LS + q0l * C::NQ1 + Q1], l2);
 #pragma unroll
       for (int b = 0; b <= P; b++) {
-        const double vb = tb[b * 2], db = tb[b * 2 + 1];
+        const double vb = CONST ? prm.ctab[1][q1][b][0] : tb[b * 2], db = CONST ? prm.ctab[1][q1][b][1] : tb[b * 2 + 1];
         const int d = b + k;
         if (GA) {
           u[d][0] = fma(X[0], vb, u[d][0]);
@@ -198,7 +234,7 @@ __device__ __forceinline__ void s2_item(const double* __restrict__ sT1, const do
       }
     }
   }
-  double* o = sT2 + q0l * NG * N12P + (i1l * WD) * NP2 + pair2;
+  double* o = sT2 + q0l * C::T2QS + (i1l * WD) * NP2 + pair2;
 #pragma unroll
   for (int d = 0; d < WD; d++) {
     if (GA) { o[0 * N12P + d * NP2] = u[d][0]; o[1 * N12P + d * NP2] = u[d][1]; o[2 * N12P + d * NP2] = u[d][2]; }
@@ -214,7 +250,7 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
   constexpr int T1 = C::T1, T2 = C::T2, H1 = C::H1, H2 = C::H2, NQ1 = C::NQ1, NQ2 = C::NQ2;
   constexpr int NP2 = C::NP2, LS = C::LS, L2S = C::L2S;
   constexpr int N12 = C::N12, N12P = C::N12P, IPT = C::IPT;
-  constexpr int NGK = FK ? 4 : 0, NG = NGK + (FM ? 1 : 0);  // S2 output groups
+  constexpr int NGK = FK ? 4 : 0;  // S2 output groups: DD DV VD VV [M]
   constexpr int NPARTS = (C::SPLIT && FK) ? 2 : 1;
   const BasisView& B = prm.B;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -223,7 +259,7 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
   double* sG = smem;                  // [7][NQ2][LS]
   double* sT2 = smem;                 // [QC][NG][N12P]   (aliases sG)
   double* sT1 = smem + C::OFF_T1;     // [NQ1][T1QS] = [NQ1][term][q0 NP2P + pair2]
-  double* sL1 = smem + C::OFF_L1;     // [NQ1][QC][T2]
+  double* sL1 = smem + C::OFF_L1;     // [T2][QC][NQ1]
   double* sL2 = smem + C::OFF_L2;     // [QC][T1][T2]
   double* sNodB = smem + C::OFF_NOD;  // 2 x [3][2][H1+1][H2+1]
   double* sTb1 = smem + C::OFF_TB1;   // [H1][NQ][NB][2]  (value, derivative) of local function a at point q of halo element
@@ -232,6 +268,7 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
   double* sPt = smem + C::OFF_PW;     // [3][NQ]
   double* sWt = sPt + 3 * NQ;         // [3][NQ]
   int* sRowB = reinterpret_cast<int*>(smem + C::OFF_ROW);  // 2 x [NB][4] = lo, wid, cum of dof e0+a along dimension 0
+  int* sSet0 = reinterpret_cast<int*>(smem + C::OFF_SET);  // [MAXL] coefficient set of the layers of this segment
 
   // ---- work unit ----
   const int t2 = blockIdx.x % prm.tiles2, t1 = (blockIdx.x / prm.tiles2) % prm.tiles1, seg = blockIdx.x / (prm.tiles2 * prm.tiles1);
@@ -257,6 +294,14 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
     sPt[t] = prm.Q.x[t / NQ][t % NQ];
     sWt[t] = prm.Q.w[t / NQ][t % NQ];
   }
+  for (int t = tid; t <= eend - ebeg; t += NT) sSet0[t] = B.setidx[0][ebeg + t];
+  // do all elements of the halo carry the dominant coefficient set?  (then S1/S2 take their 1-D factors from the constant bank)
+  bool mine = true;
+  if (tid < H1) { const int e = e1base + tid; if (e >= 0 && e < n1 && B.setidx[1][e] != prm.cset[1]) mine = false; }
+  const bool uni1 = __syncthreads_and(mine);
+  mine = true;
+  if (tid < H2) { const int e = e2base + tid; if (e >= 0 && e < n2 && B.setidx[2][e] != prm.cset[2]) mine = false; }
+  const bool uni2 = __syncthreads_and(mine);
 
   // ---- layer tables (nodes of planes e0, e0+1 over the halo; 1-D table and CSR row data of dimension 0): one value per
   //      thread, fetched one layer ahead into registers and parked in the other half of a double buffer ----
@@ -283,7 +328,7 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
       if (nod_src[r]) pf_nod[r] = __ldg(nod_src[r] + (long long)e * prm.G.stride[0]);
     if (tid < C::SZ_TB0) {
       const int k = tid & 1, a = (tid >> 1) % NB, q = tid / (2 * NB);
-      pf_tb0 = prm.Q.tab[0][((B.setidx[0][e] * 2 + k) * NB + a) * NQ + q];
+      pf_tb0 = prm.Q.tab[0][((sSet0[e - ebeg] * 2 + k) * NB + a) * NQ + q];
     }
     if (tid < 4 * NB) {
       const int a = tid >> 2, w = tid & 3, i0 = e + a;
@@ -412,9 +457,15 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
         if (i2 >= nd2) continue;
         const int e1 = e1base + (L % NQ1) / NQ;
         if (L >= LS || e1 < 0 || e1 >= n1) continue;
-        if (NPARTS == 1) s1_item<C, FK, FM, 0, 1>(sG, sTb2, sT1, sL1, i2, i2l, L, n2);
-        else if (part == 0) s1_item<C, FK, FM, 0, 2>(sG, sTb2, sT1, sL1, i2, i2l, L, n2);
-        else s1_item<C, FK, FM, 1, 2>(sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+        if (uni2) {
+          if (NPARTS == 1) s1_item<C, FK, FM, 0, 1, true>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+          else if (part == 0) s1_item<C, FK, FM, 0, 2, true>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+          else s1_item<C, FK, FM, 1, 2, true>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+        } else {
+          if (NPARTS == 1) s1_item<C, FK, FM, 0, 1, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+          else if (part == 0) s1_item<C, FK, FM, 0, 2, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+          else s1_item<C, FK, FM, 1, 2, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+        }
       }
       __syncthreads();
 
@@ -424,9 +475,15 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
         const int i1l = wj / C::WPI2, L = (wj % C::WPI2) * 32 + lane, i1 = i1lo + i1l;
         if (i1 >= nd1) continue;
         if (L >= L2S || (L % C::NP2P) >= NP2) continue;
-        if (NPARTS == 1) s2_item<C, FK, FM, 0, 1>(sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
-        else if (part == 0) s2_item<C, FK, FM, 0, 2>(sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
-        else s2_item<C, FK, FM, 1, 2>(sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+        if (uni1) {
+          if (NPARTS == 1) s2_item<C, FK, FM, 0, 1, true>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+          else if (part == 0) s2_item<C, FK, FM, 0, 2, true>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+          else s2_item<C, FK, FM, 1, 2, true>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+        } else {
+          if (NPARTS == 1) s2_item<C, FK, FM, 0, 1, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+          else if (part == 0) s2_item<C, FK, FM, 0, 2, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+          else s2_item<C, FK, FM, 1, 2, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+        }
       }
       __syncthreads();
 
@@ -443,7 +500,7 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
         for (int it = 0; it < IPT; it++) {
           const int item = tid + it * NT;
           if (item < N12) {
-            const double* x = sT2 + q0l * NG * N12P + item;
+            const double* x = sT2 + q0l * C::T2QS + item;
             double gDD = 0., gDV = 0., gVD = 0., gVV = 0., gM = 0.;
             if (FK) { gDD = x[0]; gDV = x[N12P]; gVD = x[2 * N12P]; gVV = x[3 * N12P]; }
             if (FM) gM = x[NGK * N12P];
@@ -518,11 +575,13 @@ int launch_rows_cfg(b2_ctx* ctx, RowParams& prm) {
   double bestcost = 1e300;
   const int64_t forced = ctx->opts.count("rows_nseg") ? ctx->opts["rows_nseg"] : 0;
   for (int s = 1; s <= 64 && s <= npl; s++) {
+    if ((npl + s - 1) / s + C::P > C::MAXL) continue;  // sSet0 holds the layers of one segment
     const long long waves = (tiles * s + slots - 1) / slots;
     const double cost = (double)waves * ((double)(npl + s - 1) / s + C::P + 1.5);  // +1.5: per-CTA set-up in layer units
     if (cost < bestcost) { bestcost = cost; best = s; }
   }
   prm.nseg = forced > 0 ? (int)std::min<int64_t>(forced, npl) : best;
+  if ((npl + prm.nseg - 1) / prm.nseg + C::P > C::MAXL) prm.nseg = (int)((npl + C::MAXL - C::P - 1) / (C::MAXL - C::P));
   const long long blocks = tiles * prm.nseg;
   if (blocks > 0x7fffffffLL) return B2_EUNSUPPORTED;
   {
@@ -545,7 +604,7 @@ int launch_rows_forms(b2_ctx* ctx, RowParams& prm, bool fk, bool fm) {
 
 // Owner-computes assembly of the dof planes [plane_begin, plane_end) of dimension 0.  Returns
 // B2_EUNSUPPORTED when the configuration is outside the specialised kernel (caller falls back).
-int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const BasisView& B, const QuadView& Q, const GeomView& G, const FormView& F,
+int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad, const BasisView& B, const QuadView& Q, const GeomView& G, const FormView& F,
                          const double* const* D_host, const double* const* C_host, long long plane_begin, long long plane_end) {
   if (B.ndims != 3 || B.ncomp != 1) return B2_EUNSUPPORTED;
   const int P = B.p[0];
@@ -591,6 +650,22 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const BasisView& B,
       prm.rho = D[0];
       prm.valM = F.values[m];
     }
+  }
+  // dominant coefficient set per dimension and its table at the 1-D points (host copy of what get_tabs uploaded)
+  for (int d = 0; d < 3; d++) {
+    std::vector<int> count(basis->nsets[d], 0);
+    for (int e = 0; e < B.nel[d]; e++) count[basis->setidx[d][e]]++;
+    const int cs = (int)(std::max_element(count.begin(), count.end()) - count.begin());
+    prm.cset[d] = cs;
+    for (int q = 0; q <= P; q++)
+      for (int a = 0; a <= P; a++) {
+        const double* c = &basis->coeffs[d][((size_t)cs * (P + 1) + a) * (P + 1)];
+        const double x = quad->pts[d][q];
+        double v = c[0], g = 0.;
+        for (int j = 1; j <= P; j++) { g = g * x + v; v = v * x + c[j]; }
+        prm.ctab[d][q][a][0] = v;
+        prm.ctab[d][q][a][1] = g;
+      }
   }
   prm.iso = prm.kc[1] == 0. && prm.kc[2] == 0. && prm.kc[4] == 0. && prm.kc[0] == prm.kc[3] && prm.kc[0] == prm.kc[5];
   if (F.nvec) {

@@ -163,7 +163,7 @@ int launch_assemble_fast(b2_ctx* ctx, const BasisView& B, const QuadView& Q, con
                          const double* const* D_host, const double* const* C_host, long long elem_begin, long long elem_end);
 
 // owner-computes kernel: WRITES every stored value of the dof planes [plane_begin, plane_end) of dimension 0
-int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const BasisView& B, const QuadView& Q, const GeomView& G, const FormView& F,
+int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad, const BasisView& B, const QuadView& Q, const GeomView& G, const FormView& F,
                          const double* const* D_host, const double* const* C_host, long long plane_begin, long long plane_end);
 
 // ---- device helpers ------------------------------------------------------------------------------
