@@ -6,10 +6,13 @@
 Workload (BASELINE.json configs[1]): 3-D Poisson on a structured n^3 grid (default 128^3), degree-2
 B-splines, Gauss degree 4 (27 points), stiffness K + mass M + load vector f in ONE pass, on the
 GENERAL-geometry code path: a multilinear nodal geometry whose nodes are perturbed, so every
-element has its own per-point Jacobians (no uniform-mesh shortcut).  A "step" = zero the outputs +
-one assembly pass.  N>1 (torchrun): weak scaling, rank r owns an n^3 slab of an (N n) x n x n mesh,
-integrates it into its window of the global CSR and exchanges the shared dof planes with its
-neighbours (one batched NCCL send/recv).
+element has its own per-point Jacobians (no uniform-mesh shortcut).  A "step" = one owner-computes
+assembly pass (b2_assemble_rows_device): every stored value of K, M and f is written exactly once,
+so there is no zero-fill.  N>1 (torchrun): weak scaling on an (N n) x n x n mesh, rank r owns 1/N of
+the dof planes along x and the CSR rows that go with them and integrates the two element layers
+below its first plane again instead of communicating -- no collective on the data path
+(nutils_b200.distributed.PlaneLayout).  --path scatter selects the element-scatter kernels
+(zero-fill + atomics + neighbour exchange over NCCL) for comparison.
 
 Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, device-timed (CUDA events, max over
 ranks).  `e2e`: the same pass through the host-buffer C-ABI call (b2_assemble_host) including the
@@ -166,7 +169,8 @@ def run_b200(args):
     rules = points.tensor_gauss(3, 2 * p)
     nodes = make_nodes(shape)
     plan = engine.Plan(ctx, b1, rules, nodes)
-    layout = distributed.SlabLayout(b1, 1, rank, world, plan.row_offset)
+    rows_path = args.path == 'rows'
+    layout = (distributed.PlaneLayout if rows_path else distributed.SlabLayout)(b1, 1, rank, world, plan.row_offset)
     Ds = [engine.form_stiffness(3), engine.form_mass(3)]
     Cs = [engine.form_load(3)]
     dev = torch.device('cuda', local)
@@ -177,11 +181,14 @@ def run_b200(args):
     vptr = [v.data_ptr() - 8 * layout.row_lo for v in vecs]
 
     def step():
-        for t in mats + vecs:
-            t.zero_()
-        plan.assemble_device(Ds, Cs, mptr, vptr, elem_range=layout.elem_range)
-        if world > 1:
-            distributed.exchange_interfaces(layout, mats, vecs)
+        if rows_path:
+            plan.assemble_rows_device(Ds, Cs, mptr, vptr, plane_range=layout.plane_range)
+        else:
+            for t in mats + vecs:
+                t.zero_()
+            plan.assemble_device(Ds, Cs, mptr, vptr, elem_range=layout.elem_range)
+            if world > 1:
+                distributed.exchange_interfaces(layout, mats, vecs)
 
     def barrier():
         torch.cuda.synchronize()
@@ -223,7 +230,7 @@ def run_b200(args):
     fsum = float(vecs[0].sum()) if world == 1 else None
 
     # roofline of the assembly kernel (rank-local bytes / rank-local kernel time)
-    nnodes_local = (layout.elem_range[1] - layout.elem_range[0]) // (n * n) + 1
+    nnodes_local = (layout.elem_layers[1] - layout.elem_layers[0] if rows_path else (layout.elem_range[1] - layout.elem_range[0]) // (n * n)) + 1
     alg_bytes = 8. * (len(Ds) * layout.nvalues + len(Cs) * layout.nrows + 3 * nnodes_local * (n + 1) * (n + 1))
     kernel_avg_ms = kernel_ms / max(kernel_launches, 1)
     peaks = {}
@@ -235,7 +242,8 @@ def run_b200(args):
     achieved = alg_bytes / (kernel_avg_ms * 1e-3) / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (of fallback)',
-                'kernel': 'assembly kernel (zero-fill excluded)', 'kernel_ms': kernel_avg_ms, 'algorithmic_bytes': alg_bytes,
+                'kernel': 'k_rows3d (owner-computes assembly kernel; the only kernel of the step)' if rows_path else 'assembly kernel (zero-fill excluded)',
+                'secondary_ceiling': 'FP64 pipe: the kernel issues ~1.46e9 warp-level FP64 instructions at 128^3 (see DESIGN.md), 2.5 ms at the measured 33.8 TFLOP/s DFMA rate', 'kernel_ms': kernel_avg_ms, 'algorithmic_bytes': alg_bytes,
                 'kernel_share_of_step': kernel_avg_ms / ms_per_step}
 
     # end-to-end through the host-buffer C-ABI call (single GPU path; ranks run it on their own slab problem)
@@ -282,9 +290,10 @@ def run_b200(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': workload_name(n, p, world), 'ndofs': ndofs_global, 'nnz_per_matrix': plan.nnz, 'nelems': plan.ntotal,
-                       'step': 'zero K,M,f + one assembly launch' + (' + neighbour exchange of shared dof planes (NCCL send/recv)' if world > 1 else ''),
+                       'step': ('one owner-computes assembly launch (every value written once; no zero-fill, no exchange)' if rows_path else
+                                'zero K,M,f + one assembly launch' + (' + neighbour exchange of shared dof planes (NCCL send/recv)' if world > 1 else '')),
                        'l2': 'outputs {:.2f} GB per rank >> 126 MB L2 (no flush needed)'.format(8e-9 * (len(Ds) * layout.nvalues + layout.nrows)),
-                       'parallelism': 'element slabs along x, one rank per GPU' if world > 1 else 'single GPU'},
+                       'parallelism': ('dof planes along x owned per rank, overlap layers re-integrated, no collective' if rows_path else 'element slabs along x, one rank per GPU') if world > 1 else 'single GPU'},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clk,
         }
         if msum is not None:
@@ -307,6 +316,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--path', default='rows', choices=['rows', 'scatter'], help='rows: owner-computes kernel (default); scatter: element-scatter kernels')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3

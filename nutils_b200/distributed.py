@@ -1,4 +1,11 @@
-'''Multi-GPU assembly: element slabs per rank, one neighbour exchange on the shared dof rows.
+'''Multi-GPU assembly.  Two decompositions of the same structured problem:
+
+* :class:`PlaneLayout` (default, owner-computes): a rank OWNS a contiguous range of dof planes of dimension 0 and the
+  rows of the global CSR that go with them; b2_assemble_rows_device writes every value of those rows exactly once,
+  integrating the <= degree element layers below its first plane a second time instead of communicating.  There is NO
+  collective on the data path; the matrix stays distributed by rows (what a distributed solver wants).
+* :class:`SlabLayout` + :func:`exchange_interfaces` (element-scatter kernels, any configuration): element slabs per
+  rank, one neighbour exchange on the shared dof rows, described below.
 
 The reference's only parallelism is a fork-parallel element loop with shared-memory outputs
 (src/nutils/parallel.py:27-154).  Here elements are partitioned into contiguous slabs along the
@@ -17,6 +24,40 @@ def slab_ranges(n0, world):
     'balanced contiguous ranges of the slowest element index'
     cuts = [(n0 * r) // world for r in range(world + 1)]
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def plane_ranges(ndofs0, world):
+    'balanced contiguous ranges of the dof planes of dimension 0'
+    cuts = [(ndofs0 * r) // world for r in range(world + 1)]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+class PlaneLayout:
+    '''Index arithmetic of one rank's rows under the owner-computes decomposition.
+
+    plane_range : dof planes [p0, p1) of dimension 0 owned by this rank (pass to Plan.assemble_rows_device)
+    row_lo/hi   : the rows [row_lo, row_hi) of the global matrix, off_lo/hi = rowptr[row_lo], rowptr[row_hi]
+    nvalues     : stored values of the window; global slot s lives at window[s - off_lo]
+    elem_layers : element layers [e0, e1) of dimension 0 the rank integrates (its own + the overlap below/above)
+    '''
+
+    def __init__(self, bases1d, ncomp, rank, world, row_offset):
+        b0 = bases1d[0]
+        self.rank, self.world = rank, world
+        ranges = plane_ranges(b0.ndofs, world)
+        if any(b <= a for a, b in ranges):
+            raise ValueError('more ranks than dof planes')
+        nrest_d = int(numpy.prod([b.ndofs for b in bases1d[1:]])) * ncomp
+        p0, p1 = ranges[rank]
+        self.plane_range = p0, p1
+        self.row_lo, self.row_hi = p0 * nrest_d, p1 * nrest_d
+        self.off_lo, self.off_hi = row_offset(self.row_lo), row_offset(self.row_hi)
+        self.nvalues = self.off_hi - self.off_lo
+        self.nrows = self.row_hi - self.row_lo
+        start = numpy.asarray(b0.start)
+        touching = numpy.nonzero((start < p1) & (start + b0.degree >= p0))[0]
+        self.elem_layers = (int(touching[0]), int(touching[-1]) + 1) if len(touching) else (0, 0)
+        self.neighbours = []  # nothing to exchange
 
 
 class SlabLayout:
