@@ -240,7 +240,13 @@ def run_b200(args):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.))
     achieved = alg_bytes / (kernel_avg_ms * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel at the default workload
+    if rows_path and world == 1 and n == 128 and p == 2:
+        try:
+            traffic = float(json.load(open(os.path.join(ROOT, 'profiles', 'r01', 'traffic.json')))['traffic_bytes'])
+        except (OSError, ValueError, KeyError):
+            pass
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (of fallback)',
                 'kernel': 'k_rows3d (owner-computes assembly kernel; the only kernel of the step)' if rows_path else 'assembly kernel (zero-fill excluded)',
                 'secondary_ceiling': 'FP64 pipe: the kernel issues ~1.46e9 warp-level FP64 instructions at 128^3 (see DESIGN.md), 2.5 ms at the measured 33.8 TFLOP/s DFMA rate', 'kernel_ms': kernel_avg_ms, 'algorithmic_bytes': alg_bytes,
