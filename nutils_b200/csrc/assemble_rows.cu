@@ -57,6 +57,8 @@ template <int P_, int T1_, int T2_, int QC_, int NT_, bool SPLIT_>
 struct RCfg {
   static constexpr int P = P_, NB = P + 1, NQ = P + 1, WD = 2 * P + 1;
   static constexpr int T1 = T1_, T2 = T2_, QC = QC_, NT = NT_, NW = NT / 32;
+  // one CTA per SM; the register file is split over the 4 sub-partitions (16384 each), warps are dealt round-robin
+  static constexpr int MAXREG = (16384 / ((NW + 3) / 4) / 32 / 8 * 8) > 255 ? 255 : (16384 / ((NW + 3) / 4) / 32 / 8 * 8);
   static constexpr bool SPLIT = SPLIT_;                   // S1/S2 warp items split in two term groups (more warps, fewer registers)
   static constexpr int H1 = T1 + P, H2 = T2 + P;          // halo elements per tile dimension
   static constexpr int NQ1 = H1 * NQ, NQ2 = H2 * NQ;      // halo points
@@ -102,8 +104,8 @@ struct RCfg {
   // shared memory, in doubles
   static constexpr int SZ_G = 7 * NQ2 * LS;
   static constexpr int SZ_T2 = QC * T2QS;
-  static constexpr int SZ_GT = SZ_G > SZ_T2 ? SZ_G : SZ_T2;  // T2 aliases G
-  static constexpr int OFF_T1 = SZ_GT, SZ_T1 = NQ1 * T1QS;
+  static constexpr int OFF_G = 0, OFF_T2 = SZ_G;             // separate buffers: G(l+1) is produced while T2(l) is consumed
+  static constexpr int OFF_T1 = SZ_G + SZ_T2, SZ_T1 = NQ1 * T1QS;
   static constexpr int OFF_L1 = OFF_T1 + SZ_T1, SZ_L1 = NQ1 * QC * T2;
   static constexpr int OFF_L2 = OFF_L1 + SZ_L1, SZ_L2 = QC * T1 * T2;
   static constexpr int OFF_NOD = OFF_L2 + SZ_L2, SZ_NOD = 3 * 2 * (H1 + 1) * (H2 + 1);   // x2 (double buffer)
@@ -114,7 +116,8 @@ struct RCfg {
   static constexpr int OFF_ROW = OFF_PW + SZ_PW, SZ_ROW = 2 * NB;                        // ints [NB][lo, wid, cum, pad], x2
   static constexpr int MAXL = 512;                                                       // layers per marching segment (sSet0)
   static constexpr int OFF_SET = OFF_ROW + 2 * SZ_ROW;
-  static constexpr int TOTAL = OFF_SET + MAXL / 2;
+  static constexpr int OFF_IC = OFF_SET + MAXL / 2 + 2;                                  // [IPT][NT] 64-bit row-start factors of the S3 items
+  static constexpr int TOTAL = OFF_IC + IPT * NT;
   static constexpr int NPF = (SZ_NOD + NT - 1) / NT;                                     // node values prefetched per thread
   static_assert(SZ_TB0 <= NT && 4 * NB <= NT, "layer tables are prefetched by one pass of the CTA");
 };
@@ -126,7 +129,9 @@ __device__ __forceinline__ void s1_item(const RowParams& prm, const double* __re
                                         int i2, int i2l, int L, int n2) {
   constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, NQ1 = C::NQ1, NQ2 = C::NQ2, LS = C::LS;
   constexpr int NTK = FK ? 8 : 0, GS = NQ2 * LS;
-  constexpr bool TA = FK && (NPARTS == 1 || PART == 0), TB = FK && (NPARTS == 1 || PART == 1), TM = NPARTS == 1 || PART == 0;
+  // term groups: TA = {A0,A1,A2} (v.v), TB = {B0,B1} (v.d) with the mass term and the load chain, TC = {C0,C1,D} (d.*)
+  constexpr bool TA = FK && (NPARTS == 1 || PART == 0), TB = FK && (NPARTS == 1 || PART == 1), TC = FK && (NPARTS == 1 || PART == 2);
+  constexpr bool TM = NPARTS == 1 || PART == 1;
   const int q0l = L / NQ1, Q1 = L % NQ1;
   double t[WD][9];
 #pragma unroll
@@ -146,10 +151,8 @@ __device__ __forceinline__ void s1_item(const RowParams& prm, const double* __re
       const double va = CONST ? prm.ctab[2][q2][a][0] : tb[a * 2], da = CONST ? prm.ctab[2][q2][a][1] : tb[a * 2 + 1];
       double pa[9];
       if (TA) { pa[0] = va * g[0]; pa[1] = va * g[GS]; pa[2] = va * g[3 * GS]; }
-      if (TB) {
-        const double g02 = g[2 * GS], g12 = g[4 * GS], g22 = g[5 * GS];
-        pa[3] = va * g02; pa[4] = va * g12; pa[5] = da * g02; pa[6] = da * g12; pa[7] = da * g22;
-      }
+      if (TB) { pa[3] = va * g[2 * GS]; pa[4] = va * g[4 * GS]; }
+      if (TC) { pa[5] = da * g[2 * GS]; pa[6] = da * g[4 * GS]; pa[7] = da * g[5 * GS]; }
       if (TM) { pa[8] = va * g[6 * GS]; l1 += pa[8]; }
 #pragma unroll
       for (int b = 0; b <= P; b++) {
@@ -163,6 +166,8 @@ __device__ __forceinline__ void s1_item(const RowParams& prm, const double* __re
         if (TB) {
           t[d][3] = fma(pa[3], db, t[d][3]);
           t[d][4] = fma(pa[4], db, t[d][4]);
+        }
+        if (TC) {
           t[d][5] = fma(pa[5], vb, t[d][5]);
           t[d][6] = fma(pa[6], vb, t[d][6]);
           t[d][7] = fma(pa[7], db, t[d][7]);
@@ -175,7 +180,8 @@ __device__ __forceinline__ void s1_item(const RowParams& prm, const double* __re
 #pragma unroll
   for (int d = 0; d < WD; d++) {
     if (TA) { o[0 * C::L2S + d] = t[d][0]; o[1 * C::L2S + d] = t[d][1]; o[2 * C::L2S + d] = t[d][2]; }
-    if (TB) { o[3 * C::L2S + d] = t[d][3]; o[4 * C::L2S + d] = t[d][4]; o[5 * C::L2S + d] = t[d][5]; o[6 * C::L2S + d] = t[d][6]; o[7 * C::L2S + d] = t[d][7]; }
+    if (TB) { o[3 * C::L2S + d] = t[d][3]; o[4 * C::L2S + d] = t[d][4]; }
+    if (TC) { o[5 * C::L2S + d] = t[d][5]; o[6 * C::L2S + d] = t[d][6]; o[7 * C::L2S + d] = t[d][7]; }
     if (TM && FM) o[NTK * C::L2S + d] = t[d][8];
   }
   if (TM) sL1[i2l * LS + L] = l1;
@@ -244,20 +250,121 @@ __device__ __forceinline__ void s2_item(const RowParams& prm, const double* __re
   if (diag) sL2[(q0l * T1 + i1l) * T2 + i2l] = l2;
 }
 
+// ---- G: geometry of one (Q1, Q2) column of the halo, all QC = NQ points q0 of the layer ----
+// Trilinear map x = sum_v phi_v X_v of the element: the interpolations along dimensions 2 and 1 are shared by the points of the
+// column (J[:,0] does not depend on xi0; J[:,1], J[:,2] are linear in xi0); adj(J), det and Ghat = w/|det| adj K adj^T per point.
+template <class C, bool FK>
+__device__ __forceinline__ void g_column(const RowParams& prm, const double* __restrict__ sNod, const double* __restrict__ sPt, const double* __restrict__ sWt,
+                                         double* __restrict__ sG, int col, int e1base, int e2base, int n1, int n2) {
+  constexpr int NQ = C::NQ, H1 = C::H1, H2 = C::H2, NQ1 = C::NQ1, NQ2 = C::NQ2, LS = C::LS, GS = NQ2 * LS;
+  const int Q2 = col / NQ1, Q1 = col % NQ1;
+  const int e1l = Q1 / NQ, q1 = Q1 % NQ, e2l = Q2 / NQ, q2 = Q2 % NQ;
+  const int e1 = e1base + e1l, e2 = e2base + e2l;
+  if (e1 < 0 || e1 >= n1 || e2 < 0 || e2 >= n2) return;
+  const double x1 = sPt[NQ + q1], x2 = sPt[2 * NQ + q2];
+  const double w12 = sWt[NQ + q1] * sWt[2 * NQ + q2];
+  double J0[3], D1a[3], D1d[3], D2a[3], D2d[3];  // J[:,0]; J[:,k](xi0) = Dka + xi0 Dkd
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double* X = sNod + (i * 2 * (H1 + 1) + e1l) * (H2 + 1) + e2l;
+    constexpr int SP = (H1 + 1) * (H2 + 1), S1 = H2 + 1;
+    const double c000 = X[0], c001 = X[1], c010 = X[S1], c011 = X[S1 + 1];
+    const double c100 = X[SP], c101 = X[SP + 1], c110 = X[SP + S1], c111 = X[SP + S1 + 1];
+    const double d00 = c001 - c000, d01 = c011 - c010, d10 = c101 - c100, d11 = c111 - c110;                              // d/dxi2 on the 4 edges
+    const double m00 = fma(x2, d00, c000), m01 = fma(x2, d01, c010), m10 = fma(x2, d10, c100), m11 = fma(x2, d11, c110);  // values at xi2
+    const double g0 = fma(x1, d01 - d00, d00), g1 = fma(x1, d11 - d10, d10);                                              // d/dxi2 at (xi1, xi2), planes 0/1
+    const double f0 = m01 - m00, f1 = m11 - m10;                                                                          // d/dxi1 at xi2, planes 0/1
+    const double h0 = fma(x1, f0, m00), h1 = fma(x1, f1, m10);                                                            // values at (xi1, xi2)
+    J0[i] = h1 - h0;
+    D1a[i] = f0; D1d[i] = f1 - f0;
+    D2a[i] = g0; D2d[i] = g1 - g0;
+  }
+  double* g = sG + Q2 * LS + Q1;
+  // pass 1: A[0] = J[:,1] x J[:,2], det = J[:,0] . A[0] and the scale w/|det| of every point -- the reciprocal chains interleave
+  double A0[NQ][3], sc[NQ], wd[NQ];
+#pragma unroll
+  for (int q0 = 0; q0 < NQ; q0++) {
+    const double x0 = sPt[q0];
+    double J1[3], J2[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      J1[i] = fma(x0, D1d[i], D1a[i]);
+      J2[i] = fma(x0, D2d[i], D2a[i]);
+    }
+    A0[q0][0] = J1[1] * J2[2] - J1[2] * J2[1];
+    A0[q0][1] = J1[2] * J2[0] - J1[0] * J2[2];
+    A0[q0][2] = J1[0] * J2[1] - J1[1] * J2[0];
+  }
+#pragma unroll
+  for (int q0 = 0; q0 < NQ; q0++) {
+    const double det = J0[0] * A0[q0][0] + J0[1] * A0[q0][1] + J0[2] * A0[q0][2];
+    const double adet = fabs(det), w = sWt[q0] * w12;
+    sc[q0] = w / adet;
+    wd[q0] = w * adet;
+  }
+  // pass 2: the other two adjugate rows A[1] = J[:,2] x J[:,0], A[2] = J[:,0] x J[:,1] and Ghat = s A K A^T
+#pragma unroll
+  for (int q0 = 0; q0 < NQ; q0++) {
+    const double x0 = sPt[q0];
+    double J1[3], J2[3], A[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      J1[i] = fma(x0, D1d[i], D1a[i]);
+      J2[i] = fma(x0, D2d[i], D2a[i]);
+      A[i] = A0[q0][i];
+    }
+    A[3] = J2[1] * J0[2] - J2[2] * J0[1]; A[4] = J2[2] * J0[0] - J2[0] * J0[2]; A[5] = J2[0] * J0[1] - J2[1] * J0[0];
+    A[6] = J0[1] * J1[2] - J0[2] * J1[1]; A[7] = J0[2] * J1[0] - J0[0] * J1[2]; A[8] = J0[0] * J1[1] - J0[1] * J1[0];
+    double* o = g + q0 * NQ1;
+    if (FK) {
+      const double s = sc[q0];
+      if (prm.iso) {
+        const double sk = s * prm.kc[0];
+        o[0 * GS] = sk * (A[0] * A[0] + A[1] * A[1] + A[2] * A[2]);
+        o[1 * GS] = sk * (A[0] * A[3] + A[1] * A[4] + A[2] * A[5]);
+        o[2 * GS] = sk * (A[0] * A[6] + A[1] * A[7] + A[2] * A[8]);
+        o[3 * GS] = sk * (A[3] * A[3] + A[4] * A[4] + A[5] * A[5]);
+        o[4 * GS] = sk * (A[3] * A[6] + A[4] * A[7] + A[5] * A[8]);
+        o[5 * GS] = sk * (A[6] * A[6] + A[7] * A[7] + A[8] * A[8]);
+      } else {
+        double T[9];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          T[k * 3 + 0] = A[k * 3] * prm.kc[0] + A[k * 3 + 1] * prm.kc[1] + A[k * 3 + 2] * prm.kc[2];
+          T[k * 3 + 1] = A[k * 3] * prm.kc[1] + A[k * 3 + 1] * prm.kc[3] + A[k * 3 + 2] * prm.kc[4];
+          T[k * 3 + 2] = A[k * 3] * prm.kc[2] + A[k * 3 + 1] * prm.kc[4] + A[k * 3 + 2] * prm.kc[5];
+        }
+        int t = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int l = k; l < 3; l++) o[(t++) * GS] = s * (T[k * 3] * A[l * 3] + T[k * 3 + 1] * A[l * 3 + 1] + T[k * 3 + 2] * A[l * 3 + 2]);
+      }
+    }
+    o[6 * GS] = wd[q0];
+  }
+}
+
+// The kernel.  Per element layer l two barrier-separated phases, software-pipelined so that every phase mixes FP64-heavy and
+// shared-memory-heavy work of different layers and idle warps of one task pick up the other (dynamic warp-level work queue):
+//   phase X:  S3(l-1) + store(l-1)  [static: the thread owns its dof pair's accumulators]   ||   S1(l)   [queue]
+//   phase Y:  S2(l)  [queue]   ||   G(l+1)  [queue, 32 columns per item]
 template <class C, bool FK, bool FM>
-__global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
+__global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
   constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, QC = C::QC, NT = C::NT, NW = C::NW;
   constexpr int T1 = C::T1, T2 = C::T2, H1 = C::H1, H2 = C::H2, NQ1 = C::NQ1, NQ2 = C::NQ2;
   constexpr int NP2 = C::NP2, LS = C::LS, L2S = C::L2S;
   constexpr int N12 = C::N12, N12P = C::N12P, IPT = C::IPT;
   constexpr int NGK = FK ? 4 : 0;  // S2 output groups: DD DV VD VV [M]
-  constexpr int NPARTS = (C::SPLIT && FK) ? 2 : 1;
+  constexpr int NPARTS1 = (C::SPLIT && FK) ? 3 : 1, NPARTS = (C::SPLIT && FK) ? 2 : 1;  // term groups of S1 / S2 items
+  static_assert(QC == NQ, "the pipelined kernel handles all points q0 of a layer at once");
+  constexpr int NS1 = T2 * C::WPI1 * NPARTS1, NS2 = T1 * C::WPI2 * NPARTS, NGC = (NQ1 * NQ2 + 31) / 32;
   const BasisView& B = prm.B;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   extern __shared__ __align__(16) double smem[];
-  double* sG = smem;                  // [7][NQ2][LS]
-  double* sT2 = smem;                 // [QC][NG][N12P]   (aliases sG)
+  double* sG = smem + C::OFF_G;       // [7][NQ2][q0 NQ1 + Q1]
+  double* sT2 = smem + C::OFF_T2;     // [q0][group][N12P] with stride T2QS per q0
   double* sT1 = smem + C::OFF_T1;     // [NQ1][T1QS] = [NQ1][term][q0 NP2P + pair2]
   double* sL1 = smem + C::OFF_L1;     // [T2][QC][NQ1]
   double* sL2 = smem + C::OFF_L2;     // [QC][T1][T2]
@@ -269,6 +376,7 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
   double* sWt = sPt + 3 * NQ;         // [3][NQ]
   int* sRowB = reinterpret_cast<int*>(smem + C::OFF_ROW);  // 2 x [NB][4] = lo, wid, cum of dof e0+a along dimension 0
   int* sSet0 = reinterpret_cast<int*>(smem + C::OFF_SET);  // [MAXL] coefficient set of the layers of this segment
+  int* sCnt = sSet0 + C::MAXL;                             // [2] work-queue heads of phases X and Y
 
   // ---- work unit ----
   const int t2 = blockIdx.x % prm.tiles2, t1 = (blockIdx.x / prm.tiles2) % prm.tiles1, seg = blockIdx.x / (prm.tiles2 * prm.tiles1);
@@ -295,6 +403,7 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
     sWt[t] = prm.Q.w[t / NQ][t % NQ];
   }
   for (int t = tid; t <= eend - ebeg; t += NT) sSet0[t] = B.setidx[0][ebeg + t];
+  if (tid < 2) sCnt[tid] = NW;
   // do all elements of the halo carry the dominant coefficient set?  (then S1/S2 take their 1-D factors from the constant bank)
   bool mine = true;
   if (tid < H1) { const int e = e1base + tid; if (e >= 0 && e < n1 && B.setidx[1][e] != prm.cset[1]) mine = false; }
@@ -303,8 +412,8 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
   if (tid < H2) { const int e = e2base + tid; if (e >= 0 && e < n2 && B.setidx[2][e] != prm.cset[2]) mine = false; }
   const bool uni2 = __syncthreads_and(mine);
 
-  // ---- layer tables (nodes of planes e0, e0+1 over the halo; 1-D table and CSR row data of dimension 0): one value per
-  //      thread, fetched one layer ahead into registers and parked in the other half of a double buffer ----
+  // ---- layer tables, fetched ahead into registers and parked in a double buffer (index = layer parity):
+  //      nodes of planes e, e+1 over the halo; 1-D table and CSR row data (lo, wid, cum) of dimension 0 ----
   constexpr int NPF = C::NPF;
   const double* nod_src[NPF];
   double pf_nod[NPF];
@@ -321,11 +430,20 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
   }
   double pf_tb0 = 0.;
   int pf_row = 0;
-  auto prefetch = [&](int e) {
+  auto fetch_nodes = [&](int e) {
     if (e > eend) return;
 #pragma unroll
     for (int r = 0; r < NPF; r++)
       if (nod_src[r]) pf_nod[r] = __ldg(nod_src[r] + (long long)e * prm.G.stride[0]);
+  };
+  auto park_nodes = [&](int e) {
+    if (e > eend) return;
+#pragma unroll
+    for (int r = 0; r < NPF; r++)
+      if (nod_src[r]) sNodB[(e & 1) * C::SZ_NOD + tid + r * NT] = pf_nod[r];
+  };
+  auto fetch_row = [&](int e) {
+    if (e > eend) return;
     if (tid < C::SZ_TB0) {
       const int k = tid & 1, a = (tid >> 1) % NB, q = tid / (2 * NB);
       pf_tb0 = prm.Q.tab[0][((sSet0[e - ebeg] * 2 + k) * NB + a) * NQ + q];
@@ -335,21 +453,19 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
       pf_row = w == 0 ? B.lo[0][i0] : w == 1 ? B.wid[0][i0] : w == 2 ? B.cum[0][i0] : 0;
     }
   };
-  auto park = [&](int e) {
-    const int buf = e & 1;
-#pragma unroll
-    for (int r = 0; r < NPF; r++)
-      if (nod_src[r]) sNodB[buf * C::SZ_NOD + tid + r * NT] = pf_nod[r];
-    if (tid < C::SZ_TB0) sTb0B[buf * C::SZ_TB0 + tid] = pf_tb0;
-    if (tid < 4 * NB) sRowB[buf * 4 * NB + tid] = pf_row;
+  auto park_row = [&](int e) {
+    if (e > eend) return;
+    if (tid < C::SZ_TB0) sTb0B[(e & 1) * C::SZ_TB0 + tid] = pf_tb0;
+    if (tid < 4 * NB) sRowB[(e & 1) * 4 * NB + tid] = pf_row;
   };
-  prefetch(ebeg);
-  park(ebeg);
+  fetch_nodes(ebeg);
+  park_nodes(ebeg);
 
   // ---- S3 items owned by this thread: dof pairs (i1, j1) x (i2, j2) ----
-  bool ivalid[IPT], idiag[IPT];
-  long long ic12[IPT];
-  int iw12[IPT], io12[IPT], if12[IPT], il12[IPT];
+  // packed per item: wid1*wid2 | position of (j1, j2) in that box << 8 | tile-local (i1, i2) << 16 | valid << 24 | diagonal << 25;
+  // the 64-bit row-start factor lives in shared memory (read once per layer), the rest is re-derived when needed
+  int imeta[IPT];
+  long long* sIc = reinterpret_cast<long long*>(smem + C::OFF_IC);  // [IPT][NT]
 #pragma unroll
   for (int it = 0; it < IPT; it++) {
     const int item = tid + it * NT;
@@ -357,15 +473,12 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
     const int i1l = pair1 / WD, d1 = pair1 % WD, i2l = pair2 / WD, d2 = pair2 % WD;
     const int i1 = i1lo + i1l, j1 = i1 + d1 - P, i2 = i2lo + i2l, j2 = i2 + d2 - P;
     const bool v = item < N12 && i1 < nd1 && i2 < nd2 && j1 >= 0 && j1 < nd1 && j2 >= 0 && j2 < nd2;
-    ivalid[it] = v;
-    idiag[it] = v && d1 == P && d2 == P;
-    ic12[it] = 0; iw12[it] = 0; io12[it] = 0; if12[it] = 0; il12[it] = i1l * T2 + i2l;
+    imeta[it] = (i1l * T2 + i2l) << 16;
+    sIc[it * NT + tid] = 0;
     if (v) {
       const int w1 = B.wid[1][i1], w2 = B.wid[2][i2];
-      ic12[it] = (long long)B.cum[1][i1] * B.W[2] + (long long)w1 * B.cum[2][i2];
-      iw12[it] = w1 * w2;
-      io12[it] = (j1 - B.lo[1][i1]) * w2 + (j2 - B.lo[2][i2]);
-      if12[it] = i1 * nd2 + i2;
+      sIc[it * NT + tid] = (long long)B.cum[1][i1] * B.W[2] + (long long)w1 * B.cum[2][i2];
+      imeta[it] |= (w1 * w2) | ((j1 - B.lo[1][i1]) * w2 + (j2 - B.lo[2][i2])) << 8 | 1 << 24 | (d1 == P && d2 == P ? 1 << 25 : 0);
     }
   }
   const long long W12 = B.W[1] * B.W[2];
@@ -380,121 +493,27 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
       for (int b = 0; b < NB; b++) accK[it][a][b] = accM[it][a][b] = 0.;
     }
 
-  for (int e0 = ebeg; e0 <= eend; e0++) {
-    const double* sNod = sNodB + (e0 & 1) * C::SZ_NOD;
-    const double* sTb0 = sTb0B + (e0 & 1) * C::SZ_TB0;
-    const int* sRow = sRowB + (e0 & 1) * 4 * NB;
-    prefetch(e0 + 1);   // consumed by park() at the end of this layer
-    __syncthreads();    // tables of this layer parked by all threads; previous layer's stores issued
+  // ---- prologue: G(ebeg) ----
+  __syncthreads();
+  for (int col = tid; col < NQ1 * NQ2; col += NT) g_column<C, FK>(prm, sNodB + (ebeg & 1) * C::SZ_NOD, sPt, sWt, sG, col, e1base, e2base, n1, n2);
+  __syncthreads();
 
-    for (int qc = 0; qc < NQ; qc += QC) {
-      // ================= G: geometry at the halo points of QC point-planes =================
-      for (int pt = tid; pt < NQ2 * LS; pt += NT) {
-        const int Q2 = pt / LS, L = pt % LS, q0 = qc + L / NQ1, Q1 = L % NQ1;
-        const int e1l = Q1 / NQ, q1 = Q1 % NQ, e2l = Q2 / NQ, q2 = Q2 % NQ;
-        const int e1 = e1base + e1l, e2 = e2base + e2l;
-        if (e1 < 0 || e1 >= n1 || e2 < 0 || e2 >= n2) continue;
-        const double x1 = sPt[q0], x2 = sPt[NQ + q1], x3 = sPt[2 * NQ + q2];
-        const double w = sWt[q0] * sWt[NQ + q1] * sWt[2 * NQ + q2];
-        double J[9];
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-          const double* X = sNod + (i * 2 * (H1 + 1) + e1l) * (H2 + 1) + e2l;
-          constexpr int SP = (H1 + 1) * (H2 + 1), S1 = H2 + 1;
-          const double c000 = X[0], c001 = X[1], c010 = X[S1], c011 = X[S1 + 1];
-          const double c100 = X[SP], c101 = X[SP + 1], c110 = X[SP + S1], c111 = X[SP + S1 + 1];
-          const double d00 = c001 - c000, d01 = c011 - c010, d10 = c101 - c100, d11 = c111 - c110;
-          const double m00 = fma(x3, d00, c000), m01 = fma(x3, d01, c010), m10 = fma(x3, d10, c100), m11 = fma(x3, d11, c110);
-          const double g0 = fma(x2, d01 - d00, d00), g1 = fma(x2, d11 - d10, d10);
-          J[i * 3 + 2] = fma(x1, g1 - g0, g0);
-          const double f0 = m01 - m00, f1 = m11 - m10;
-          const double h0 = fma(x2, f0, m00), h1 = fma(x2, f1, m10);
-          J[i * 3 + 1] = fma(x1, f1 - f0, f0);
-          J[i * 3 + 0] = h1 - h0;
-        }
-        // adjugate rows A[k][i] (J^-1 = A / det)
-        double A[9];
-        A[0] = J[4] * J[8] - J[5] * J[7]; A[1] = J[2] * J[7] - J[1] * J[8]; A[2] = J[1] * J[5] - J[2] * J[4];
-        A[3] = J[5] * J[6] - J[3] * J[8]; A[4] = J[0] * J[8] - J[2] * J[6]; A[5] = J[2] * J[3] - J[0] * J[5];
-        A[6] = J[3] * J[7] - J[4] * J[6]; A[7] = J[1] * J[6] - J[0] * J[7]; A[8] = J[0] * J[4] - J[1] * J[3];
-        const double det = J[0] * A[0] + J[1] * A[3] + J[2] * A[6];
-        const double adet = fabs(det);
-        double* g = sG + Q2 * LS + L;
-        constexpr int GS = NQ2 * LS;
-        if (FK) {
-          const double s = w / adet;
-          if (prm.iso) {
-            const double sk = s * prm.kc[0];
-            g[0 * GS] = sk * (A[0] * A[0] + A[1] * A[1] + A[2] * A[2]);
-            g[1 * GS] = sk * (A[0] * A[3] + A[1] * A[4] + A[2] * A[5]);
-            g[2 * GS] = sk * (A[0] * A[6] + A[1] * A[7] + A[2] * A[8]);
-            g[3 * GS] = sk * (A[3] * A[3] + A[4] * A[4] + A[5] * A[5]);
-            g[4 * GS] = sk * (A[3] * A[6] + A[4] * A[7] + A[5] * A[8]);
-            g[5 * GS] = sk * (A[6] * A[6] + A[7] * A[7] + A[8] * A[8]);
-          } else {
-            double T[9];
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-              T[k * 3 + 0] = A[k * 3] * prm.kc[0] + A[k * 3 + 1] * prm.kc[1] + A[k * 3 + 2] * prm.kc[2];
-              T[k * 3 + 1] = A[k * 3] * prm.kc[1] + A[k * 3 + 1] * prm.kc[3] + A[k * 3 + 2] * prm.kc[4];
-              T[k * 3 + 2] = A[k * 3] * prm.kc[2] + A[k * 3 + 1] * prm.kc[4] + A[k * 3 + 2] * prm.kc[5];
-            }
-            int t = 0;
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-#pragma unroll
-              for (int l = k; l < 3; l++) g[(t++) * GS] = s * (T[k * 3] * A[l * 3] + T[k * 3 + 1] * A[l * 3 + 1] + T[k * 3 + 2] * A[l * 3 + 2]);
-          }
-        }
-        g[6 * GS] = w * adet;
-      }
-      __syncthreads();
-
-      // ================= S1: contract Q2 =================
-      for (int wi = warp; wi < T2 * C::WPI1 * NPARTS; wi += NW) {
-        const int part = wi % NPARTS, wj = wi / NPARTS;
-        const int i2l = wj / C::WPI1, L = (wj % C::WPI1) * 32 + lane, i2 = i2lo + i2l;
-        if (i2 >= nd2) continue;
-        const int e1 = e1base + (L % NQ1) / NQ;
-        if (L >= LS || e1 < 0 || e1 >= n1) continue;
-        if (uni2) {
-          if (NPARTS == 1) s1_item<C, FK, FM, 0, 1, true>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
-          else if (part == 0) s1_item<C, FK, FM, 0, 2, true>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
-          else s1_item<C, FK, FM, 1, 2, true>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
-        } else {
-          if (NPARTS == 1) s1_item<C, FK, FM, 0, 1, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
-          else if (part == 0) s1_item<C, FK, FM, 0, 2, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
-          else s1_item<C, FK, FM, 1, 2, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
-        }
-      }
-      __syncthreads();
-
-      // ================= S2: contract Q1 =================
-      for (int wi = warp; wi < T1 * C::WPI2 * NPARTS; wi += NW) {
-        const int part = wi % NPARTS, wj = wi / NPARTS;
-        const int i1l = wj / C::WPI2, L = (wj % C::WPI2) * 32 + lane, i1 = i1lo + i1l;
-        if (i1 >= nd1) continue;
-        if (L >= L2S || (L % C::NP2P) >= NP2) continue;
-        if (uni1) {
-          if (NPARTS == 1) s2_item<C, FK, FM, 0, 1, true>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
-          else if (part == 0) s2_item<C, FK, FM, 0, 2, true>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
-          else s2_item<C, FK, FM, 1, 2, true>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
-        } else {
-          if (NPARTS == 1) s2_item<C, FK, FM, 0, 1, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
-          else if (part == 0) s2_item<C, FK, FM, 0, 2, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
-          else s2_item<C, FK, FM, 1, 2, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
-        }
-      }
-      __syncthreads();
-
-      // ================= S3: contract q0 into the marching accumulators =================
+  for (int l = ebeg; l <= eend + 1; l++) {
+    // ======================= phase X: S3(l-1) + store(l-1)  ||  S1(l) =======================
+    fetch_nodes(l + 1);
+    fetch_row(l);
+    if (tid == 0) sCnt[1] = NW;
+    if (l > ebeg) {
+      const int e0 = l - 1;
+      const double* sTb0 = sTb0B + (e0 & 1) * C::SZ_TB0;
+      const int* sRow = sRowB + (e0 & 1) * 4 * NB;
 #pragma unroll
       for (int q0l = 0; q0l < QC; q0l++) {
         double va[NB], da[NB];
 #pragma unroll
         for (int a = 0; a < NB; a++) {
-          va[a] = sTb0[((qc + q0l) * NB + a) * 2];
-          da[a] = sTb0[((qc + q0l) * NB + a) * 2 + 1];
+          va[a] = sTb0[(q0l * NB + a) * 2];
+          da[a] = sTb0[(q0l * NB + a) * 2 + 1];
         }
 #pragma unroll
         for (int it = 0; it < IPT; it++) {
@@ -513,50 +532,108 @@ __global__ void __launch_bounds__(C::NT, 1) k_rows3d(const RowParams prm) {
                 if (FM) accM[it][a][b] = fma(va[a], um, accM[it][a][b]);
               }
             }
-            if (prm.has_f && idiag[it]) {
-              const double l2 = sL2[q0l * T1 * T2 + il12[it]];
+            if (prm.has_f && (imeta[it] >> 25 & 1)) {
+              const double l2 = sL2[q0l * T1 * T2 + (imeta[it] >> 16 & 255)];
 #pragma unroll
               for (int a = 0; a < NB; a++) accF[it][a] = fma(va[a], l2, accF[it][a]);
             }
           }
         }
       }
-      __syncthreads();
-    }
-
-    // ---- store the completed entries of this layer, carry the rest ----
-    park(e0 + 1);
-    const bool last = e0 == n0 - 1;
+      // store the completed entries of layer e0, carry the rest
+      const bool last = e0 == n0 - 1;
 #pragma unroll
-    for (int it = 0; it < IPT; it++) {
-      if (ivalid[it]) {
+      for (int it = 0; it < IPT; it++) {
+        if (imeta[it] >> 24 & 1) {
+          const long long ic12 = sIc[it * NT + tid];
+          const int iw12 = imeta[it] & 255, io12 = imeta[it] >> 8 & 255;
 #pragma unroll
-        for (int a = 0; a < NB; a++) {
-          const int i0 = e0 + a;
-          if (i0 < r0 || i0 >= r1) continue;
-          const int rlo = sRow[a * 4], rwid = sRow[a * 4 + 1], rcum = sRow[a * 4 + 2];
-          const long long rowslot = (long long)rcum * W12 + (long long)rwid * ic12[it] + io12[it];
+          for (int a = 0; a < NB; a++) {
+            const int i0 = e0 + a;
+            if (i0 < r0 || i0 >= r1) continue;
+            const int rlo = sRow[a * 4], rwid = sRow[a * 4 + 1], rcum = sRow[a * 4 + 2];
+            const long long rowslot = (long long)rcum * W12 + (long long)rwid * ic12 + io12;
 #pragma unroll
-          for (int b = 0; b < NB; b++) {
-            if (a == 0 || b == 0 || last) {
-              const long long slot = rowslot + (long long)(e0 + b - rlo) * iw12[it];
-              if (FK) prm.valK[slot] = accK[it][a][b];
-              if (FM && prm.valM) prm.valM[slot] = accM[it][a][b] * prm.rho;
+            for (int b = 0; b < NB; b++) {
+              if (a == 0 || b == 0 || last) {
+                const long long slot = rowslot + (long long)(e0 + b - rlo) * iw12;
+                if (FK) prm.valK[slot] = accK[it][a][b];
+                if (FM && prm.valM) prm.valM[slot] = accM[it][a][b] * prm.rho;
+              }
+            }
+            if (prm.has_f && (imeta[it] >> 25 & 1) && (a == 0 || last)) {
+              const int il = imeta[it] >> 16 & 255;
+              prm.rhs[((long long)i0 * nd1 + i1lo + il / T2) * nd2 + i2lo + il % T2] = accF[it][a] * prm.vcoef;
             }
           }
-          if (prm.has_f && idiag[it] && (a == 0 || last)) prm.rhs[(long long)i0 * nd1 * nd2 + if12[it]] = accF[it][a] * prm.vcoef;
         }
-      }
 #pragma unroll
-      for (int a = 0; a < NB; a++) {
-        accF[it][a] = a < P ? accF[it][a + 1] : 0.;
+        for (int a = 0; a < NB; a++) {
+          accF[it][a] = a < P ? accF[it][a + 1] : 0.;
 #pragma unroll
-        for (int b = 0; b < NB; b++) {
-          if (FK) accK[it][a][b] = (a < P && b < P) ? accK[it][a + 1][b + 1] : 0.;
-          if (FM) accM[it][a][b] = (a < P && b < P) ? accM[it][a + 1][b + 1] : 0.;
+          for (int b = 0; b < NB; b++) {
+            if (FK) accK[it][a][b] = (a < P && b < P) ? accK[it][a + 1][b + 1] : 0.;
+            if (FM) accM[it][a][b] = (a < P && b < P) ? accM[it][a + 1][b + 1] : 0.;
+          }
         }
       }
     }
+    if (l <= eend) {
+      // work queue: the first item of a warp is static, the rest is handed out by a shared counter (starts at NW)
+      for (int wi = warp; wi < NS1;) {
+        const int part = wi % NPARTS1, wj = wi / NPARTS1;
+        const int i2l = wj / C::WPI1, L = (wj % C::WPI1) * 32 + lane, i2 = i2lo + i2l;
+        const int e1 = e1base + (L % NQ1) / NQ;
+        if (i2 < nd2 && L < LS && e1 >= 0 && e1 < n1) {
+          if (uni2) {
+            if (NPARTS1 == 1) s1_item<C, FK, FM, 0, 1, true>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+            else if (part == 0) s1_item<C, FK, FM, 0, 3, true>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+            else if (part == 1) s1_item<C, FK, FM, 1, 3, true>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+            else s1_item<C, FK, FM, 2, 3, true>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+          } else {
+            if (NPARTS1 == 1) s1_item<C, FK, FM, 0, 1, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+            else if (part == 0) s1_item<C, FK, FM, 0, 3, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+            else if (part == 1) s1_item<C, FK, FM, 1, 3, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+            else s1_item<C, FK, FM, 2, 3, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) wi = atomicAdd(&sCnt[0], 1);
+        wi = __shfl_sync(0xffffffffu, wi, 0);
+      }
+    }
+    park_nodes(l + 1);
+    park_row(l);
+    __syncthreads();
+    if (l > eend) break;
+
+    // ======================= phase Y: S2(l)  ||  G(l+1) =======================
+    if (tid == 0) sCnt[0] = NW;
+    const int ngc = l + 1 <= eend ? NGC : 0;
+    for (int wi = warp; wi < NS2 + ngc;) {
+      if (wi >= NS2) {
+        const int col = (wi - NS2) * 32 + lane;
+        if (col < NQ1 * NQ2) g_column<C, FK>(prm, sNodB + ((l + 1) & 1) * C::SZ_NOD, sPt, sWt, sG, col, e1base, e2base, n1, n2);
+      } else {
+        const int part = wi % NPARTS, wj = wi / NPARTS;
+        const int i1l = wj / C::WPI2, L = (wj % C::WPI2) * 32 + lane, i1 = i1lo + i1l;
+        if (i1 < nd1 && L < L2S && (L % C::NP2P) < NP2) {
+          if (uni1) {
+            if (NPARTS == 1) s2_item<C, FK, FM, 0, 1, true>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+            else if (part == 0) s2_item<C, FK, FM, 0, 2, true>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+            else s2_item<C, FK, FM, 1, 2, true>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+          } else {
+            if (NPARTS == 1) s2_item<C, FK, FM, 0, 1, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+            else if (part == 0) s2_item<C, FK, FM, 0, 2, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+            else s2_item<C, FK, FM, 1, 2, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) wi = atomicAdd(&sCnt[1], 1);
+      wi = __shfl_sync(0xffffffffu, wi, 0);
+    }
+    __syncthreads();
   }
 }
 
@@ -676,8 +753,23 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
     prm.rhs = F.rhs[0];
     if (!fk && !fm) fm = true, prm.valM = nullptr;  // load vector only: run the mass chain without storing it
   }
+  // Tile / thread configuration.  Measured at 128^3 (profiles/r01/variants.txt): few register-rich warps with unsplit
+  // S1/S2 items (256 threads, 230 registers, no spills) beat more, thinner warps (512 threads cap at 128 registers and spill).
   const int64_t variant = ctx->opts.count("rows_variant") ? ctx->opts["rows_variant"] : 0;
-  if (P == 1) return launch_rows_forms<RCfg<1, 8, 8, 2, 512, true>>(ctx, prm, fk, fm);
-  if (variant == 1) return launch_rows_forms<RCfg<2, 4, 4, 3, 256, false>>(ctx, prm, fk, fm);
-  return launch_rows_forms<RCfg<2, 4, 4, 3, 512, true>>(ctx, prm, fk, fm);
+  if (P == 1) {
+    if (variant == 1) return launch_rows_forms<RCfg<1, 8, 8, 2, 512, true>>(ctx, prm, fk, fm);
+    return launch_rows_forms<RCfg<1, 8, 8, 2, 256, false>>(ctx, prm, fk, fm);
+  }
+  if (variant == 1) return launch_rows_forms<RCfg<2, 4, 4, 3, 512, true>>(ctx, prm, fk, fm);
+#ifdef B2_EXPERIMENT
+  if (fk && fm) {
+    if (variant == 2) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, true>, true, true>(ctx, prm);
+    if (variant == 3) return launch_rows_cfg<RCfg<2, 5, 3, 3, 384, true>, true, true>(ctx, prm);
+    if (variant == 4) return launch_rows_cfg<RCfg<2, 3, 5, 3, 384, true>, true, true>(ctx, prm);
+    if (variant == 5) return launch_rows_cfg<RCfg<2, 4, 4, 3, 384, true>, true, true>(ctx, prm);
+    if (variant == 6) return launch_rows_cfg<RCfg<2, 4, 4, 3, 320, false>, true, true>(ctx, prm);
+    if (variant == 7) return launch_rows_cfg<RCfg<2, 4, 4, 3, 384, false>, true, true>(ctx, prm);
+  }
+#endif
+  return launch_rows_forms<RCfg<2, 4, 4, 3, 256, false>>(ctx, prm, fk, fm);
 }

@@ -9,7 +9,7 @@ mkdir -p "$HERE/_obj"
 for f in api pattern assemble_generic assemble_fast assemble_rows; do
   src="$HERE/$f.cu"; obj="$HERE/_obj/$f.o"
   if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/common.cuh" -nt "$obj" ] || [ "$HERE/../../include/b200fem.h" -nt "$obj" ]; then
-    "$NVCC" $FLAGS ${B2_PTXAS_V:+-Xptxas -v} -c "$src" -o "$obj"
+    "$NVCC" $FLAGS ${B2_PTXAS_V:+-Xptxas -v} ${B2_EXPERIMENT:+-DB2_EXPERIMENT} -c "$src" -o "$obj"
   fi
 done
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o "$OUT" "$HERE"/_obj/api.o "$HERE"/_obj/pattern.o "$HERE"/_obj/assemble_generic.o "$HERE"/_obj/assemble_fast.o "$HERE"/_obj/assemble_rows.o
