@@ -226,8 +226,15 @@ def run_b200(args):
     value = ndofs_global / (ms_per_step * 1e-3)
 
     # sanity inside the bench: partition of unity on the assembled result of the last step (sum M == sum f)
-    msum = float(mats[1].sum()) if world == 1 else None
-    fsum = float(vecs[0].sum()) if world == 1 else None
+    # (N>1: the ranks' windows tile the global arrays, so the global sums are the all-reduced window sums)
+    sums = torch.stack([mats[1].sum(), vecs[0].sum()])
+    if world > 1:
+        if not rows_path:  # shared planes are complete on both neighbours after the exchange: count the owned rows only
+            sums = torch.stack([mats[1][:layout.off_own_hi - layout.off_lo].sum() if hasattr(layout, 'off_own_hi') else mats[1].sum(), vecs[0][layout.own_rows].sum()])
+        dist.all_reduce(sums)
+    msum, fsum = (float(x) for x in sums.tolist())
+    if world > 1 and not rows_path:
+        msum = fsum = None  # the value windows of the slab layout overlap; the row-sum check is only meaningful for the rows path
 
     # roofline of the assembly kernel (rank-local bytes / rank-local kernel time)
     nnodes_local = (layout.elem_layers[1] - layout.elem_layers[0] if rows_path else (layout.elem_range[1] - layout.elem_range[0]) // (n * n)) + 1
@@ -304,6 +311,7 @@ def run_b200(args):
         }
         if msum is not None:
             line['config']['check_sumM_minus_sumf'] = msum - fsum
+            assert abs(msum - fsum) <= 1e-10 * abs(fsum), 'partition of unity violated: sum(M) != sum(f)'
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
