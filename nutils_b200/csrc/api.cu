@@ -86,6 +86,7 @@ extern "C" int b2_ctx_destroy(b2_ctx* ctx) {
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->formbuf) cudaFree(ctx->formbuf);
+  if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->copy_event); }
   for (auto* v : {&ctx->kernel_events, &ctx->event_pool})
     for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   cudaEventDestroy(ctx->ev0);
@@ -591,11 +592,28 @@ static int assemble_impl(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis*
     for (int d = nd - 1; d >= 0; d--) { G.stride[d] = s; s *= geom->nel[d] + 1; }
   }
 
+  const int64_t kernel_opt = ctx->opts.count("kernel") ? ctx->opts["kernel"] : 0;
+  for (int m = 0; m < nmat; m++)
+    if (!D_host[m] || !values_dev[m]) return b2_fail(ctx, B2_EINVAL, "null matrix form");
+  for (int v = 0; v < nvec; v++)
+    if (!C_host[v] || !rhs_dev[v]) return b2_fail(ctx, B2_EINVAL, "null vector form");
+  if (rows && kernel_opt != 1) {
+    // the specialised owner-computes kernel takes its coefficients as kernel parameters: no upload, no synchronisation
+    FormView F0;
+    memset(&F0, 0, sizeof(F0));
+    F0.nmat = nmat;
+    F0.nvec = nvec;
+    for (int m = 0; m < nmat; m++) F0.values[m] = values_dev[m];
+    for (int v = 0; v < nvec; v++) F0.rhs[v] = rhs_dev[v];
+    rc = launch_assemble_rows(ctx, basis, quad, B, Q, G, F0, D_host, C_host, plane_begin, plane_end);
+    if (rc != B2_EUNSUPPORTED) return rc;
+    if (kernel_opt >= 2) return b2_fail(ctx, B2_EUNSUPPORTED, "requested specialised kernel does not cover this configuration");
+  }
+
   // sparse term lists of the coefficient tensors
   std::vector<int> termptr(1, 0), termxy;
   std::vector<double> termval, vcoef;
   for (int m = 0; m < nmat; m++) {
-    if (!D_host[m] || !values_dev[m]) return b2_fail(ctx, B2_EINVAL, "null matrix form");
     for (int c = 0; c < nc; c++)
       for (int e = 0; e < nc; e++) {
         for (int x = 0; x < na; x++)
@@ -607,7 +625,6 @@ static int assemble_impl(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis*
       }
   }
   for (int v = 0; v < nvec; v++) {
-    if (!C_host[v] || !rhs_dev[v]) return b2_fail(ctx, B2_EINVAL, "null vector form");
     vcoef.insert(vcoef.end(), C_host[v], C_host[v] + nc * na);
   }
   const size_t b_ptr = termptr.size() * sizeof(int), b_xy = std::max<size_t>(termxy.size(), 1) * sizeof(int);
@@ -642,13 +659,7 @@ static int assemble_impl(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis*
   for (int m = 0; m < nmat; m++) F.values[m] = values_dev[m];
   for (int v = 0; v < nvec; v++) F.rhs[v] = rhs_dev[v];
 
-  const int64_t kernel_opt = ctx->opts.count("kernel") ? ctx->opts["kernel"] : 0;
   if (rows) {
-    if (kernel_opt != 1) {
-      rc = launch_assemble_rows(ctx, basis, quad, B, Q, G, F, D_host, C_host, plane_begin, plane_end);
-      if (rc != B2_EUNSUPPORTED) return rc;
-      if (kernel_opt >= 2) return b2_fail(ctx, B2_EUNSUPPORTED, "requested specialised kernel does not cover this configuration");
-    }
     // coverage path: zero the planes' slots, then scatter only the rows inside the planes
     const int64_t nb_plane = basis->nbasis / basis->ndofs_d[0] * nc;
     const int64_t s0 = b2_pattern_row_offset(pattern, plane_begin * nb_plane), s1 = b2_pattern_row_offset(pattern, plane_end * nb_plane);
@@ -703,16 +714,43 @@ extern "C" int b2_assemble_host(b2_ctx* ctx, const b2_pattern* pattern, const b2
   unsigned char* base = (unsigned char*)ctx->scratch;
   for (int m = 0; m < nmat; m++) vals[m] = (double*)(base + bm * m);
   for (int v = 0; v < nvec; v++) rhs[v] = (double*)(base + bm * nmat + bv * v);
-  // the whole topology: owner-computes rows (every value written once, no zero fill); a slab: accumulate
+  for (int m = 0; m < nmat; m++)
+    if (!values_host[m]) return b2_fail(ctx, B2_EINVAL, "null output buffer");
+  for (int v = 0; v < nvec; v++)
+    if (!rhs_host[v]) return b2_fail(ctx, B2_EINVAL, "null output buffer");
+  // The whole topology: owner-computes rows (every value written once, no zero fill).  Large results are produced in
+  // chunks of dof planes so that the device-to-host copy of one chunk (copy stream) overlaps the integration of the next.
+  if (whole && need >= ((size_t)64 << 20) && basis->ndofs_d[0] >= 16) {
+    if (!ctx->copy_stream) {
+      B2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
+    }
+    const int64_t np = basis->ndofs_d[0], per_plane = pattern->nrows / np;
+    const int nchunk = (int)std::min<int64_t>(8, np / 8);
+    for (int k = 0; k < nchunk; k++) {
+      const int64_t p0 = np * k / nchunk, p1 = np * (k + 1) / nchunk;
+      int rc = assemble_impl(ctx, pattern, basis, quad, geom, p0, p1, nmat, D_host, vals, nvec, C_host, rhs, true);
+      if (rc != B2_OK) { cudaStreamSynchronize(ctx->copy_stream); return rc; }
+      B2_CUDA(ctx, cudaEventRecord(ctx->copy_event, ctx->stream));
+      B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
+      const int64_t s0 = b2_pattern_row_offset(pattern, p0 * per_plane), s1 = b2_pattern_row_offset(pattern, p1 * per_plane);
+      for (int m = 0; m < nmat; m++)
+        B2_CUDA(ctx, cudaMemcpyAsync(values_host[m] + s0, vals[m] + s0, sizeof(double) * (size_t)(s1 - s0), cudaMemcpyDeviceToHost, ctx->copy_stream));
+      for (int v = 0; v < nvec; v++)
+        B2_CUDA(ctx, cudaMemcpyAsync(rhs_host[v] + p0 * per_plane, rhs[v] + p0 * per_plane, sizeof(double) * (size_t)((p1 - p0) * per_plane), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    B2_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B2_OK;
+  }
+  // otherwise one pass: rows for the whole topology, accumulate for a slab of elements
   int rc = whole ? assemble_impl(ctx, pattern, basis, quad, geom, 0, -1, nmat, D_host, vals, nvec, C_host, rhs, true)
                  : assemble_impl(ctx, pattern, basis, quad, geom, elem_begin, elem_end, nmat, D_host, vals, nvec, C_host, rhs);
   if (rc != B2_OK) return rc;
   for (int m = 0; m < nmat; m++) {
-    if (!values_host[m]) return b2_fail(ctx, B2_EINVAL, "null output buffer");
     B2_CUDA(ctx, cudaMemcpyAsync(values_host[m], vals[m], bm, cudaMemcpyDeviceToHost, ctx->stream));
   }
   for (int v = 0; v < nvec; v++) {
-    if (!rhs_host[v]) return b2_fail(ctx, B2_EINVAL, "null output buffer");
     B2_CUDA(ctx, cudaMemcpyAsync(rhs_host[v], rhs[v], bv, cudaMemcpyDeviceToHost, ctx->stream));
   }
   B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

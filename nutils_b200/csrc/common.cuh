@@ -66,6 +66,9 @@ struct b2_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // second stream for the device-to-host copies of b2_assemble_host (overlap with the next chunk's kernel)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_event = nullptr;
   std::string err;
   int64_t launches = 0;
   void* flush_buf = nullptr;

@@ -225,6 +225,60 @@ def test_properties_large(ctx):
     assert abs(A - A.T).max() <= 1e-12 * abs(K).max()
 
 
+def test_full_size_properties(ctx):
+    '''BASELINE.json configs[1] at its full size (128^3, p=2, K+M+f; the oracle would need hours and ~100 GB): size-independent
+    properties checked on the device.  (1) the two independent CUDA paths -- owner-computes rows kernel and element-scatter
+    kernel -- agree to 1e-12; (2) partition of unity: K 1 = 0, M 1 = f, sum f = volume; (3) scaling the nodes by 2 scales K by
+    exactly 2 and M, f by exactly 8 (power-of-two scaling commutes with every rounding), bitwise.'''
+    import torch
+    from bench import make_nodes
+    n, p = 128, 2
+    b1 = util.bases_1d((n,) * 3, p, 'spline')
+    rules = points.tensor_gauss(3, 2 * p)
+    X = make_nodes((n,) * 3)
+    plan = engine.Plan(ctx, b1, rules, X)
+    assert plan.ndofs == 130 ** 3 and plan.nnz == 644 ** 3
+    dev = torch.device('cuda', 0)
+    Ds, Cs = [engine.form_stiffness(3), engine.form_mass(3)], [engine.form_load(3)]
+    K, M = (torch.empty(plan.nnz, dtype=torch.float64, device=dev) for _ in range(2))
+    f = torch.empty(plan.ndofs, dtype=torch.float64, device=dev)
+    ctx.set_option('kernel', 2)
+    try:
+        plan.assemble_rows_device(Ds, Cs, [K, M], [f])
+    finally:
+        ctx.set_option('kernel', 0)
+    ctx.synchronize()
+    # (2) row sums
+    rowptr = torch.empty(plan.ndofs + 1, dtype=torch.int64, device=dev)
+    colidx = torch.empty(plan.nnz, dtype=torch.int64, device=dev)
+    plan.csr_pattern_device(rowptr, colidx)
+    ctx.synchronize()
+    del colidx
+    lengths = rowptr[1:] - rowptr[:-1]
+    Ksum = torch.segment_reduce(K, 'sum', lengths=lengths)
+    Msum = torch.segment_reduce(M, 'sum', lengths=lengths)
+    assert float(Ksum.abs().max()) <= 1e-12 * 125 * float(K.abs().max())
+    assert float((Msum - f).norm() / f.norm()) <= 1e-12
+    volume = float(f.sum())
+    assert abs(volume - 1.) < 1e-3 and abs(float(M.sum()) - volume) <= 1e-12 * volume  # warped unit cube
+    # (1) element-scatter path
+    K2, M2 = torch.zeros_like(K), torch.zeros_like(M)
+    f2 = torch.zeros_like(f)
+    torch.cuda.synchronize()  # the zero-fill runs on torch's stream, the assembly on the context's own
+    plan.assemble_device(Ds, Cs, [K2, M2], [f2])
+    ctx.synchronize()
+    for a, b in ((K, K2), (M, M2), (f, f2)):
+        assert float((a - b).norm() / b.norm()) <= TOL
+    del K2, M2, f2, Ksum, Msum
+    # (3) exact scaling
+    plan2 = engine.Plan(ctx, b1, rules, 2. * X)
+    K3, M3 = torch.empty_like(K), torch.empty_like(M)
+    f3 = torch.empty_like(f)
+    plan2.assemble_rows_device(Ds, Cs, [K3, M3], [f3])
+    ctx.synchronize()
+    assert bool((K3 == 2. * K).all()) and bool((M3 == 8. * M).all()) and bool((f3 == 8. * f).all())
+
+
 def test_errors(ctx):
     from nutils_b200._lib import B200Error
     prob = _random_problem(1, (3, 3), 2)
