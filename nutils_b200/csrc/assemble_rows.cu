@@ -250,13 +250,13 @@ __device__ __forceinline__ void s2_item(const RowParams& prm, const double* __re
   if (diag) sL2[(q0l * T1 + i1l) * T2 + i2l] = l2;
 }
 
-// ---- G: geometry of one (Q1, Q2) column of the halo, all QC = NQ points q0 of the layer ----
+// ---- G: geometry of one (Q1, Q2) column of the halo, the QC points q0 = qc.. of the current chunk ----
 // Trilinear map x = sum_v phi_v X_v of the element: the interpolations along dimensions 2 and 1 are shared by the points of the
 // column (J[:,0] does not depend on xi0; J[:,1], J[:,2] are linear in xi0); adj(J), det and Ghat = w/|det| adj K adj^T per point.
 template <class C, bool FK>
 __device__ __forceinline__ void g_column(const RowParams& prm, const double* __restrict__ sNod, const double* __restrict__ sPt, const double* __restrict__ sWt,
-                                         double* __restrict__ sG, int col, int e1base, int e2base, int n1, int n2) {
-  constexpr int NQ = C::NQ, H1 = C::H1, H2 = C::H2, NQ1 = C::NQ1, NQ2 = C::NQ2, LS = C::LS, GS = NQ2 * LS;
+                                         double* __restrict__ sG, int col, int qc, int e1base, int e2base, int n1, int n2) {
+  constexpr int NQ = C::NQ, QC = C::QC, H1 = C::H1, H2 = C::H2, NQ1 = C::NQ1, NQ2 = C::NQ2, LS = C::LS, GS = NQ2 * LS;
   const int Q2 = col / NQ1, Q1 = col % NQ1;
   const int e1l = Q1 / NQ, q1 = Q1 % NQ, e2l = Q2 / NQ, q2 = Q2 % NQ;
   const int e1 = e1base + e1l, e2 = e2base + e2l;
@@ -281,10 +281,10 @@ __device__ __forceinline__ void g_column(const RowParams& prm, const double* __r
   }
   double* g = sG + Q2 * LS + Q1;
   // pass 1: A[0] = J[:,1] x J[:,2], det = J[:,0] . A[0] and the scale w/|det| of every point -- the reciprocal chains interleave
-  double A0[NQ][3], sc[NQ], wd[NQ];
+  double A0[QC][3], sc[QC], wd[QC];
 #pragma unroll
-  for (int q0 = 0; q0 < NQ; q0++) {
-    const double x0 = sPt[q0];
+  for (int q0 = 0; q0 < QC; q0++) {
+    const double x0 = sPt[qc + q0];
     double J1[3], J2[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -296,16 +296,16 @@ __device__ __forceinline__ void g_column(const RowParams& prm, const double* __r
     A0[q0][2] = J1[0] * J2[1] - J1[1] * J2[0];
   }
 #pragma unroll
-  for (int q0 = 0; q0 < NQ; q0++) {
+  for (int q0 = 0; q0 < QC; q0++) {
     const double det = J0[0] * A0[q0][0] + J0[1] * A0[q0][1] + J0[2] * A0[q0][2];
-    const double adet = fabs(det), w = sWt[q0] * w12;
+    const double adet = fabs(det), w = sWt[qc + q0] * w12;
     sc[q0] = w / adet;
     wd[q0] = w * adet;
   }
   // pass 2: the other two adjugate rows A[1] = J[:,2] x J[:,0], A[2] = J[:,0] x J[:,1] and Ghat = s A K A^T
 #pragma unroll
-  for (int q0 = 0; q0 < NQ; q0++) {
-    const double x0 = sPt[q0];
+  for (int q0 = 0; q0 < QC; q0++) {
+    const double x0 = sPt[qc + q0];
     double J1[3], J2[3], A[9];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -357,7 +357,8 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
   constexpr int N12 = C::N12, N12P = C::N12P, IPT = C::IPT;
   constexpr int NGK = FK ? 4 : 0;  // S2 output groups: DD DV VD VV [M]
   constexpr int NPARTS1 = (C::SPLIT && FK) ? 3 : 1, NPARTS = (C::SPLIT && FK) ? 2 : 1;  // term groups of S1 / S2 items
-  static_assert(QC == NQ, "the pipelined kernel handles all points q0 of a layer at once");
+  static_assert(NQ % QC == 0, "the points q0 of a layer are processed in NQ/QC chunks");
+  constexpr int NCH = NQ / QC;
   constexpr int NS1 = T2 * C::WPI1 * NPARTS1, NS2 = T1 * C::WPI2 * NPARTS, NGC = (NQ1 * NQ2 + 31) / 32;
   const BasisView& B = prm.B;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -493,18 +494,21 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
       for (int b = 0; b < NB; b++) accK[it][a][b] = accM[it][a][b] = 0.;
     }
 
-  // ---- prologue: G(ebeg) ----
+  // ---- prologue: G of the first step ----
   __syncthreads();
-  for (int col = tid; col < NQ1 * NQ2; col += NT) g_column<C, FK>(prm, sNodB + (ebeg & 1) * C::SZ_NOD, sPt, sWt, sG, col, e1base, e2base, n1, n2);
+  for (int col = tid; col < NQ1 * NQ2; col += NT) g_column<C, FK>(prm, sNodB + (ebeg & 1) * C::SZ_NOD, sPt, sWt, sG, col, 0, e1base, e2base, n1, n2);
   __syncthreads();
 
-  for (int l = ebeg; l <= eend + 1; l++) {
-    // ======================= phase X: S3(l-1) + store(l-1)  ||  S1(l) =======================
-    fetch_nodes(l + 1);
-    fetch_row(l);
+  // one pipeline step = one chunk of QC point-planes q0 of one element layer
+  const int nstep = (eend - ebeg + 1) * NCH;
+  for (int s = 0; s <= nstep; s++) {
+    const int l = ebeg + s / NCH, ch = s % NCH;
+    // ======================= phase X: S3(s-1) [+ store of its layer]  ||  S1(s) =======================
+    if (ch == NCH - 1) fetch_nodes(l + 1);
+    if (ch == 0) fetch_row(l);
     if (tid == 0) sCnt[1] = NW;
-    if (l > ebeg) {
-      const int e0 = l - 1;
+    if (s > 0) {
+      const int e0 = ebeg + (s - 1) / NCH, qc = ((s - 1) % NCH) * QC;
       const double* sTb0 = sTb0B + (e0 & 1) * C::SZ_TB0;
       const int* sRow = sRowB + (e0 & 1) * 4 * NB;
 #pragma unroll
@@ -512,8 +516,8 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
         double va[NB], da[NB];
 #pragma unroll
         for (int a = 0; a < NB; a++) {
-          va[a] = sTb0[(q0l * NB + a) * 2];
-          da[a] = sTb0[(q0l * NB + a) * 2 + 1];
+          va[a] = sTb0[((qc + q0l) * NB + a) * 2];
+          da[a] = sTb0[((qc + q0l) * NB + a) * 2 + 1];
         }
 #pragma unroll
         for (int it = 0; it < IPT; it++) {
@@ -540,6 +544,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
           }
         }
       }
+      if ((s - 1) % NCH == NCH - 1) {
       // store the completed entries of layer e0, carry the rest
       const bool last = e0 == n0 - 1;
 #pragma unroll
@@ -577,8 +582,9 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
           }
         }
       }
+      }
     }
-    if (l <= eend) {
+    if (s < nstep) {
       // work queue: the first item of a warp is static, the rest is handed out by a shared counter (starts at NW)
       for (int wi = warp; wi < NS1;) {
         const int part = wi % NPARTS1, wj = wi / NPARTS1;
@@ -602,18 +608,19 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
         wi = __shfl_sync(0xffffffffu, wi, 0);
       }
     }
-    park_nodes(l + 1);
-    park_row(l);
+    if (ch == NCH - 1) park_nodes(l + 1);
+    if (ch == 0) park_row(l);
     __syncthreads();
-    if (l > eend) break;
+    if (s >= nstep) break;
 
-    // ======================= phase Y: S2(l)  ||  G(l+1) =======================
+    // ======================= phase Y: S2(s)  ||  G(s+1) =======================
     if (tid == 0) sCnt[0] = NW;
-    const int ngc = l + 1 <= eend ? NGC : 0;
+    const int ngc = s + 1 < nstep ? NGC : 0;
+    const int ln = ebeg + (s + 1) / NCH, qcn = ((s + 1) % NCH) * QC;
     for (int wi = warp; wi < NS2 + ngc;) {
       if (wi >= NS2) {
         const int col = (wi - NS2) * 32 + lane;
-        if (col < NQ1 * NQ2) g_column<C, FK>(prm, sNodB + ((l + 1) & 1) * C::SZ_NOD, sPt, sWt, sG, col, e1base, e2base, n1, n2);
+        if (col < NQ1 * NQ2) g_column<C, FK>(prm, sNodB + (ln & 1) * C::SZ_NOD, sPt, sWt, sG, col, qcn, e1base, e2base, n1, n2);
       } else {
         const int part = wi % NPARTS, wj = wi / NPARTS;
         const int i1l = wj / C::WPI2, L = (wj % C::WPI2) * 32 + lane, i1 = i1lo + i1l;
@@ -685,7 +692,7 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
                          const double* const* D_host, const double* const* C_host, long long plane_begin, long long plane_end) {
   if (B.ndims != 3 || B.ncomp != 1) return B2_EUNSUPPORTED;
   const int P = B.p[0];
-  if (B.p[1] != P || B.p[2] != P || (P != 1 && P != 2)) return B2_EUNSUPPORTED;
+  if (B.p[1] != P || B.p[2] != P || P < 1 || P > 3) return B2_EUNSUPPORTED;
   for (int d = 0; d < 3; d++) {
     if (Q.nq[d] != P + 1) return B2_EUNSUPPORTED;
     // maximal smoothness: element e carries dofs e..e+P
@@ -759,6 +766,20 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
   if (P == 1) {
     if (variant == 1) return launch_rows_forms<RCfg<1, 8, 8, 2, 512, true>>(ctx, prm, fk, fm);
     return launch_rows_forms<RCfg<1, 8, 8, 2, 256, false>>(ctx, prm, fk, fm);
+  }
+  if (P == 3) {
+    // two chunks of two point-planes per layer; K and M in separate launches: 2 x 16 accumulators per dof pair and form
+    // for two dof pairs per thread would not fit the register file together
+    using C3 = RCfg<3, 3, 3, 2, 256, true>;
+    if (!(fk && fm)) return launch_rows_forms<C3>(ctx, prm, fk, fm);
+    RowParams pk = prm;
+    pk.valM = nullptr;
+    int rc = launch_rows_cfg<C3, true, false>(ctx, pk);
+    if (rc != B2_OK) return rc;
+    RowParams pm = prm;
+    pm.valK = nullptr;
+    pm.has_f = 0;
+    return launch_rows_cfg<C3, false, true>(ctx, pm);
   }
   if (variant == 1) return launch_rows_forms<RCfg<2, 4, 4, 3, 512, true>>(ctx, prm, fk, fm);
 #ifdef B2_EXPERIMENT

@@ -15,7 +15,12 @@ TOL = 1e-12
 
 @pytest.fixture(scope='module')
 def ctx():
-    return engine.Context.get(0)
+    # run on torch's current stream: several tests fill torch tensors right before handing them to the C ABI
+    import torch
+    c = engine.Context.get(0)
+    c.set_stream(torch.cuda.current_stream().cuda_stream)
+    yield c
+    c.set_stream(None)
 
 
 def _plan(ctx, prob):
@@ -80,7 +85,7 @@ CASES = [
     dict(nelems=(9, 8, 7), degree=1), dict(nelems=(10, 9, 11), degree=2), dict(nelems=(5, 4, 6), degree=3), dict(nelems=(3, 2, 3), degree=4),
     dict(nelems=(6, 5, 4), degree=2, btype='std'), dict(nelems=(6, 5, 4), degree=2, qdegree=6),
     dict(nelems=(9, 7), degree=2, ncomp=2), dict(nelems=(5, 4, 5), degree=2, ncomp=3), dict(nelems=(4, 3, 3), degree=3, ncomp=3),
-    dict(nelems=(1, 1, 1), degree=2), dict(nelems=(3, 13, 18), degree=2), dict(nelems=(7, 11, 5), degree=1), dict(nelems=(1, 2, 9), degree=2),
+    dict(nelems=(1, 1, 1), degree=2), dict(nelems=(3, 13, 18), degree=2), dict(nelems=(7, 11, 5), degree=1), dict(nelems=(1, 2, 9), degree=2), dict(nelems=(7, 9, 8), degree=3), dict(nelems=(2, 1, 3), degree=3),
 ]
 
 
@@ -130,7 +135,7 @@ def test_element_ranges_accumulate(ctx):
 ROWS_CASES = [
     dict(nelems=(10, 9, 11), degree=2), dict(nelems=(9, 8, 7), degree=1), dict(nelems=(3, 13, 18), degree=2), dict(nelems=(1, 1, 1), degree=2),
     dict(nelems=(2, 1, 1), degree=1), dict(nelems=(6, 5, 4), degree=2, btype='std'), dict(nelems=(5, 4, 6), degree=3), dict(nelems=(12, 15), degree=2),
-    dict(nelems=(5, 4, 5), degree=2, ncomp=3),
+    dict(nelems=(5, 4, 5), degree=2, ncomp=3), dict(nelems=(8, 7, 10), degree=3), dict(nelems=(1, 1, 1), degree=3), dict(nelems=(3, 2, 2), degree=4),
 ]
 
 
