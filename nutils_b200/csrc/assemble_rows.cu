@@ -44,6 +44,12 @@ struct RowParams {
   int has_f, iso;
   double kc[6];  // symmetric conductivity (00,01,02,11,12,22)
   double rho, vcoef;
+  // vector-valued spaces (ncomp > 1): one launch writes the rows of component `crow`; form e = column component e:
+  //   stiffness-like:  dm[e][x][y] = D[crow][1+x][e][1+y]  (any 3x3 block, not necessarily symmetric)
+  //   mass-like:       rhoe[e]     = D[crow][0][e][0]
+  int ncomp, crow;
+  double dm[3][9];
+  double rhoe[3];
   // (value, derivative) of the local functions of the DOMINANT coefficient set of each dimension at the 1-D points,
   // [dim][q][a][2]: kernel parameters live in the constant bank, so these are free FP64 operands
   int cset[3];
@@ -53,8 +59,9 @@ struct RowParams {
   double* rhs;
 };
 
-template <int P_, int T1_, int T2_, int QC_, int NT_, bool SPLIT_>
+template <int P_, int T1_, int T2_, int QC_, int NT_, bool SPLIT_, int NG_ = 7>
 struct RCfg {
+  static constexpr int NG = NG_;  // components of the coefficient per point: 7 = symmetric Ghat (6) + w|det|, 10 = general Ghat (9) + w|det|
   static constexpr int P = P_, NB = P + 1, NQ = P + 1, WD = 2 * P + 1;
   static constexpr int T1 = T1_, T2 = T2_, QC = QC_, NT = NT_, NW = NT / 32;
   // one CTA per SM; the register file is split over the 4 sub-partitions (16384 each), warps are dealt round-robin
@@ -102,7 +109,7 @@ struct RCfg {
   static constexpr int IPT = (N12 + NT - 1) / NT;
   static constexpr int WPI1 = (LS + 31) / 32, WPI2 = (L2S + 31) / 32;
   // shared memory, in doubles
-  static constexpr int SZ_G = 7 * NQ2 * LS;
+  static constexpr int SZ_G = NG * NQ2 * LS;
   static constexpr int SZ_T2 = QC * T2QS;
   static constexpr int OFF_G = 0, OFF_T2 = SZ_G;             // separate buffers: G(l+1) is produced while T2(l) is consumed
   static constexpr int OFF_T1 = SZ_G + SZ_T2, SZ_T1 = NQ1 * T1QS;
@@ -150,10 +157,14 @@ __device__ __forceinline__ void s1_item(const RowParams& prm, const double* __re
       const double* tb = sTb2 + (e2l * NQ + q2) * NB * 2;
       const double va = CONST ? prm.ctab[2][q2][a][0] : tb[a * 2], da = CONST ? prm.ctab[2][q2][a][1] : tb[a * 2 + 1];
       double pa[9];
-      if (TA) { pa[0] = va * g[0]; pa[1] = va * g[GS]; pa[2] = va * g[3 * GS]; }
-      if (TB) { pa[3] = va * g[2 * GS]; pa[4] = va * g[4 * GS]; }
-      if (TC) { pa[5] = da * g[2 * GS]; pa[6] = da * g[4 * GS]; pa[7] = da * g[5 * GS]; }
-      if (TM) { pa[8] = va * g[6 * GS]; l1 += pa[8]; }
+      // component of Ghat[k][l]: symmetric storage (00,01,02,11,12,22) or general k*3+l
+      constexpr bool SYM = C::NG == 7;
+      constexpr int I00 = 0, I01 = 1, I02 = 2, I10 = SYM ? 1 : 3, I11 = SYM ? 3 : 4, I12 = SYM ? 4 : 5, I20 = SYM ? 2 : 6, I21 = SYM ? 4 : 7, I22 = SYM ? 5 : 8;
+      double pw = 0., p10 = 0.;
+      if (TA) { pa[0] = va * g[I00 * GS]; pa[1] = va * g[I01 * GS]; pa[2] = va * g[I11 * GS]; if (!SYM) p10 = va * g[I10 * GS]; }
+      if (TB) { pa[3] = va * g[I02 * GS]; pa[4] = va * g[I12 * GS]; }
+      if (TC) { pa[5] = da * g[I20 * GS]; pa[6] = da * g[I21 * GS]; pa[7] = da * g[I22 * GS]; }
+      if (TM) { pw = va * g[(C::NG - 1) * GS]; l1 += pw; }
 #pragma unroll
       for (int b = 0; b <= P; b++) {
         const double vb = CONST ? prm.ctab[2][q2][b][0] : tb[b * 2], db = CONST ? prm.ctab[2][q2][b][1] : tb[b * 2 + 1];
@@ -162,6 +173,7 @@ __device__ __forceinline__ void s1_item(const RowParams& prm, const double* __re
           t[d][0] = fma(pa[0], vb, t[d][0]);
           t[d][1] = fma(pa[1], vb, t[d][1]);
           t[d][2] = fma(pa[2], vb, t[d][2]);
+          if (!SYM) t[d][8] = fma(p10, vb, t[d][8]);   // A10 takes the slot of the mass term (general forms carry no mass)
         }
         if (TB) {
           t[d][3] = fma(pa[3], db, t[d][3]);
@@ -172,14 +184,14 @@ __device__ __forceinline__ void s1_item(const RowParams& prm, const double* __re
           t[d][6] = fma(pa[6], vb, t[d][6]);
           t[d][7] = fma(pa[7], db, t[d][7]);
         }
-        if (TM && FM) t[d][8] = fma(pa[8], vb, t[d][8]);
+        if (TM && FM) t[d][8] = fma(pw, vb, t[d][8]);
       }
     }
   }
   double* o = sT1 + Q1 * C::T1QS + q0l * C::NP2P + i2l * WD;
 #pragma unroll
   for (int d = 0; d < WD; d++) {
-    if (TA) { o[0 * C::L2S + d] = t[d][0]; o[1 * C::L2S + d] = t[d][1]; o[2 * C::L2S + d] = t[d][2]; }
+    if (TA) { o[0 * C::L2S + d] = t[d][0]; o[1 * C::L2S + d] = t[d][1]; o[2 * C::L2S + d] = t[d][2]; if (C::NG == 10) o[8 * C::L2S + d] = t[d][8]; }
     if (TB) { o[3 * C::L2S + d] = t[d][3]; o[4 * C::L2S + d] = t[d][4]; }
     if (TC) { o[5 * C::L2S + d] = t[d][5]; o[6 * C::L2S + d] = t[d][6]; o[7 * C::L2S + d] = t[d][7]; }
     if (TM && FM) o[NTK * C::L2S + d] = t[d][8];
@@ -218,7 +230,8 @@ __device__ __forceinline__ void s2_item(const RowParams& prm, const double* __re
       double X[7];
       if (GA) {
         const double A0 = x[0], A1 = x[L2S], B0 = x[3 * L2S], C0 = x[5 * L2S];
-        X[0] = va * A0; X[1] = va * A1; X[2] = va * B0; X[3] = fma(da, A1, va * C0);
+        const double A10 = C::NG == 10 ? x[8 * L2S] : A1;
+        X[0] = va * A0; X[1] = va * A1; X[2] = va * B0; X[3] = fma(da, A10, va * C0);
       }
       if (GB) {
         const double A2 = x[2 * L2S], B1 = x[4 * L2S], C1 = x[6 * L2S], D = x[7 * L2S];
@@ -254,7 +267,7 @@ __device__ __forceinline__ void s2_item(const RowParams& prm, const double* __re
 // Trilinear map x = sum_v phi_v X_v of the element: the interpolations along dimensions 2 and 1 are shared by the points of the
 // column (J[:,0] does not depend on xi0; J[:,1], J[:,2] are linear in xi0); adj(J), det and Ghat = w/|det| adj K adj^T per point.
 template <class C, bool FK>
-__device__ __forceinline__ void g_column(const RowParams& prm, const double* __restrict__ sNod, const double* __restrict__ sPt, const double* __restrict__ sWt,
+__device__ __forceinline__ void g_column(const RowParams& prm, int form, const double* __restrict__ sNod, const double* __restrict__ sPt, const double* __restrict__ sWt,
                                          double* __restrict__ sG, int col, int qc, int e1base, int e2base, int n1, int n2) {
   constexpr int NQ = C::NQ, QC = C::QC, H1 = C::H1, H2 = C::H2, NQ1 = C::NQ1, NQ2 = C::NQ2, LS = C::LS, GS = NQ2 * LS;
   const int Q2 = col / NQ1, Q1 = col % NQ1;
@@ -316,7 +329,20 @@ __device__ __forceinline__ void g_column(const RowParams& prm, const double* __r
     A[3] = J2[1] * J0[2] - J2[2] * J0[1]; A[4] = J2[2] * J0[0] - J2[0] * J0[2]; A[5] = J2[0] * J0[1] - J2[1] * J0[0];
     A[6] = J0[1] * J1[2] - J0[2] * J1[1]; A[7] = J0[2] * J1[0] - J0[0] * J1[2]; A[8] = J0[0] * J1[1] - J0[1] * J1[0];
     double* o = g + q0 * NQ1;
-    if (FK) {
+    if (FK && C::NG == 10) {
+      // general coefficient of form `form`: Ghat[k][l] = s sum_xy A[k][x] M[x][y] A[l][y]
+      const double s = sc[q0];
+      const double* M = prm.dm[form];
+      double T[9];
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int y = 0; y < 3; y++) T[k * 3 + y] = A[k * 3] * M[y] + A[k * 3 + 1] * M[3 + y] + A[k * 3 + 2] * M[6 + y];
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int l = 0; l < 3; l++) o[(k * 3 + l) * GS] = s * (T[k * 3] * A[l * 3] + T[k * 3 + 1] * A[l * 3 + 1] + T[k * 3 + 2] * A[l * 3 + 2]);
+    } else if (FK) {
       const double s = sc[q0];
       if (prm.iso) {
         const double sk = s * prm.kc[0];
@@ -341,7 +367,7 @@ __device__ __forceinline__ void g_column(const RowParams& prm, const double* __r
           for (int l = k; l < 3; l++) o[(t++) * GS] = s * (T[k * 3] * A[l * 3] + T[k * 3 + 1] * A[l * 3 + 1] + T[k * 3 + 2] * A[l * 3 + 2]);
       }
     }
-    o[6 * GS] = wd[q0];
+    o[(C::NG - 1) * GS] = wd[q0];
   }
 }
 
@@ -349,8 +375,10 @@ __device__ __forceinline__ void g_column(const RowParams& prm, const double* __r
 // shared-memory-heavy work of different layers and idle warps of one task pick up the other (dynamic warp-level work queue):
 //   phase X:  S3(l-1) + store(l-1)  [static: the thread owns its dof pair's accumulators]   ||   S1(l)   [queue]
 //   phase Y:  S2(l)  [queue]   ||   G(l+1)  [queue, 32 columns per item]
-template <class C, bool FK, bool FM>
+// NFORM > 1: vector-valued stiffness-like launch, forms = column components, one pipeline step per (layer, form, chunk)
+template <class C, bool FK, bool FM, int NFORM, bool VEC>
 __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
+  static_assert(NFORM == 1 || (FK && !FM && C::NG == 10), "several forms per launch: general stiffness-like forms only");
   constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, QC = C::QC, NT = C::NT, NW = C::NW;
   constexpr int T1 = C::T1, T2 = C::T2, H1 = C::H1, H2 = C::H2, NQ1 = C::NQ1, NQ2 = C::NQ2;
   constexpr int NP2 = C::NP2, LS = C::LS, L2S = C::L2S;
@@ -358,7 +386,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
   constexpr int NGK = FK ? 4 : 0;  // S2 output groups: DD DV VD VV [M]
   constexpr int NPARTS1 = (C::SPLIT && FK) ? 3 : 1, NPARTS = (C::SPLIT && FK) ? 2 : 1;  // term groups of S1 / S2 items
   static_assert(NQ % QC == 0, "the points q0 of a layer are processed in NQ/QC chunks");
-  constexpr int NCH = NQ / QC;
+  constexpr int NCH = NQ / QC, NSUB = NCH * NFORM;
   constexpr int NS1 = T2 * C::WPI1 * NPARTS1, NS2 = T1 * C::WPI2 * NPARTS, NGC = (NQ1 * NQ2 + 31) / 32;
   const BasisView& B = prm.B;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -484,31 +512,35 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
   }
   const long long W12 = B.W[1] * B.W[2];
 
-  double accK[IPT][NB][NB], accM[IPT][NB][NB], accF[IPT][NB];
+  double accK[IPT][NFORM][NB][NB], accM[IPT][NB][NB], accF[IPT][NB];
 #pragma unroll
   for (int it = 0; it < IPT; it++)
 #pragma unroll
     for (int a = 0; a < NB; a++) {
       accF[it][a] = 0.;
 #pragma unroll
-      for (int b = 0; b < NB; b++) accK[it][a][b] = accM[it][a][b] = 0.;
+      for (int b = 0; b < NB; b++) {
+        accM[it][a][b] = 0.;
+#pragma unroll
+        for (int f = 0; f < NFORM; f++) accK[it][f][a][b] = 0.;
+      }
     }
 
   // ---- prologue: G of the first step ----
   __syncthreads();
-  for (int col = tid; col < NQ1 * NQ2; col += NT) g_column<C, FK>(prm, sNodB + (ebeg & 1) * C::SZ_NOD, sPt, sWt, sG, col, 0, e1base, e2base, n1, n2);
+  for (int col = tid; col < NQ1 * NQ2; col += NT) g_column<C, FK>(prm, 0, sNodB + (ebeg & 1) * C::SZ_NOD, sPt, sWt, sG, col, 0, e1base, e2base, n1, n2);
   __syncthreads();
 
-  // one pipeline step = one chunk of QC point-planes q0 of one element layer
-  const int nstep = (eend - ebeg + 1) * NCH;
+  // one pipeline step = one chunk of QC point-planes q0 of one form of one element layer (order: layer, form, chunk)
+  const int nstep = (eend - ebeg + 1) * NSUB;
   for (int s = 0; s <= nstep; s++) {
-    const int l = ebeg + s / NCH, ch = s % NCH;
+    const int l = ebeg + s / NSUB, ch = s % NSUB;
     // ======================= phase X: S3(s-1) [+ store of its layer]  ||  S1(s) =======================
-    if (ch == NCH - 1) fetch_nodes(l + 1);
+    if (ch == NSUB - 1) fetch_nodes(l + 1);
     if (ch == 0) fetch_row(l);
     if (tid == 0) sCnt[1] = NW;
     if (s > 0) {
-      const int e0 = ebeg + (s - 1) / NCH, qc = ((s - 1) % NCH) * QC;
+      const int e0 = ebeg + (s - 1) / NSUB, qc = ((s - 1) % NCH) * QC, form = ((s - 1) % NSUB) / NCH;
       const double* sTb0 = sTb0B + (e0 & 1) * C::SZ_TB0;
       const int* sRow = sRowB + (e0 & 1) * 4 * NB;
 #pragma unroll
@@ -532,11 +564,15 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
               const double ud = fma(da[b], gDD, va[b] * gDV), uv = fma(da[b], gVD, va[b] * gVV), um = va[b] * gM;
 #pragma unroll
               for (int a = 0; a < NB; a++) {
-                if (FK) accK[it][a][b] = fma(da[a], ud, fma(va[a], uv, accK[it][a][b]));
+                if (FK) {
+#pragma unroll
+                  for (int f = 0; f < NFORM; f++)
+                    if (f == form) accK[it][f][a][b] = fma(da[a], ud, fma(va[a], uv, accK[it][f][a][b]));
+                }
                 if (FM) accM[it][a][b] = fma(va[a], um, accM[it][a][b]);
               }
             }
-            if (prm.has_f && (imeta[it] >> 25 & 1)) {
+            if (prm.has_f && form == 0 && (imeta[it] >> 25 & 1)) {
               const double l2 = sL2[q0l * T1 * T2 + (imeta[it] >> 16 & 255)];
 #pragma unroll
               for (int a = 0; a < NB; a++) accF[it][a] = fma(va[a], l2, accF[it][a]);
@@ -544,7 +580,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
           }
         }
       }
-      if ((s - 1) % NCH == NCH - 1) {
+      if ((s - 1) % NSUB == NSUB - 1) {
       // store the completed entries of layer e0, carry the rest
       const bool last = e0 == n0 - 1;
 #pragma unroll
@@ -557,18 +593,28 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
             const int i0 = e0 + a;
             if (i0 < r0 || i0 >= r1) continue;
             const int rlo = sRow[a * 4], rwid = sRow[a * 4 + 1], rcum = sRow[a * 4 + 2];
-            const long long rowslot = (long long)rcum * W12 + (long long)rwid * ic12 + io12;
+            // scalar space: slot = R + pos;  ncomp components: row (I, crow) starts at (R ncomp + crow w) ncomp and holds
+            // (J, e) at pos ncomp + e, with R = first slot of basis row I, w = its width, pos = position of J in the row
+            const int nc = VEC ? prm.ncomp : 1;
+            const long long rowslot = (((long long)rcum * W12 + (long long)rwid * ic12) * nc + (long long)prm.crow * rwid * iw12) * nc + (long long)io12 * nc;
 #pragma unroll
             for (int b = 0; b < NB; b++) {
               if (a == 0 || b == 0 || last) {
-                const long long slot = rowslot + (long long)(e0 + b - rlo) * iw12;
-                if (FK) prm.valK[slot] = accK[it][a][b];
-                if (FM && prm.valM) prm.valM[slot] = accM[it][a][b] * prm.rho;
+                const long long slot = rowslot + (long long)(e0 + b - rlo) * iw12 * nc;
+                if (FK) {
+#pragma unroll
+                  for (int f = 0; f < NFORM; f++) prm.valK[slot + f] = accK[it][f][a][b];
+                }
+                if (FM && prm.valM) {
+                  if (nc == 1) prm.valM[slot] = accM[it][a][b] * prm.rho;
+                  else
+                    for (int e = 0; e < nc; e++) prm.valM[slot + e] = accM[it][a][b] * prm.rhoe[e];
+                }
               }
             }
             if (prm.has_f && (imeta[it] >> 25 & 1) && (a == 0 || last)) {
               const int il = imeta[it] >> 16 & 255;
-              prm.rhs[((long long)i0 * nd1 + i1lo + il / T2) * nd2 + i2lo + il % T2] = accF[it][a] * prm.vcoef;
+              prm.rhs[(((long long)i0 * nd1 + i1lo + il / T2) * nd2 + i2lo + il % T2) * nc + prm.crow] = accF[it][a] * prm.vcoef;
             }
           }
         }
@@ -577,7 +623,10 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
           accF[it][a] = a < P ? accF[it][a + 1] : 0.;
 #pragma unroll
           for (int b = 0; b < NB; b++) {
-            if (FK) accK[it][a][b] = (a < P && b < P) ? accK[it][a + 1][b + 1] : 0.;
+            if (FK) {
+#pragma unroll
+              for (int f = 0; f < NFORM; f++) accK[it][f][a][b] = (a < P && b < P) ? accK[it][f][a + 1][b + 1] : 0.;
+            }
             if (FM) accM[it][a][b] = (a < P && b < P) ? accM[it][a + 1][b + 1] : 0.;
           }
         }
@@ -608,7 +657,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
         wi = __shfl_sync(0xffffffffu, wi, 0);
       }
     }
-    if (ch == NCH - 1) park_nodes(l + 1);
+    if (ch == NSUB - 1) park_nodes(l + 1);
     if (ch == 0) park_row(l);
     __syncthreads();
     if (s >= nstep) break;
@@ -616,11 +665,11 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
     // ======================= phase Y: S2(s)  ||  G(s+1) =======================
     if (tid == 0) sCnt[0] = NW;
     const int ngc = s + 1 < nstep ? NGC : 0;
-    const int ln = ebeg + (s + 1) / NCH, qcn = ((s + 1) % NCH) * QC;
+    const int ln = ebeg + (s + 1) / NSUB, qcn = ((s + 1) % NCH) * QC, formn = ((s + 1) % NSUB) / NCH;
     for (int wi = warp; wi < NS2 + ngc;) {
       if (wi >= NS2) {
         const int col = (wi - NS2) * 32 + lane;
-        if (col < NQ1 * NQ2) g_column<C, FK>(prm, sNodB + (ln & 1) * C::SZ_NOD, sPt, sWt, sG, col, qcn, e1base, e2base, n1, n2);
+        if (col < NQ1 * NQ2) g_column<C, FK>(prm, formn, sNodB + (ln & 1) * C::SZ_NOD, sPt, sWt, sG, col, qcn, e1base, e2base, n1, n2);
       } else {
         const int part = wi % NPARTS, wj = wi / NPARTS;
         const int i1l = wj / C::WPI2, L = (wj % C::WPI2) * 32 + lane, i1 = i1lo + i1l;
@@ -644,9 +693,9 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
   }
 }
 
-template <class C, bool FK, bool FM>
+template <class C, bool FK, bool FM, int NFORM = 1, bool VEC = false>
 int launch_rows_cfg(b2_ctx* ctx, RowParams& prm) {
-  auto kern = k_rows3d<C, FK, FM>;
+  auto kern = k_rows3d<C, FK, FM, NFORM, VEC>;
   const size_t smem = sizeof(double) * C::TOTAL;
   static_assert(sizeof(double) * C::TOTAL <= 227 * 1024, "tile does not fit in shared memory");
   B2_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -684,13 +733,74 @@ int launch_rows_forms(b2_ctx* ctx, RowParams& prm, bool fk, bool fm) {
   return launch_rows_cfg<C, false, true>(ctx, prm);
 }
 
+// Vector-valued space (3 components): one launch per (matrix form, row component).  Stiffness-like forms (any 3x3 block
+// D[c][1+x][e][1+y], e.g. elasticity) run the general-coefficient pipeline with the 3 column components as forms; mass-like
+// forms (D[c][0][e][0]) run the scalar mass chain once and store rho[c][e] M; the load vector rides along.
+int launch_rows_vector(b2_ctx* ctx, RowParams& base, const FormView& F, const double* const* D_host, const double* const* C_host, int P) {
+  constexpr int nc = 3, na = 4;
+  if (P != 1 && P != 2) return B2_EUNSUPPORTED;
+  if (F.nvec > 1 || (F.nmat == 0 && F.nvec == 0)) return B2_EUNSUPPORTED;
+  int kind[B2_MAX_FORMS];  // 0 stiffness-like, 1 mass-like
+  for (int m = 0; m < F.nmat; m++) {
+    bool gg = false, mass = false, mixed = false;
+    for (int c = 0; c < nc; c++)
+      for (int e = 0; e < nc; e++)
+        for (int x = 0; x < na; x++)
+          for (int y = 0; y < na; y++) {
+            const double v = D_host[m][((c * na + x) * nc + e) * na + y];
+            if (v == 0.) continue;
+            if (x && y) gg = true;
+            else if (!x && !y) mass = true;
+            else mixed = true;
+          }
+    if (mixed || (gg && mass) || (!gg && !mass)) return B2_EUNSUPPORTED;
+    kind[m] = gg ? 0 : 1;
+  }
+  if (F.nvec)
+    for (int c = 0; c < nc; c++)
+      for (int x = 1; x < na; x++)
+        if (C_host[0][c * na + x] != 0.) return B2_EUNSUPPORTED;
+  for (int c = 0; c < nc; c++) {
+    bool want_f = F.nvec > 0;
+    for (int m = 0; m <= F.nmat; m++) {
+      if (m == F.nmat && !want_f) break;
+      RowParams prm = base;
+      prm.crow = c;
+      prm.has_f = want_f;
+      if (want_f) {
+        prm.vcoef = C_host[0][c * na];
+        prm.rhs = F.rhs[0];
+        want_f = false;
+      }
+      int rc;
+      if (m < F.nmat && kind[m] == 0) {
+        for (int e = 0; e < nc; e++)
+          for (int x = 0; x < 3; x++)
+            for (int y = 0; y < 3; y++) prm.dm[e][x * 3 + y] = D_host[m][((c * na + 1 + x) * nc + e) * na + 1 + y];
+        prm.valK = F.values[m];
+        rc = P == 1 ? launch_rows_cfg<RCfg<1, 8, 8, 2, 256, false, 10>, true, false, 3, true>(ctx, prm) : launch_rows_cfg<RCfg<2, 4, 4, 3, 256, false, 10>, true, false, 3, true>(ctx, prm);
+      } else {
+        // mass-like form, or the load vector alone (mass chain without a matrix)
+        prm.valM = nullptr;
+        if (m < F.nmat) {
+          for (int e = 0; e < nc; e++) prm.rhoe[e] = D_host[m][((c * na) * nc + e) * na];
+          prm.valM = F.values[m];
+        }
+        rc = P == 1 ? launch_rows_cfg<RCfg<1, 8, 8, 2, 256, false>, false, true, 1, true>(ctx, prm) : launch_rows_cfg<RCfg<2, 4, 4, 3, 256, false>, false, true, 1, true>(ctx, prm);
+      }
+      if (rc != B2_OK) return rc;
+    }
+  }
+  return B2_OK;
+}
+
 }  // namespace
 
 // Owner-computes assembly of the dof planes [plane_begin, plane_end) of dimension 0.  Returns
 // B2_EUNSUPPORTED when the configuration is outside the specialised kernel (caller falls back).
 int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad, const BasisView& B, const QuadView& Q, const GeomView& G, const FormView& F,
                          const double* const* D_host, const double* const* C_host, long long plane_begin, long long plane_end) {
-  if (B.ndims != 3 || B.ncomp != 1) return B2_EUNSUPPORTED;
+  if (B.ndims != 3 || (B.ncomp != 1 && B.ncomp != 3)) return B2_EUNSUPPORTED;
   const int P = B.p[0];
   if (B.p[1] != P || B.p[2] != P || P < 1 || P > 3) return B2_EUNSUPPORTED;
   for (int d = 0; d < 3; d++) {
@@ -710,6 +820,24 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
   prm.plane_end = (int)plane_end;
   prm.rho = 1.;
   prm.kc[0] = prm.kc[3] = prm.kc[5] = 1.;
+  prm.ncomp = B.ncomp;
+  // dominant coefficient set per dimension and its table at the 1-D points (host copy of what get_tabs uploaded)
+  for (int d = 0; d < 3; d++) {
+    std::vector<int> count(basis->nsets[d], 0);
+    for (int e = 0; e < B.nel[d]; e++) count[basis->setidx[d][e]]++;
+    const int cs = (int)(std::max_element(count.begin(), count.end()) - count.begin());
+    prm.cset[d] = cs;
+    for (int q = 0; q <= P; q++)
+      for (int a = 0; a <= P; a++) {
+        const double* c = &basis->coeffs[d][((size_t)cs * (P + 1) + a) * (P + 1)];
+        const double x = quad->pts[d][q];
+        double v = c[0], g = 0.;
+        for (int j = 1; j <= P; j++) { g = g * x + v; v = v * x + c[j]; }
+        prm.ctab[d][q][a][0] = v;
+        prm.ctab[d][q][a][1] = g;
+      }
+  }
+  if (B.ncomp == 3) return launch_rows_vector(ctx, prm, F, D_host, C_host, P);
   bool fk = false, fm = false;
   for (int m = 0; m < F.nmat; m++) {
     const double* D = D_host[m];  // [4][4]
@@ -734,22 +862,6 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
       prm.rho = D[0];
       prm.valM = F.values[m];
     }
-  }
-  // dominant coefficient set per dimension and its table at the 1-D points (host copy of what get_tabs uploaded)
-  for (int d = 0; d < 3; d++) {
-    std::vector<int> count(basis->nsets[d], 0);
-    for (int e = 0; e < B.nel[d]; e++) count[basis->setidx[d][e]]++;
-    const int cs = (int)(std::max_element(count.begin(), count.end()) - count.begin());
-    prm.cset[d] = cs;
-    for (int q = 0; q <= P; q++)
-      for (int a = 0; a <= P; a++) {
-        const double* c = &basis->coeffs[d][((size_t)cs * (P + 1) + a) * (P + 1)];
-        const double x = quad->pts[d][q];
-        double v = c[0], g = 0.;
-        for (int j = 1; j <= P; j++) { g = g * x + v; v = v * x + c[j]; }
-        prm.ctab[d][q][a][0] = v;
-        prm.ctab[d][q][a][1] = g;
-      }
   }
   prm.iso = prm.kc[1] == 0. && prm.kc[2] == 0. && prm.kc[4] == 0. && prm.kc[0] == prm.kc[3] && prm.kc[0] == prm.kc[5];
   if (F.nvec) {

@@ -136,23 +136,34 @@ ROWS_CASES = [
     dict(nelems=(10, 9, 11), degree=2), dict(nelems=(9, 8, 7), degree=1), dict(nelems=(3, 13, 18), degree=2), dict(nelems=(1, 1, 1), degree=2),
     dict(nelems=(2, 1, 1), degree=1), dict(nelems=(6, 5, 4), degree=2, btype='std'), dict(nelems=(5, 4, 6), degree=3), dict(nelems=(12, 15), degree=2),
     dict(nelems=(5, 4, 5), degree=2, ncomp=3), dict(nelems=(8, 7, 10), degree=3), dict(nelems=(1, 1, 1), degree=3), dict(nelems=(3, 2, 2), degree=4),
+    dict(nelems=(6, 7, 5), degree=2, ncomp=3, vector_forms=True), dict(nelems=(9, 4, 9), degree=1, ncomp=3, vector_forms=True),
+    dict(nelems=(1, 1, 1), degree=2, ncomp=3, vector_forms=True), dict(nelems=(3, 3, 2), degree=3, ncomp=3, vector_forms=True),
 ]
 
 
 @pytest.mark.parametrize('nseg', [0, 1, 3])
-@pytest.mark.parametrize('case', ROWS_CASES, ids=lambda c: 'x'.join(map(str, c['nelems'])) + 'p{}c{}'.format(c['degree'], c.get('ncomp', 1)) + c.get('btype', ''))
+@pytest.mark.parametrize('case', ROWS_CASES, ids=lambda c: 'x'.join(map(str, c['nelems'])) + 'p{}c{}'.format(c['degree'], c.get('ncomp', 1)) + c.get('btype', '') + ('v' if c.get('vector_forms') else ''))
 def test_rows_plane_ranges(ctx, case, nseg):
+    case = dict(case)
     '''b2_assemble_rows_device: physical coefficients (anisotropic conductivity, density, load) against the oracle; disjoint
     plane ranges written into one poisoned array give the full result (the multi-GPU decomposition: no exchange, no zero-fill),
     and rows outside a range are not touched.  Covers the specialised owner-computes kernel (3-D scalar p=1,2 splines) and the
     coverage path (everything else).'''
     import torch
-    prob = _random_problem(seed=hash(str(case)) % 2**31, **case)
+    prob = _random_problem(seed=hash(str(case)) % 2**31, **{k: v for k, v in case.items() if k != 'vector_forms'})
     nd, nc = prob.ndims, prob.ncomp
     rng = numpy.random.RandomState(11)
     A = rng.rand(nd, nd)
     Ds = [engine.form_stiffness(nd, nc, conductivity=A @ A.T + numpy.eye(nd)), 2.5 * engine.form_mass(nd, nc)]
     Cs = [-.75 * engine.form_load(nd, nc)]
+    if nc == nd == 3 and case.get('vector_forms'):
+        # elasticity, an arbitrary (non-symmetric) gradient-gradient coupling of the components, a full component mass matrix
+        Dgg = numpy.zeros((nc, nd + 1, nc, nd + 1))
+        Dgg[:, 1:, :, 1:] = rng.rand(nc, nd, nc, nd) - .5
+        Dm = numpy.zeros((nc, nd + 1, nc, nd + 1))
+        Dm[:, 0, :, 0] = rng.rand(nc, nc)
+        Ds = [engine.form_elasticity(nd, 1.3, .7), Dgg, Dm]
+        Cs = [engine.form_load(nd, nc, f=[.3, -1.1, 2.])]
     mats, vecs = c_oracle.assemble(prob, [('generic', D) for D in Ds], [('generic', C) for C in Cs])
     plan = _plan(ctx, prob)
     rowptr, _ = plan.csr_pattern()
