@@ -583,9 +583,33 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
       if ((s - 1) % NSUB == NSUB - 1) {
       // store the completed entries of layer e0, carry the rest
       const bool last = e0 == n0 - 1;
+      // interior layer of a scalar space (the common case): all P+1 rows have the full width 2P+1, their first coupled dof is
+      // i0-P and they all lie in the planes of this launch -- the slot arithmetic collapses to one 64-bit base per row
+      const bool interior = !VEC && e0 >= P && e0 <= n0 - 1 - P && e0 >= r0 && e0 + P < r1;
 #pragma unroll
       for (int it = 0; it < IPT; it++) {
-        if (imeta[it] >> 24 & 1) {
+        if (interior) {
+          if (imeta[it] >> 24 & 1) {
+            const int iw12 = imeta[it] & 255;
+            const long long b12 = (long long)WD * sIc[it * NT + tid] + (imeta[it] >> 8 & 255);
+#pragma unroll
+            for (int a = 0; a < NB; a++) {
+              const long long ra = (long long)sRow[a * 4 + 2] * W12 + b12;
+#pragma unroll
+              for (int b = 0; b < NB; b++) {
+                if (a == 0 || b == 0) {
+                  const long long slot = ra + (P - a + b) * iw12;
+                  if (FK) prm.valK[slot] = accK[it][0][a][b];
+                  if (FM && prm.valM) prm.valM[slot] = accM[it][a][b] * prm.rho;
+                }
+              }
+            }
+            if (prm.has_f && (imeta[it] >> 25 & 1)) {
+              const int il = imeta[it] >> 16 & 255;
+              prm.rhs[((long long)e0 * nd1 + i1lo + il / T2) * nd2 + i2lo + il % T2] = accF[it][0] * prm.vcoef;
+            }
+          }
+        } else if (imeta[it] >> 24 & 1) {
           const long long ic12 = sIc[it * NT + tid];
           const int iw12 = imeta[it] & 255, io12 = imeta[it] >> 8 & 255;
 #pragma unroll
