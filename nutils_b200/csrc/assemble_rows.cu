@@ -263,6 +263,18 @@ __device__ __forceinline__ void s2_item(const RowParams& prm, const double* __re
   if (diag) sL2[(q0l * T1 + i1l) * T2 + i2l] = l2;
 }
 
+// Out-of-line variants for halos that contain elements with a non-dominant coefficient set (domain boundary): the 1-D factors
+// come from shared memory.  Kept out of the main instruction stream (the kernel is I-cache sensitive: ~6 k instructions).
+template <class C, bool FK, bool FM, int PART, int NPARTS>
+__device__ __noinline__ void s1_item_tab(const RowParams& prm, const double* sG, const double* sTb2, double* sT1, double* sL1, int i2, int i2l, int L, int n2) {
+  s1_item<C, FK, FM, PART, NPARTS, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+}
+template <class C, bool FK, bool FM, int PART, int NPARTS>
+__device__ __noinline__ void s2_item_tab(const RowParams& prm, const double* sT1, const double* sTb1, const double* sL1, double* sT2, double* sL2, int i1, int i1l, int L,
+                                         int n1, bool want_f) {
+  s2_item<C, FK, FM, PART, NPARTS, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, want_f);
+}
+
 // ---- G: geometry of one (Q1, Q2) column of the halo, the QC points q0 = qc.. of the current chunk ----
 // Trilinear map x = sum_v phi_v X_v of the element: the interpolations along dimensions 2 and 1 are shared by the points of the
 // column (J[:,0] does not depend on xi0; J[:,1], J[:,2] are linear in xi0); adj(J), det and Ghat = w/|det| adj K adj^T per point.
@@ -526,14 +538,13 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
       }
     }
 
-  // ---- prologue: G of the first step ----
-  __syncthreads();
-  for (int col = tid; col < NQ1 * NQ2; col += NT) g_column<C, FK>(prm, 0, sNodB + (ebeg & 1) * C::SZ_NOD, sPt, sWt, sG, col, 0, e1base, e2base, n1, n2);
   __syncthreads();
 
   // one pipeline step = one chunk of QC point-planes q0 of one form of one element layer (order: layer, form, chunk)
+  // (the loop starts at s = -1 with phase Y only: that is the prologue G(0), through the one call site of g_column)
   const int nstep = (eend - ebeg + 1) * NSUB;
-  for (int s = 0; s <= nstep; s++) {
+  for (int s = -1; s <= nstep; s++) {
+    if (s >= 0) {
     const int l = ebeg + s / NSUB, ch = s % NSUB;
     // ======================= phase X: S3(s-1) [+ store of its layer]  ||  S1(s) =======================
     if (ch == NSUB - 1) fetch_nodes(l + 1);
@@ -670,10 +681,10 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
             else if (part == 1) s1_item<C, FK, FM, 1, 3, true>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
             else s1_item<C, FK, FM, 2, 3, true>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
           } else {
-            if (NPARTS1 == 1) s1_item<C, FK, FM, 0, 1, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
-            else if (part == 0) s1_item<C, FK, FM, 0, 3, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
-            else if (part == 1) s1_item<C, FK, FM, 1, 3, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
-            else s1_item<C, FK, FM, 2, 3, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+            if (NPARTS1 == 1) s1_item_tab<C, FK, FM, 0, 1>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+            else if (part == 0) s1_item_tab<C, FK, FM, 0, 3>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+            else if (part == 1) s1_item_tab<C, FK, FM, 1, 3>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
+            else s1_item_tab<C, FK, FM, 2, 3>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
           }
         }
         __syncwarp();
@@ -685,14 +696,16 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
     if (ch == 0) park_row(l);
     __syncthreads();
     if (s >= nstep) break;
+    }
 
     // ======================= phase Y: S2(s)  ||  G(s+1) =======================
     if (tid == 0) sCnt[0] = NW;
     const int ngc = s + 1 < nstep ? NGC : 0;
     const int ln = ebeg + (s + 1) / NSUB, qcn = ((s + 1) % NCH) * QC, formn = ((s + 1) % NSUB) / NCH;
-    for (int wi = warp; wi < NS2 + ngc;) {
-      if (wi >= NS2) {
-        const int col = (wi - NS2) * 32 + lane;
+    const int ns2 = s >= 0 ? NS2 : 0;
+    for (int wi = warp; wi < ns2 + ngc;) {
+      if (wi >= ns2) {
+        const int col = (wi - ns2) * 32 + lane;
         if (col < NQ1 * NQ2) g_column<C, FK>(prm, formn, sNodB + (ln & 1) * C::SZ_NOD, sPt, sWt, sG, col, qcn, e1base, e2base, n1, n2);
       } else {
         const int part = wi % NPARTS, wj = wi / NPARTS;
@@ -703,9 +716,9 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
             else if (part == 0) s2_item<C, FK, FM, 0, 2, true>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
             else s2_item<C, FK, FM, 1, 2, true>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
           } else {
-            if (NPARTS == 1) s2_item<C, FK, FM, 0, 1, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
-            else if (part == 0) s2_item<C, FK, FM, 0, 2, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
-            else s2_item<C, FK, FM, 1, 2, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+            if (NPARTS == 1) s2_item_tab<C, FK, FM, 0, 1>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+            else if (part == 0) s2_item_tab<C, FK, FM, 0, 2>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+            else s2_item_tab<C, FK, FM, 1, 2>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
           }
         }
       }
