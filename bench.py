@@ -38,6 +38,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'assembled DOFs/sec (stiffness+mass+RHS), 3D Poisson p=2'
 UNIT = 'DOF/s'
+METRIC_ELAST = 'assembled DOFs/sec (stiffness+RHS), 3D elasticity p=2'
 
 
 def make_nodes(shape, seed=0, warp=.2):
@@ -49,14 +50,16 @@ def make_nodes(shape, seed=0, warp=.2):
     return X
 
 
-def workload_name(n, degree, N):
+def workload_name(n, degree, N, elast=False):
     mesh = '{}x{}x{}'.format(n * N, n, n)
+    if elast:
+        return '3D linear elasticity {} p={} spline (3 components), gauss{} ({} pts), K+f, nodal multilinear geometry (per-point Jacobians)'.format(mesh, degree, 2 * degree, (degree + 1) ** 3)
     return '3D Poisson {} p={} spline, gauss{} ({} pts), K+M+f, nodal multilinear geometry (per-point Jacobians)'.format(mesh, degree, 2 * degree, (degree + 1) ** 3)
 
 
 # ---- CPU arm: the oracle port on host cores ----------------------------------------------------------
 
-def cpu_assembly_rate(n, degree, nthreads=0, repeats=1):
+def cpu_assembly_rate(n, degree, nthreads=0, repeats=1, elast=False):
     '''DOF/s of the C restatement of the reference algorithm (element loop on all cores + serial
     sort/unique/accumulate), on an n^3 sample of the workload.'''
     from nutils_b200 import bspline, points
@@ -64,12 +67,14 @@ def cpu_assembly_rate(n, degree, nthreads=0, repeats=1):
     b1 = [bspline.spline_basis_1d(n, degree) for _ in range(3)]
     rules = points.tensor_gauss(3, 2 * degree)
     prob = fem_oracle.Problem((n,) * 3, [degree] * 3, [b.coeffs for b in b1], [b.setidx for b in b1], [b.start for b in b1],
-                              [b.ndofs for b in b1], [r[0] for r in rules], [r[1] for r in rules], make_nodes((n,) * 3))
+                              [b.ndofs for b in b1], [r[0] for r in rules], [r[1] for r in rules], make_nodes((n,) * 3), ncomp=3 if elast else 1)
+    mforms = [('elasticity', 1., .5 / .3 - 1.)] if elast else [('stiffness',), ('mass',)]
+    vforms = [('generic', numpy.array([[0., 0, 0, 0], [0, 0, 0, 0], [-1., 0, 0, 0]]))] if elast else [('load',)]
     c_oracle.lib()
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        c_oracle.assemble(prob, [('stiffness',), ('mass',)], [('load',)], nthreads=nthreads)
+        c_oracle.assemble(prob, mforms, vforms, nthreads=nthreads)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return prob.ndofs / best, best, prob.ndofs, (nthreads or c_oracle.max_threads())
@@ -79,10 +84,11 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    n = min(args.cpu_n, 32)  # keeps warmup+steps repetitions within a few minutes
+    # bounded sample: ~1.2 s per step at 32^3 on 16 cores, ~0.5 s at 24^3 -- the whole run stays within a few minutes
+    n = min(args.cpu_n, 32 if args.warmup + args.steps <= 40 else 24)
     times = []
     for i in range(args.warmup + args.steps):
-        rate, dt, ndofs, cores = cpu_assembly_rate(n, args.degree)
+        rate, dt, ndofs, cores = cpu_assembly_rate(n if args.workload == 'poisson' else min(n, 20), args.degree, elast=args.workload == 'elasticity')
         if i >= args.warmup:
             times.append(dt)
     t = sum(times) / len(times)
@@ -168,11 +174,18 @@ def run_b200(args):
     b1 = [bspline.spline_basis_1d(m, p) for m in shape]
     rules = points.tensor_gauss(3, 2 * p)
     nodes = make_nodes(shape)
-    plan = engine.Plan(ctx, b1, rules, nodes)
+    elast = args.workload == 'elasticity'
+    ncomp = 3 if elast else 1
+    plan = engine.Plan(ctx, b1, rules, nodes, ncomp=ncomp)
     rows_path = args.path == 'rows'
-    layout = (distributed.PlaneLayout if rows_path else distributed.SlabLayout)(b1, 1, rank, world, plan.row_offset)
-    Ds = [engine.form_stiffness(3), engine.form_mass(3)]
-    Cs = [engine.form_load(3)]
+    layout = (distributed.PlaneLayout if rows_path else distributed.SlabLayout)(b1, ncomp, rank, world, plan.row_offset)
+    if elast:
+        # BASELINE.json configs[2]: the 3-D extension of examples/elasticity.py (lambda = 1, mu = .5/nu - 1 with nu = .3, body force -e_z)
+        Ds = [engine.form_elasticity(3, 1., .5 / .3 - 1.)]
+        Cs = [numpy.array([[0., 0, 0, 0], [0, 0, 0, 0], [-1., 0, 0, 0]])]
+    else:
+        Ds = [engine.form_stiffness(3), engine.form_mass(3)]
+        Cs = [engine.form_load(3)]
     dev = torch.device('cuda', local)
     mats = [torch.empty(layout.nvalues, dtype=torch.float64, device=dev) for _ in Ds]
     vecs = [torch.empty(layout.nrows, dtype=torch.float64, device=dev) for _ in Cs]
@@ -227,19 +240,20 @@ def run_b200(args):
 
     # sanity inside the bench: partition of unity on the assembled result of the last step (sum M == sum f)
     # (N>1: the ranks' windows tile the global arrays, so the global sums are the all-reduced window sums)
-    sums = torch.stack([mats[1].sum(), vecs[0].sum()])
+    sums = torch.stack([mats[-1].sum(), vecs[0].sum()])
     if world > 1:
         if not rows_path:  # shared planes are complete on both neighbours after the exchange: count the owned rows only
             sums = torch.stack([mats[1][:layout.off_own_hi - layout.off_lo].sum() if hasattr(layout, 'off_own_hi') else mats[1].sum(), vecs[0][layout.own_rows].sum()])
         dist.all_reduce(sums)
     msum, fsum = (float(x) for x in sums.tolist())
-    if world > 1 and not rows_path:
+    if (world > 1 and not rows_path) or elast:
         msum = fsum = None  # the value windows of the slab layout overlap; the row-sum check is only meaningful for the rows path
 
     # roofline of the assembly kernel (rank-local bytes / rank-local kernel time)
     nnodes_local = (layout.elem_layers[1] - layout.elem_layers[0] if rows_path else (layout.elem_range[1] - layout.elem_range[0]) // (n * n)) + 1
     alg_bytes = 8. * (len(Ds) * layout.nvalues + len(Cs) * layout.nrows + 3 * nnodes_local * (n + 1) * (n + 1))
-    kernel_avg_ms = kernel_ms / max(kernel_launches, 1)
+    # the dominant kernel's device time per step (a vector-valued step is one launch per row component)
+    kernel_avg_ms = kernel_ms / max(args.steps, 1)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -257,12 +271,12 @@ def run_b200(args):
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (of fallback)',
                 'kernel': 'k_rows3d (owner-computes assembly kernel; the only kernel of the step)' if rows_path else 'assembly kernel (zero-fill excluded)',
                 'secondary_ceiling': 'FP64 pipe: the kernel issues ~1.46e9 warp-level FP64 instructions at 128^3 (see DESIGN.md), 2.5 ms at the measured 33.8 TFLOP/s DFMA rate', 'kernel_ms': kernel_avg_ms, 'algorithmic_bytes': alg_bytes,
-                'kernel_share_of_step': kernel_avg_ms / ms_per_step}
+                'kernel_share_of_step': kernel_avg_ms / ms_per_step, 'kernel_launches_per_step': kernel_launches / max(args.steps, 1)}
 
     # end-to-end through the host-buffer C-ABI call (single GPU path; ranks run it on their own slab problem)
     e2e = None
     if not args.no_e2e:
-        lplan = plan if world == 1 else engine.Plan(ctx, [bspline.spline_basis_1d(n, p) for _ in range(3)], rules, make_nodes((n, n, n), seed=rank))
+        lplan = plan if world == 1 else engine.Plan(ctx, [bspline.spline_basis_1d(n, p) for _ in range(3)], rules, make_nodes((n, n, n), seed=rank), ncomp=ncomp)
         lnodes = ctx.host_empty(lplan.nodes.shape)
         lnodes[...] = lplan.nodes
         hv = [ctx.host_empty(lplan.nnz) for _ in Ds]
@@ -288,21 +302,22 @@ def run_b200(args):
         e2e = {'value': lplan.ndofs * world / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(lnodes.nbytes),
                'd2h_bytes_per_step': int(sum(a.nbytes for a in hv + hr)), 'ms_per_step': dt * 1e3, 'steps': ksteps,
                'note': 'b2_assemble_host with pinned host buffers; per rank an independent {}^3 problem'.format(n) if world > 1 else 'b2_assemble_host with pinned host buffers'}
-        if world == 1:
+        if world == 1 and not elast:
             # the host result of the e2e path doubles as a correctness check of the timed configuration
             assert abs(hv[1].sum() - hr[0].sum()) <= 1e-10 * abs(hr[0].sum()), 'sum(M) != sum(f)'
 
     cpu = None
     if rank == 0 and not args.no_cpu:
-        rate, dt, ndofs_s, cores = cpu_assembly_rate(args.cpu_n, p)
+        cpu_n = args.cpu_n if not elast else min(args.cpu_n, 24)
+        rate, dt, ndofs_s, cores = cpu_assembly_rate(cpu_n, p, elast=elast)
         cpu = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'seconds': dt,
-               'sample': '{}^3 elements ({} dofs) of the same workload; C port of the reference algorithm (oracle/fem_oracle.c): threaded element loop + serial stable sort/unique/accumulate'.format(args.cpu_n, ndofs_s)}
+               'sample': '{}^3 elements ({} dofs) of the same workload; C port of the reference algorithm (oracle/fem_oracle.c): threaded element loop + serial stable sort/unique/accumulate'.format(cpu_n, ndofs_s)}
 
     if rank == 0:
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
+            'metric': METRIC_ELAST if elast else METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': workload_name(n, p, world), 'ndofs': ndofs_global, 'nnz_per_matrix': plan.nnz, 'nelems': plan.ntotal,
+            'config': {'workload': workload_name(n, p, world, elast), 'ndofs': ndofs_global, 'nnz_per_matrix': plan.nnz, 'nelems': plan.ntotal,
                        'step': ('one owner-computes assembly launch (every value written once; no zero-fill, no exchange)' if rows_path else
                                 'zero K,M,f + one assembly launch' + (' + neighbour exchange of shared dof planes (NCCL send/recv)' if world > 1 else '')),
                        'l2': 'outputs {:.2f} GB per rank >> 126 MB L2 (no flush needed)'.format(8e-9 * (len(Ds) * layout.nvalues + layout.nrows)),
@@ -321,7 +336,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--n', type=int, default=128, help='elements per direction and GPU')
@@ -330,6 +345,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--workload', default='poisson', choices=['poisson', 'elasticity'], help='poisson: BASELINE.json configs[1] (the metric); elasticity: configs[2] (use --n 96)')
     ap.add_argument('--path', default='rows', choices=['rows', 'scatter'], help='rows: owner-computes kernel (default); scatter: element-scatter kernels')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
