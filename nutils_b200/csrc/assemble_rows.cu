@@ -912,10 +912,8 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
   // Tile / thread configuration.  Measured at 128^3 (profiles/r01/variants.txt): few register-rich warps with unsplit
   // S1/S2 items (256 threads, 230 registers, no spills) beat more, thinner warps (512 threads cap at 128 registers and spill).
   const int64_t variant = ctx->opts.count("rows_variant") ? ctx->opts["rows_variant"] : 0;
-  if (P == 1) {
-    if (variant == 1) return launch_rows_forms<RCfg<1, 8, 8, 2, 512, true>>(ctx, prm, fk, fm);
-    return launch_rows_forms<RCfg<1, 8, 8, 2, 256, false>>(ctx, prm, fk, fm);
-  }
+  (void)variant;
+  if (P == 1) return launch_rows_forms<RCfg<1, 8, 8, 2, 256, false>>(ctx, prm, fk, fm);
   if (P == 3) {
     // two chunks of two point-planes per layer; K and M in separate launches: 2 x 16 accumulators per dof pair and form
     // for two dof pairs per thread would not fit the register file together
@@ -930,9 +928,9 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
     pm.has_f = 0;
     return launch_rows_cfg<C3, false, true>(ctx, pm);
   }
-  if (variant == 1) return launch_rows_forms<RCfg<2, 4, 4, 3, 512, true>>(ctx, prm, fk, fm);
 #ifdef B2_EXPERIMENT
   if (fk && fm) {
+    if (variant == 1) return launch_rows_cfg<RCfg<2, 4, 4, 3, 512, true>, true, true>(ctx, prm);
     if (variant == 2) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, true>, true, true>(ctx, prm);
     if (variant == 3) return launch_rows_cfg<RCfg<2, 5, 3, 3, 384, true>, true, true>(ctx, prm);
     if (variant == 4) return launch_rows_cfg<RCfg<2, 3, 5, 3, 384, true>, true, true>(ctx, prm);
