@@ -192,6 +192,38 @@ def test_rows_plane_ranges(ctx, case, nseg):
     assert util.relerr(rhs[0].cpu().numpy(), vecs[0]) <= TOL
 
 
+def test_rows_nonuniform_knots_and_long_march(ctx):
+    '''Graded knot vectors give every element its own coefficient set (the kernel's table-driven variants instead of the
+    constant-bank fast path), and 700 element layers exceed one marching segment (512 layers), forcing a split.'''
+    import torch
+    rng = numpy.random.RandomState(4)
+    dev = torch.device('cuda', 0)
+    for nelems, degree in (((9, 8, 7), 2), ((700, 2, 3), 2), ((6, 9, 5), 1), ((5, 6, 4), 3)):
+        knots = [numpy.concatenate([[0.], numpy.cumsum(.3 + rng.rand(n))]) for n in nelems]
+        b1 = [bspline.spline_basis_1d(n, degree, knotvalues=k) for n, k in zip(nelems, knots)]
+        assert degree == 1 or len(b1[1].coeffs) > 3 or nelems[1] <= 3  # (hat functions are the same polynomials on every element)
+        rules = points.tensor_gauss(3, 2 * degree)
+        X = numpy.stack(numpy.meshgrid(*knots, indexing='ij'))
+        X = X + .1 * (rng.rand(*X.shape) - .5)
+        prob = fem_oracle.Problem(nelems, [degree] * 3, [b.coeffs for b in b1], [b.setidx for b in b1], [b.start for b in b1],
+                                  [b.ndofs for b in b1], [r[0] for r in rules], [r[1] for r in rules], X)
+        Ds, Cs = [engine.form_stiffness(3), engine.form_mass(3)], [engine.form_load(3)]
+        mats, vecs = c_oracle.assemble(prob, [('generic', D) for D in Ds], [('generic', C) for C in Cs])
+        plan = _plan(ctx, prob)
+        rowptr, colidx = plan.csr_pattern()
+        assert numpy.array_equal(rowptr, mats[0][1]) and numpy.array_equal(colidx, mats[0][2])
+        vals = [torch.full((plan.nnz,), 9., dtype=torch.float64, device=dev) for _ in Ds]
+        rhs = [torch.full((plan.ndofs,), 9., dtype=torch.float64, device=dev)]
+        ctx.set_option('kernel', 2)  # the specialised kernel or an error
+        try:
+            plan.assemble_rows_device(Ds, Cs, vals, rhs)
+        finally:
+            ctx.set_option('kernel', 0)
+        for v, (ref, _, _) in zip(vals, mats):
+            assert util.relerr(v.cpu().numpy(), ref) <= TOL
+        assert util.relerr(rhs[0].cpu().numpy(), vecs[0]) <= TOL
+
+
 def test_rows_single_forms(ctx):
     # K only, M only, f only through the owner-computes kernel
     import torch
