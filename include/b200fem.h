@@ -171,6 +171,55 @@ int b2_assemble_host(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis* bas
                      int64_t elem_begin, int64_t elem_end,
                      int nmat, const double* const* D_host, double* const* values_host,
                      int nvec, const double* const* C_host, double* const* rhs_host);
+/* ---- element sets: trimmed topologies, ragged quadrature, pruned and rational bases ----------------
+ * The structured entry points above integrate EVERY element of the grid with ONE tensor rule.  An element set
+ * describes what the reference builds for the other topologies that still live on a structured grid:
+ *   - a subset of the elements (SubsetTopology / trimmed topologies, src/nutils/topology.py:1598-1660; the element
+ *     indices are what PrunedBasis keeps as _transmap, function.py:3118-3123);
+ *   - per-element point sets of different length, in element-local coordinates (PointsSequence._Plain over
+ *     ConcatPoints of the cut cells, pointsseq.py:324-332, points.py:257-337, element.py:669-680, 861-873);
+ *   - the pruned dof numbering (PrunedBasis._renumber, function.py:3121-3133): renumber[parent basis function] = new
+ *     index, or -1 (or >= nbasis_new) for functions without support on the subset; must be increasing over the kept
+ *     functions, which is what numeric.invmap of a sorted dof list gives;
+ *   - rational (NURBS) functions R_i = c_i B_i / W (examples/platewithhole.py:66-83): `scale` holds c_i per PARENT
+ *     basis function; `rational` selects the denominator: 0 none (scale only), 1 W = sum_j c_j B_j (the weight function
+ *     in the solution basis), 2 the weight function of a rational spline geometry (b2_geom_create_spline).
+ * elem_ids: int64[nsel], strictly increasing C-order element indices (NULL = all elements, nsel = their number).
+ * qoff: int64[nsel+1] offsets into qcoords (float64[npoints][ndims], xi in [0,1]) and qweights (float64[npoints]);
+ * NULL = every element uses the tensor rule passed at assembly time.  All arrays are copied. */
+typedef struct b2_elemset b2_elemset;
+int b2_elemset_create(b2_ctx* ctx, const b2_basis* basis, int64_t nsel, const int64_t* elem_ids,
+                      const int64_t* qoff, const double* qcoords, const double* qweights,
+                      const int64_t* renumber, int64_t nbasis_new, const double* scale, int rational, b2_elemset** out);
+int b2_elemset_destroy(b2_elemset* elemset);
+int64_t b2_elemset_ndofs(const b2_elemset* elemset);   /* nbasis_new * ncomp */
+int64_t b2_elemset_npoints(const b2_elemset* elemset); /* total number of quadrature points (0 for tensor rules) */
+
+/* Spline geometry x(xi) = sum_i B_i(xi) X_i, or the rational map sum_i B_i w_i X_i / sum_i B_i w_i (the NURBS map of
+ * examples/platewithhole.py:66-78 represented in the basis of the refined topology): gbasis is a scalar b2_basis on
+ * the same element grid, ctrl_host float64[ndims][nbasis] the control points X_i, weights_host float64[nbasis] or NULL.
+ * J = dx/dxi follows from the derivatives of the basis (function.py:1207-1231 applied to a spline geometry). */
+int b2_geom_create_spline(b2_ctx* ctx, const b2_basis* gbasis, const double* ctrl_host, const double* weights_host, b2_geom** out);
+
+/* CSR pattern of an element set: the sorted unique (row, col) pairs of the dofs that share a SELECTED element -- what
+ * the reference finds by argsort/unique over the COO keys (evaluable.py:588-616, 5646-5682) -- built on the device
+ * from the tensor structure (candidate box per row, kept if a selected element lies in the common support), two
+ * passes (count, scan, fill).  rowptr/colidx are materialised on the device; b2_pattern_export_*, _nnz, _nrows and
+ * _row_offset work on it like on the analytic pattern. */
+int b2_pattern_create_elemset(b2_ctx* ctx, const b2_elemset* elemset, b2_pattern** out);
+
+/* Element-scatter assembly of the selected elements [sel_begin, sel_end) (positions in elem_ids; 0, -1 = all):
+ * same forms and the same ACCUMULATE semantics as b2_assemble_device.  quad may be NULL when the element set
+ * carries its own points.  The slot of (row, col) is found by bisection in the row's sorted column list. */
+int b2_assemble_elemset_device(b2_ctx* ctx, const b2_pattern* pattern, const b2_elemset* elemset, const b2_quad* quad, const b2_geom* geom,
+                               int64_t sel_begin, int64_t sel_end,
+                               int nmat, const double* const* D_host, double* const* values_dev,
+                               int nvec, const double* const* C_host, double* const* rhs_dev);
+/* zero-fill + b2_assemble_elemset_device + copy to host buffers */
+int b2_assemble_elemset_host(b2_ctx* ctx, const b2_pattern* pattern, const b2_elemset* elemset, const b2_quad* quad, const b2_geom* geom,
+                             int nmat, const double* const* D_host, double* const* values_host,
+                             int nvec, const double* const* C_host, double* const* rhs_host);
+
 /* Experiments and profiling.  "kernel": 0 = automatic, 1 = generic (coverage) kernel only, 2 = specialised kernel or
  * B2_EUNSUPPORTED.  "path": 0 = b2_assemble_host uses the owner-computes rows path for the whole topology, 1 = always
  * the element-scatter path.  "rows_nseg": force the number of marching segments of the rows kernel (0 = automatic).

@@ -74,6 +74,14 @@ SIGNATURES = {
     'b2_pattern_export_device': (ctypes.c_int, [c_vp, c_vp, c_vp]),
     'b2_assemble_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
     'b2_assemble_rows_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
+    'b2_elemset_create': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, ctypes.c_int, p_vp]),
+    'b2_elemset_destroy': (ctypes.c_int, [c_vp]),
+    'b2_elemset_ndofs': (c_i64, [c_vp]),
+    'b2_elemset_npoints': (c_i64, [c_vp]),
+    'b2_geom_create_spline': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, p_vp]),
+    'b2_pattern_create_elemset': (ctypes.c_int, [c_vp, c_vp, p_vp]),
+    'b2_assemble_elemset_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
+    'b2_assemble_elemset_host': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
     'b2_assemble_host': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
 }
 

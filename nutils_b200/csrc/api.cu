@@ -419,7 +419,7 @@ extern "C" int b2_geom_create_nodal(b2_ctx* ctx, int ndims, const int64_t* nelem
 }
 
 extern "C" int b2_geom_update_nodal(b2_geom* g, const double* nodes_host) {
-  if (!g || !nodes_host) return B2_EINVAL;
+  if (!g || !nodes_host || g->gbasis) return B2_EINVAL;
   b2_ctx* ctx = g->ctx;
   B2_CUDA(ctx, cudaMemcpyAsync(g->d_nodes, nodes_host, sizeof(double) * g->nnodes * g->ndims, cudaMemcpyHostToDevice, ctx->stream));
   return B2_OK;
@@ -429,6 +429,10 @@ extern "C" int b2_geom_destroy(b2_geom* g) {
   if (!g) return B2_OK;
   cudaSetDevice(g->ctx->device);
   if (g->d_nodes) cudaFree(g->d_nodes);
+  if (g->d_ctrl) cudaFree(g->d_ctrl);
+  if (g->d_wts) cudaFree(g->d_wts);
+  for (int d = 0; d < B2_MAXD; d++)
+    if (g->d_gcoeffs[d]) cudaFree(g->d_gcoeffs[d]);
   delete g;
   return B2_OK;
 }
@@ -450,6 +454,12 @@ extern "C" int b2_pattern_create(b2_ctx* ctx, const b2_basis* basis, b2_pattern*
 }
 
 extern "C" int b2_pattern_destroy(b2_pattern* p) {
+  if (!p) return B2_OK;
+  if (p->d_rowptr_b || p->d_colidx_b) {
+    cudaSetDevice(p->ctx->device);
+    if (p->d_rowptr_b) cudaFree(p->d_rowptr_b);
+    if (p->d_colidx_b) cudaFree(p->d_colidx_b);
+  }
   delete p;
   return B2_OK;
 }
@@ -462,6 +472,11 @@ extern "C" int64_t b2_pattern_row_offset(const b2_pattern* p, int64_t row) {
   if (row == p->nrows) return p->nnz;
   const b2_basis* b = p->basis;
   const int nc = b->ncomp;
+  if (p->elemset) {
+    const int64_t In = row / nc, c = row % nc;
+    const long long r0 = p->rowptr_b[In], len = p->rowptr_b[In + 1] - r0;
+    return (r0 * nc + c * len) * nc;
+  }
   int64_t I = row / nc;
   const int c = (int)(row % nc);
   int i[B2_MAXD] = {0, 0, 0};
@@ -477,6 +492,7 @@ extern "C" int64_t b2_pattern_row_offset(const b2_pattern* p, int64_t row) {
 extern "C" int b2_pattern_export_device(b2_pattern* p, int64_t* rowptr_dev, int64_t* colidx_dev) {
   if (!p || !rowptr_dev || !colidx_dev) return B2_EINVAL;
   B2_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+  if (p->elemset) return launch_pattern_export_general(p->ctx, p->d_rowptr_b, p->d_colidx_b, p->nrows / p->basis->ncomp, p->basis->ncomp, (long long*)rowptr_dev, (long long*)colidx_dev);
   return launch_pattern_export(p->ctx, p->basis->view(), (long long*)rowptr_dev, (long long*)colidx_dev);
 }
 
@@ -488,7 +504,8 @@ extern "C" int b2_pattern_export_host(b2_pattern* p, int64_t* rowptr_host, int64
   B2_CUDA(ctx, cudaMalloc((void**)&d_rp, sizeof(long long) * (p->nrows + 1)));
   cudaError_t e = cudaMalloc((void**)&d_ci, sizeof(long long) * std::max<int64_t>(p->nnz, 1));
   if (e != cudaSuccess) { cudaFree(d_rp); return b2_cuda_fail(ctx, e, "cudaMalloc(colidx)"); }
-  int rc = launch_pattern_export(ctx, p->basis->view(), d_rp, d_ci);
+  int rc = p->elemset ? launch_pattern_export_general(ctx, p->d_rowptr_b, p->d_colidx_b, p->nrows / p->basis->ncomp, p->basis->ncomp, d_rp, d_ci)
+                      : launch_pattern_export(ctx, p->basis->view(), d_rp, d_ci);
   if (rc == B2_OK) {
     e = cudaMemcpyAsync(rowptr_host, d_rp, sizeof(long long) * (p->nrows + 1), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(colidx_host, d_ci, sizeof(long long) * p->nnz, cudaMemcpyDeviceToHost, ctx->stream);
@@ -531,85 +548,10 @@ static int get_tabs(b2_ctx* ctx, const b2_basis* cb, const b2_quad* q, TabDev* o
   return B2_OK;
 }
 
-// rows == false: integrate elements [elem_begin, elem_end) and ACCUMULATE into the outputs.
-// rows == true:  elem_begin/elem_end are dof planes of dimension 0; every stored value of those planes is WRITTEN.
-static int assemble_impl(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis* basis, const b2_quad* quad, const b2_geom* geom,
-                         int64_t elem_begin, int64_t elem_end, int nmat, const double* const* D_host, double* const* values_dev,
-                         int nvec, const double* const* C_host, double* const* rhs_dev, bool rows = false) {
-  if (!ctx || !pattern || !basis || !quad || !geom) return b2_fail(ctx, B2_EINVAL, "null argument");
-  if (nmat < 0 || nmat > B2_MAX_FORMS || nvec < 0 || nvec > B2_MAX_FORMS) return b2_fail(ctx, B2_EINVAL, "0..4 matrix and vector forms per call");
-  if ((nmat && (!D_host || !values_dev)) || (nvec && (!C_host || !rhs_dev))) return b2_fail(ctx, B2_EINVAL, "null form argument");
-  if (pattern->basis != basis) return b2_fail(ctx, B2_EINVAL, "pattern was built for a different basis");
-  if (quad->ndims != basis->ndims || geom->ndims != basis->ndims) return b2_fail(ctx, B2_EINVAL, "dimension mismatch");
-  int64_t ntot = 1;
-  for (int d = 0; d < basis->ndims; d++) {
-    if (geom->nel[d] != basis->nel[d]) return b2_fail(ctx, B2_EINVAL, "geometry and basis live on different topologies");
-    ntot *= basis->nel[d];
-  }
-  int64_t plane_begin = 0, plane_end = basis->ndofs_d[0];
-  if (rows) {
-    plane_begin = elem_begin;
-    plane_end = elem_end < 0 ? basis->ndofs_d[0] : elem_end;
-    if (plane_begin < 0 || plane_begin > plane_end || plane_end > basis->ndofs_d[0]) return b2_fail(ctx, B2_EINVAL, "invalid dof-plane range");
-    if (plane_begin == plane_end || (nmat == 0 && nvec == 0)) return B2_OK;
-    // elements of dimension 0 whose dofs touch the planes (start is non-decreasing)
-    int64_t e_lo = basis->nel[0], e_hi = -1;
-    for (int64_t e = 0; e < basis->nel[0]; e++)
-      if (basis->start[0][e] < plane_end && basis->start[0][e] + basis->p[0] >= plane_begin) { e_lo = std::min(e_lo, e); e_hi = std::max(e_hi, e); }
-    const int64_t per_layer = ntot / basis->nel[0];
-    elem_begin = e_lo * per_layer;
-    elem_end = (e_hi + 1) * per_layer;
-    if (e_hi < e_lo) elem_begin = elem_end = 0;
-  } else {
-    if (elem_end < 0) elem_end = ntot;
-    if (elem_begin < 0 || elem_begin > elem_end || elem_end > ntot) return b2_fail(ctx, B2_EINVAL, "invalid element range");
-    if (elem_begin == elem_end || (nmat == 0 && nvec == 0)) return B2_OK;
-  }
-  B2_CUDA(ctx, cudaSetDevice(ctx->device));
-
-  const int nd = basis->ndims, nc = basis->ncomp, na = nd + 1;
-  TabDev tabs;
-  int rc = get_tabs(ctx, basis, quad, &tabs);
-  if (rc != B2_OK) return rc;
-
-  BasisView B = basis->view();
-  QuadView Q;
-  memset(&Q, 0, sizeof(Q));
-  Q.nqt = 1;
-  for (int d = 0; d < nd; d++) {
-    Q.nq[d] = quad->nq[d];
-    Q.nqt *= quad->nq[d];
-    Q.x[d] = quad->d_x[d];
-    Q.w[d] = quad->d_w[d];
-    Q.tab[d] = tabs.tab[d];
-  }
-  GeomView G;
-  memset(&G, 0, sizeof(G));
-  G.nodes = geom->d_nodes;
-  G.nnodes = geom->nnodes;
-  {
-    long long s = 1;
-    for (int d = nd - 1; d >= 0; d--) { G.stride[d] = s; s *= geom->nel[d] + 1; }
-  }
-
-  const int64_t kernel_opt = ctx->opts.count("kernel") ? ctx->opts["kernel"] : 0;
-  for (int m = 0; m < nmat; m++)
-    if (!D_host[m] || !values_dev[m]) return b2_fail(ctx, B2_EINVAL, "null matrix form");
-  for (int v = 0; v < nvec; v++)
-    if (!C_host[v] || !rhs_dev[v]) return b2_fail(ctx, B2_EINVAL, "null vector form");
-  if (rows && kernel_opt != 1) {
-    // the specialised owner-computes kernel takes its coefficients as kernel parameters: no upload, no synchronisation
-    FormView F0;
-    memset(&F0, 0, sizeof(F0));
-    F0.nmat = nmat;
-    F0.nvec = nvec;
-    for (int m = 0; m < nmat; m++) F0.values[m] = values_dev[m];
-    for (int v = 0; v < nvec; v++) F0.rhs[v] = rhs_dev[v];
-    rc = launch_assemble_rows(ctx, basis, quad, B, Q, G, F0, D_host, C_host, plane_begin, plane_end);
-    if (rc != B2_EUNSUPPORTED) return rc;
-    if (kernel_opt >= 2) return b2_fail(ctx, B2_EUNSUPPORTED, "requested specialised kernel does not cover this configuration");
-  }
-
+// Sparse term lists of the coefficient tensors D_m / C_v, uploaded into the context's form buffer (synchronous small copy).
+int b2_upload_forms(b2_ctx* ctx, int nd, int nc, int nmat, const double* const* D_host, double* const* values_dev,
+                    int nvec, const double* const* C_host, double* const* rhs_dev, FormView* out) {
+  const int na = nd + 1;
   // sparse term lists of the coefficient tensors
   std::vector<int> termptr(1, 0), termxy;
   std::vector<double> termval, vcoef;
@@ -658,6 +600,95 @@ static int assemble_impl(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis*
   F.termxy = (const int*)(fb + off_xy);
   for (int m = 0; m < nmat; m++) F.values[m] = values_dev[m];
   for (int v = 0; v < nvec; v++) F.rhs[v] = rhs_dev[v];
+
+  *out = F;
+  return B2_OK;
+}
+
+// rows == false: integrate elements [elem_begin, elem_end) and ACCUMULATE into the outputs.
+// rows == true:  elem_begin/elem_end are dof planes of dimension 0; every stored value of those planes is WRITTEN.
+static int assemble_impl(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis* basis, const b2_quad* quad, const b2_geom* geom,
+                         int64_t elem_begin, int64_t elem_end, int nmat, const double* const* D_host, double* const* values_dev,
+                         int nvec, const double* const* C_host, double* const* rhs_dev, bool rows = false) {
+  if (!ctx || !pattern || !basis || !quad || !geom) return b2_fail(ctx, B2_EINVAL, "null argument");
+  if (nmat < 0 || nmat > B2_MAX_FORMS || nvec < 0 || nvec > B2_MAX_FORMS) return b2_fail(ctx, B2_EINVAL, "0..4 matrix and vector forms per call");
+  if ((nmat && (!D_host || !values_dev)) || (nvec && (!C_host || !rhs_dev))) return b2_fail(ctx, B2_EINVAL, "null form argument");
+  if (pattern->basis != basis) return b2_fail(ctx, B2_EINVAL, "pattern was built for a different basis");
+  if (pattern->elemset) return b2_fail(ctx, B2_EINVAL, "pattern of an element set: use b2_assemble_elemset_*");
+  if (geom->gbasis) return b2_fail(ctx, B2_EUNSUPPORTED, "spline geometries are integrated through b2_assemble_elemset_*");
+  if (quad->ndims != basis->ndims || geom->ndims != basis->ndims) return b2_fail(ctx, B2_EINVAL, "dimension mismatch");
+  int64_t ntot = 1;
+  for (int d = 0; d < basis->ndims; d++) {
+    if (geom->nel[d] != basis->nel[d]) return b2_fail(ctx, B2_EINVAL, "geometry and basis live on different topologies");
+    ntot *= basis->nel[d];
+  }
+  int64_t plane_begin = 0, plane_end = basis->ndofs_d[0];
+  if (rows) {
+    plane_begin = elem_begin;
+    plane_end = elem_end < 0 ? basis->ndofs_d[0] : elem_end;
+    if (plane_begin < 0 || plane_begin > plane_end || plane_end > basis->ndofs_d[0]) return b2_fail(ctx, B2_EINVAL, "invalid dof-plane range");
+    if (plane_begin == plane_end || (nmat == 0 && nvec == 0)) return B2_OK;
+    // elements of dimension 0 whose dofs touch the planes (start is non-decreasing)
+    int64_t e_lo = basis->nel[0], e_hi = -1;
+    for (int64_t e = 0; e < basis->nel[0]; e++)
+      if (basis->start[0][e] < plane_end && basis->start[0][e] + basis->p[0] >= plane_begin) { e_lo = std::min(e_lo, e); e_hi = std::max(e_hi, e); }
+    const int64_t per_layer = ntot / basis->nel[0];
+    elem_begin = e_lo * per_layer;
+    elem_end = (e_hi + 1) * per_layer;
+    if (e_hi < e_lo) elem_begin = elem_end = 0;
+  } else {
+    if (elem_end < 0) elem_end = ntot;
+    if (elem_begin < 0 || elem_begin > elem_end || elem_end > ntot) return b2_fail(ctx, B2_EINVAL, "invalid element range");
+    if (elem_begin == elem_end || (nmat == 0 && nvec == 0)) return B2_OK;
+  }
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  const int nd = basis->ndims, nc = basis->ncomp;
+  TabDev tabs;
+  int rc = get_tabs(ctx, basis, quad, &tabs);
+  if (rc != B2_OK) return rc;
+
+  BasisView B = basis->view();
+  QuadView Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.nqt = 1;
+  for (int d = 0; d < nd; d++) {
+    Q.nq[d] = quad->nq[d];
+    Q.nqt *= quad->nq[d];
+    Q.x[d] = quad->d_x[d];
+    Q.w[d] = quad->d_w[d];
+    Q.tab[d] = tabs.tab[d];
+  }
+  GeomView G;
+  memset(&G, 0, sizeof(G));
+  G.nodes = geom->d_nodes;
+  G.nnodes = geom->nnodes;
+  {
+    long long s = 1;
+    for (int d = nd - 1; d >= 0; d--) { G.stride[d] = s; s *= geom->nel[d] + 1; }
+  }
+
+  const int64_t kernel_opt = ctx->opts.count("kernel") ? ctx->opts["kernel"] : 0;
+  for (int m = 0; m < nmat; m++)
+    if (!D_host[m] || !values_dev[m]) return b2_fail(ctx, B2_EINVAL, "null matrix form");
+  for (int v = 0; v < nvec; v++)
+    if (!C_host[v] || !rhs_dev[v]) return b2_fail(ctx, B2_EINVAL, "null vector form");
+  if (rows && kernel_opt != 1) {
+    // the specialised owner-computes kernel takes its coefficients as kernel parameters: no upload, no synchronisation
+    FormView F0;
+    memset(&F0, 0, sizeof(F0));
+    F0.nmat = nmat;
+    F0.nvec = nvec;
+    for (int m = 0; m < nmat; m++) F0.values[m] = values_dev[m];
+    for (int v = 0; v < nvec; v++) F0.rhs[v] = rhs_dev[v];
+    rc = launch_assemble_rows(ctx, basis, quad, B, Q, G, F0, D_host, C_host, plane_begin, plane_end);
+    if (rc != B2_EUNSUPPORTED) return rc;
+    if (kernel_opt >= 2) return b2_fail(ctx, B2_EUNSUPPORTED, "requested specialised kernel does not cover this configuration");
+  }
+
+  FormView F;
+  rc = b2_upload_forms(ctx, nd, nc, nmat, D_host, values_dev, nvec, C_host, rhs_dev, &F);
+  if (rc != B2_OK) return rc;
 
   if (rows) {
     // coverage path: zero the planes' slots, then scatter only the rows inside the planes

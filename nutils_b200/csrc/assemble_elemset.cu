@@ -1,0 +1,507 @@
+// Element-set integration kernel: the element loop of the reference for topologies that live on a structured grid
+// but are NOT the plain tensor case -- trimmed / subset topologies with per-element point sets (finite cell method),
+// pruned dof numberings, rational (NURBS) functions and spline geometries.
+//
+// What it replaces in the reference (src/nutils): the generated loop body (evaluable.py:6773-6787) with
+//   - the per-element point set coords/weights looked up through PointsSequence.get (pointsseq.py:324-332; ragged
+//     ConcatPoints of cut cells, points.py:257-337),
+//   - Polyval / PolyGrad of the element's coefficient rows at ARBITRARY local points (evaluable.py:4328-4374,
+//     4584-4634) -- here Horner on the 1-D factors,
+//   - PrunedBasis.f_dofs_coeffs (function.py:3130-3133): parent dofs renumbered,
+//   - rational functions c_i B_i / W and their gradients (quotient rule the reference derives symbolically,
+//     examples/platewithhole.py:66-83),
+//   - J, J^-1, |det J| of a multilinear OR (rational) spline geometry (function.py:1207-1231, 1266-1295),
+//   - the integrand einsums, the weighted point sum (sample.py:951-956), COO append + accumulate
+//     (evaluable.py:5383-5501, numeric.py:434-460) as fp64 atomicAdd into the CSR slot found by bisection in the
+//     row's sorted column list, and numpy.add.at for load vectors (evaluable.py:3582-3620).
+//
+// Mapping: one CTA per selected element (grid-stride), quadrature points in chunks through shared memory:
+//   P0 points of the chunk -> P1 1-D values/derivatives (Horner) -> P2 geometry per point -> P3 (N, grad N) per
+//   (point, function) -> P4 block entries in registers; scatter at the end of the element.
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int EPT = 8;  // block entries per thread and pass
+
+struct ESParams {
+  BasisView B;
+  QuadView Q;
+  GeomView G;
+  SplineGeomView SG;
+  ElemSetView E;
+  FormView F;
+  long long sel_begin, sel_end;
+  int qchunk;  // points per chunk
+  int pm1;     // max(p)+1 of the solution basis
+  int pgm1;    // max(p)+1 of the geometry basis (spline geometry)
+  int nbg;     // functions per element of the geometry basis
+  int ne;      // nb * ncomp
+};
+
+template <int DIM>
+__device__ __forceinline__ void inv_det(const double* J, double* Ji, double& det) {
+  if (DIM == 1) {
+    det = J[0];
+    Ji[0] = 1. / J[0];
+  } else if (DIM == 2) {
+    det = J[0] * J[3] - J[1] * J[2];
+    const double r = 1. / det;
+    Ji[0] = J[3] * r; Ji[1] = -J[1] * r;
+    Ji[2] = -J[2] * r; Ji[3] = J[0] * r;
+  } else {
+    const double c00 = J[4] * J[8] - J[5] * J[7];
+    const double c01 = J[5] * J[6] - J[3] * J[8];
+    const double c02 = J[3] * J[7] - J[4] * J[6];
+    det = J[0] * c00 + J[1] * c01 + J[2] * c02;
+    const double r = 1. / det;
+    Ji[0] = c00 * r; Ji[1] = (J[2] * J[7] - J[1] * J[8]) * r; Ji[2] = (J[1] * J[5] - J[2] * J[4]) * r;
+    Ji[3] = c01 * r; Ji[4] = (J[0] * J[8] - J[2] * J[6]) * r; Ji[5] = (J[2] * J[3] - J[0] * J[5]) * r;
+    Ji[6] = c02 * r; Ji[7] = (J[1] * J[6] - J[0] * J[7]) * r; Ji[8] = (J[0] * J[4] - J[1] * J[3]) * r;
+  }
+}
+
+// value and xi-gradient of local function `a` (C-order multi-index over per-dimension degrees p[]) at chunk point ql,
+// from the 1-D table tab[ql][d][pm1][2]
+template <int DIM>
+__device__ __forceinline__ void tensor_eval(const double* tab, int pm1, const int* p, int a, double& N, double* dxi) {
+  int ad[3] = {0, 0, 0};
+  for (int d = DIM - 1; d >= 0; d--) {
+    ad[d] = a % (p[d] + 1);
+    a /= p[d] + 1;
+  }
+  double val[DIM], der[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    val[d] = tab[(d * pm1 + ad[d]) * 2];
+    der[d] = tab[(d * pm1 + ad[d]) * 2 + 1];
+  }
+  N = 1.;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) N *= val[d];
+#pragma unroll
+  for (int k = 0; k < DIM; k++) {
+    double g = 1.;
+#pragma unroll
+    for (int d = 0; d < DIM; d++) g *= d == k ? der[d] : val[d];
+    dxi[k] = g;
+  }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(512) k_assemble_elemset(const ESParams P) {
+  constexpr int NA = DIM + 1;
+  constexpr int NV = 1 << DIM;
+  constexpr int JS = DIM * DIM + 1;
+  const BasisView& B = P.B;
+  const ElemSetView& E = P.E;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int nb = B.nb, nc = B.ncomp, ne = P.ne, ne2 = ne * ne;
+  const int qc = P.qchunk, pm1 = P.pm1, pgm1 = P.pgm1, nbg = P.nbg;
+  const bool spline = P.SG.enabled != 0;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sC = reinterpret_cast<double*>(smem_raw);     // [DIM][pm1][pm1]   coefficient rows of the element
+  double* sCg = sC + DIM * pm1 * pm1;                   // [DIM][pgm1][pgm1] same for the geometry basis
+  double* sX = sCg + DIM * pgm1 * pgm1;                 // nodal: [DIM][NV]; spline: [DIM+1][nbg] (w X, w)
+  double* sS = sX + (spline ? (DIM + 1) * nbg : DIM * NV);  // [nb] scale c_a
+  double* sPt = sS + nb;                                // [qc][NA]  xi, weight
+  double* sA = sPt + qc * NA;                           // [qc][DIM][pm1][2]
+  double* sAg = sA + qc * DIM * pm1 * 2;                // [qc][DIM][pgm1][2]
+  double* sJ = sAg + qc * DIM * pgm1 * 2;               // [qc][JS]  J^-1 (k,i) then w|det|
+  double* sW = sJ + qc * JS;                            // [qc][NA]  W, dW/dxi (rational functions)
+  double* sB = sW + qc * NA;                            // [qc][nb][NA]
+  double* sV = sB + qc * nb * NA;                       // [nvec][ne]
+  long long* sRow = reinterpret_cast<long long*>(sV + B2_MAX_FORMS * ne);  // [nb] first slot of the basis row
+  int* sLen = reinterpret_cast<int*>(sRow + nb);        // [nb] columns of the basis row
+  int* sDof = sLen + nb;                                // [nb] new basis index, -1: dropped
+
+  for (long long sel = P.sel_begin + blockIdx.x; sel < P.sel_end; sel += gridDim.x) {
+    const long long elem = E.elem_ids ? E.elem_ids[sel] : sel;
+    int ie[3] = {0, 0, 0};
+    {
+      long long r = elem;
+      for (int d = DIM - 1; d >= 0; d--) {
+        ie[d] = (int)(r % B.nel[d]);
+        r /= B.nel[d];
+      }
+    }
+    const long long qbeg = E.qoff ? E.qoff[sel] : 0;
+    const int nqt = E.qoff ? (int)(E.qoff[sel + 1] - qbeg) : P.Q.nqt;
+    __syncthreads();  // previous element fully scattered before shared memory is reused
+    for (int t = tid; t < DIM * pm1 * pm1; t += T) {
+      const int j = t % pm1, a = (t / pm1) % pm1, d = t / (pm1 * pm1);
+      const int p = B.p[d];
+      sC[t] = (a <= p && j <= p) ? E.coeffs[d][((long long)B.setidx[d][ie[d]] * (p + 1) + a) * (p + 1) + j] : 0.;
+    }
+    if (spline) {
+      const BasisView& GB = P.SG.GB;
+      for (int t = tid; t < DIM * pgm1 * pgm1; t += T) {
+        const int j = t % pgm1, a = (t / pgm1) % pgm1, d = t / (pgm1 * pgm1);
+        const int p = GB.p[d];
+        sCg[t] = (a <= p && j <= p) ? P.SG.coeffs[d][((long long)GB.setidx[d][ie[d]] * (p + 1) + a) * (p + 1) + j] : 0.;
+      }
+      for (int a = tid; a < nbg; a += T) {
+        long long I = 0;
+        int r = a, ad[3] = {0, 0, 0};
+        for (int d = DIM - 1; d >= 0; d--) {
+          ad[d] = r % (GB.p[d] + 1);
+          r /= GB.p[d] + 1;
+        }
+        for (int d = 0; d < DIM; d++) I = I * GB.ndofs[d] + GB.start[d][ie[d]] + ad[d];
+        const double w = P.SG.wts ? P.SG.wts[I] : 1.;
+        for (int i = 0; i < DIM; i++) sX[i * nbg + a] = w * P.SG.ctrl[i * P.SG.nbasis + I];
+        sX[DIM * nbg + a] = w;
+      }
+    } else {
+      for (int t = tid; t < DIM * NV; t += T) {
+        const int v = t % NV, i = t / NV;
+        long long off = 0;
+        for (int d = 0; d < DIM; d++) off += (long long)(ie[d] + ((v >> (DIM - 1 - d)) & 1)) * P.G.stride[d];
+        sX[t] = P.G.nodes[i * P.G.nnodes + off];
+      }
+    }
+    for (int a = tid; a < nb; a += T) {
+      long long I = 0;
+      int r = a, ad[3] = {0, 0, 0};
+      for (int d = DIM - 1; d >= 0; d--) {
+        ad[d] = r % (B.p[d] + 1);
+        r /= B.p[d] + 1;
+      }
+      for (int d = 0; d < DIM; d++) I = I * B.ndofs[d] + B.start[d][ie[d]] + ad[d];
+      int In = E.renumber ? E.renumber[I] : (int)I;
+      if (In < 0 || In >= E.nbasis_new) In = -1;
+      sDof[a] = In;
+      sS[a] = E.scale ? E.scale[I] : 1.;
+      sRow[a] = In >= 0 ? E.rowptr_b[In] : 0;
+      sLen[a] = In >= 0 ? (int)(E.rowptr_b[In + 1] - E.rowptr_b[In]) : 0;
+    }
+    for (int t = tid; t < P.F.nvec * ne; t += T) sV[t] = 0.;
+    __syncthreads();
+
+    for (int pass0 = 0; pass0 < ne2 || pass0 == 0; pass0 += T * EPT) {
+      double acc[B2_MAX_FORMS][EPT];
+#pragma unroll
+      for (int m = 0; m < B2_MAX_FORMS; m++)
+#pragma unroll
+        for (int e = 0; e < EPT; e++) acc[m][e] = 0.;
+
+      for (int q0 = 0; q0 < nqt; q0 += qc) {
+        const int nqc = min(qc, nqt - q0);
+        // P0: local coordinates and weights of the chunk
+        for (int ql = tid; ql < nqc; ql += T) {
+          double* pt = sPt + ql * NA;
+          if (E.qoff) {
+            const long long q = qbeg + q0 + ql;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) pt[d] = E.qcoords[q * DIM + d];
+            pt[DIM] = E.qweights[q];
+          } else {
+            int r = q0 + ql;
+            double w = 1.;
+            for (int d = DIM - 1; d >= 0; d--) {
+              const int k = r % P.Q.nq[d];
+              r /= P.Q.nq[d];
+              pt[d] = P.Q.x[d][k];
+              w *= P.Q.w[d][k];
+            }
+            pt[DIM] = w;
+          }
+        }
+        __syncthreads();
+        // P1: 1-D values and derivatives (Horner with derivative; rows are highest power first)
+        for (int t = tid; t < nqc * DIM * pm1; t += T) {
+          const int a = t % pm1, d = (t / pm1) % DIM, ql = t / (pm1 * DIM);
+          const int p = B.p[d];
+          double v = 0., g = 0.;
+          if (a <= p) {
+            const double x = sPt[ql * NA + d];
+            const double* c = sC + (d * pm1 + a) * pm1;
+            v = c[0];
+            for (int j = 1; j <= p; j++) { g = g * x + v; v = v * x + c[j]; }
+          }
+          sA[t * 2] = v;
+          sA[t * 2 + 1] = g;
+        }
+        if (spline) {
+          for (int t = tid; t < nqc * DIM * pgm1; t += T) {
+            const int a = t % pgm1, d = (t / pgm1) % DIM, ql = t / (pgm1 * DIM);
+            const int p = P.SG.GB.p[d];
+            double v = 0., g = 0.;
+            if (a <= p) {
+              const double x = sPt[ql * NA + d];
+              const double* c = sCg + (d * pgm1 + a) * pgm1;
+              v = c[0];
+              for (int j = 1; j <= p; j++) { g = g * x + v; v = v * x + c[j]; }
+            }
+            sAg[t * 2] = v;
+            sAg[t * 2 + 1] = g;
+          }
+        }
+        __syncthreads();
+        // P2: geometry at the points of the chunk (and the weight function of rational bases)
+        for (int ql = tid; ql < nqc; ql += T) {
+          const double* pt = sPt + ql * NA;
+          double J[DIM * DIM];
+          double Wg = 1., dWg[DIM];
+#pragma unroll
+          for (int k = 0; k < DIM; k++) dWg[k] = 0.;
+          if (spline) {
+            double Xh[DIM], dXh[DIM * DIM];
+#pragma unroll
+            for (int i = 0; i < DIM; i++) Xh[i] = 0.;
+#pragma unroll
+            for (int i = 0; i < DIM * DIM; i++) dXh[i] = 0.;
+            double W = 0.;
+            for (int a = 0; a < nbg; a++) {
+              double N, dxi[DIM];
+              tensor_eval<DIM>(sAg + ql * DIM * pgm1 * 2, pgm1, P.SG.GB.p, a, N, dxi);
+              const double w = sX[DIM * nbg + a];
+              W = fma(N, w, W);
+#pragma unroll
+              for (int k = 0; k < DIM; k++) dWg[k] = fma(dxi[k], w, dWg[k]);
+#pragma unroll
+              for (int i = 0; i < DIM; i++) {
+                const double xw = sX[i * nbg + a];
+                Xh[i] = fma(N, xw, Xh[i]);
+#pragma unroll
+                for (int k = 0; k < DIM; k++) dXh[i * DIM + k] = fma(dxi[k], xw, dXh[i * DIM + k]);
+              }
+            }
+            // x = Xh / W,  dx/dxi = (dXh - x dW) / W   (W = 1, dW = 0 for polynomial splines)
+            const double rW = 1. / W;
+#pragma unroll
+            for (int i = 0; i < DIM; i++) {
+              const double x = Xh[i] * rW;
+#pragma unroll
+              for (int k = 0; k < DIM; k++) J[i * DIM + k] = (dXh[i * DIM + k] - x * dWg[k]) * rW;
+            }
+            Wg = W;
+          } else {
+#pragma unroll
+            for (int i = 0; i < DIM * DIM; i++) J[i] = 0.;
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+#pragma unroll
+              for (int k = 0; k < DIM; k++) {
+                double f = 1.;
+#pragma unroll
+                for (int d = 0; d < DIM; d++) {
+                  const bool bit = (v >> (DIM - 1 - d)) & 1;
+                  f *= d == k ? (bit ? 1. : -1.) : (bit ? pt[d] : 1. - pt[d]);
+                }
+#pragma unroll
+                for (int i = 0; i < DIM; i++) J[i * DIM + k] += sX[i * NV + v] * f;
+              }
+            }
+          }
+          double Ji[DIM * DIM], det;
+          inv_det<DIM>(J, Ji, det);
+#pragma unroll
+          for (int i = 0; i < DIM * DIM; i++) sJ[ql * JS + i] = Ji[i];
+          sJ[ql * JS + DIM * DIM] = pt[DIM] * fabs(det);
+          if (E.rational == 1) {
+            double W = 0., dW[DIM];
+#pragma unroll
+            for (int k = 0; k < DIM; k++) dW[k] = 0.;
+            for (int a = 0; a < nb; a++) {
+              double N, dxi[DIM];
+              tensor_eval<DIM>(sA + ql * DIM * pm1 * 2, pm1, B.p, a, N, dxi);
+              W = fma(N, sS[a], W);
+#pragma unroll
+              for (int k = 0; k < DIM; k++) dW[k] = fma(dxi[k], sS[a], dW[k]);
+            }
+            sW[ql * NA] = W;
+#pragma unroll
+            for (int k = 0; k < DIM; k++) sW[ql * NA + 1 + k] = dW[k];
+          } else if (E.rational == 2) {
+            sW[ql * NA] = Wg;
+#pragma unroll
+            for (int k = 0; k < DIM; k++) sW[ql * NA + 1 + k] = dWg[k];
+          }
+        }
+        __syncthreads();
+        // P3: values and physical gradients of the (scaled, rational) functions
+        for (int t = tid; t < nqc * nb; t += T) {
+          const int a = t % nb, ql = t / nb;
+          double N, dxi[DIM];
+          tensor_eval<DIM>(sA + ql * DIM * pm1 * 2, pm1, B.p, a, N, dxi);
+          const double c = sS[a];
+          N *= c;
+#pragma unroll
+          for (int k = 0; k < DIM; k++) dxi[k] *= c;
+          if (E.rational) {
+            // R = N / W,  dR = (dN - R dW) / W
+            const double rW = 1. / sW[ql * NA];
+            N *= rW;
+#pragma unroll
+            for (int k = 0; k < DIM; k++) dxi[k] = (dxi[k] - N * sW[ql * NA + 1 + k]) * rW;
+          }
+          double* b = sB + (ql * nb + a) * NA;
+          b[0] = N;
+#pragma unroll
+          for (int i = 0; i < DIM; i++) {
+            double s = 0.;
+#pragma unroll
+            for (int k = 0; k < DIM; k++) s += dxi[k] * sJ[ql * JS + k * DIM + i];
+            b[1 + i] = s;
+          }
+        }
+        __syncthreads();
+        // P4: block entries
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+          const int entry = pass0 + e * T + tid;
+          if (entry < ne2) {
+            const int r = entry / ne, c = entry % ne;
+            const int a = r / nc, ci = r % nc, b = c / nc, cj = c % nc;
+            for (int ql = 0; ql < nqc; ql++) {
+              const double* Ba = sB + (ql * nb + a) * NA;
+              const double* Bb = sB + (ql * nb + b) * NA;
+              const double w = sJ[ql * JS + DIM * DIM];
+              double va[NA], vb[NA];
+#pragma unroll
+              for (int x = 0; x < NA; x++) {
+                va[x] = Ba[x] * w;
+                vb[x] = Bb[x];
+              }
+#pragma unroll
+              for (int m = 0; m < B2_MAX_FORMS; m++) {
+                if (m < P.F.nmat) {
+                  const int t0 = P.F.termptr[(m * nc + ci) * nc + cj], t1 = P.F.termptr[(m * nc + ci) * nc + cj + 1];
+                  double s = 0.;
+                  for (int t = t0; t < t1; t++) {
+                    const int xy = P.F.termxy[t];
+                    double ax = va[0], by = vb[0];
+#pragma unroll
+                    for (int x = 1; x < NA; x++) {
+                      if ((xy & 255) == x) ax = va[x];
+                      if ((xy >> 8) == x) by = vb[x];
+                    }
+                    s += P.F.termval[t] * ax * by;
+                  }
+                  acc[m][e] += s;
+                }
+              }
+            }
+          }
+        }
+        // linear forms: thread r owns sV[.][r]
+        if (pass0 == 0) {
+          for (int r = tid; r < ne; r += T) {
+            const int a = r / nc, ci = r % nc;
+            for (int v = 0; v < P.F.nvec; v++) {
+              double s = 0.;
+              for (int ql = 0; ql < nqc; ql++) {
+                const double* Ba = sB + (ql * nb + a) * NA;
+                double t = 0.;
+#pragma unroll
+                for (int x = 0; x < NA; x++) t += P.F.vcoef[(v * nc + ci) * NA + x] * Ba[x];
+                s += t * sJ[ql * JS + DIM * DIM];
+              }
+              sV[v * ne + r] += s;
+            }
+          }
+        }
+        __syncthreads();
+      }
+      // scatter: bisection of the column in the row's sorted list
+#pragma unroll
+      for (int e = 0; e < EPT; e++) {
+        const int entry = pass0 + e * T + tid;
+        if (entry < ne2 && P.F.nmat) {
+          const int r = entry / ne, c = entry % ne;
+          const int a = r / nc, ci = r % nc, b = c / nc, cj = c % nc;
+          const int In = sDof[a], Jn = sDof[b];
+          if (In >= 0 && Jn >= 0) {
+            const int len = sLen[a];
+            const int* cols = E.colidx_b + sRow[a];
+            int lo = 0, hi = len;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (cols[mid] < Jn) lo = mid + 1;
+              else hi = mid;
+            }
+            if (lo < len && cols[lo] == Jn) {
+              const long long slot = (sRow[a] * nc + (long long)ci * len) * nc + (long long)lo * nc + cj;
+#pragma unroll
+              for (int m = 0; m < B2_MAX_FORMS; m++)
+                if (m < P.F.nmat) atomicAdd(P.F.values[m] + slot, acc[m][e]);
+            }
+          }
+        }
+      }
+    }
+    for (int t = tid; t < P.F.nvec * ne; t += T) {
+      const int v = t / ne, r = t % ne;
+      const int a = r / nc, ci = r % nc;
+      if (sDof[a] >= 0) atomicAdd(P.F.rhs[v] + (long long)sDof[a] * nc + ci, sV[t]);
+    }
+  }
+}
+
+template <int DIM>
+int launch_dim(b2_ctx* ctx, ESParams& P, int max_nq) {
+  const int nb = P.B.nb, ne = P.ne, ne2 = ne * ne;
+  constexpr int NA = DIM + 1, NV = 1 << DIM, JS = DIM * DIM + 1;
+  int threads = (ne2 + EPT - 1) / EPT;
+  threads = std::min(512, std::max(64, (threads + 31) / 32 * 32));
+  const bool spline = P.SG.enabled != 0;
+  const size_t fixed = sizeof(double) * (DIM * P.pm1 * P.pm1 + DIM * P.pgm1 * P.pgm1 + (spline ? (DIM + 1) * P.nbg : DIM * NV) + nb + B2_MAX_FORMS * ne) +
+                       sizeof(long long) * nb + sizeof(int) * 2 * nb;
+  const size_t per_q = sizeof(double) * (NA + DIM * P.pm1 * 2 + DIM * P.pgm1 * 2 + JS + NA + nb * NA);
+  const size_t budget = 96 * 1024;
+  int qc = (int)std::max<size_t>(1, (budget > fixed ? (budget - fixed) / per_q : 1));
+  qc = std::min(qc, std::max(max_nq, 1));
+  P.qchunk = qc;
+  const size_t smem = fixed + per_q * qc + 16;
+  if (smem > 200 * 1024) return b2_fail(ctx, B2_EUNSUPPORTED, "element too large for the element-set kernel");
+  B2_CUDA(ctx, cudaFuncSetAttribute(k_assemble_elemset<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  B2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_elemset<DIM>, threads, smem));
+  per_sm = std::max(per_sm, 1);
+  const long long nel = P.sel_end - P.sel_begin;
+  const int blocks = (int)std::min<long long>(nel, (long long)ctx->sm_count * per_sm * 4);
+  {
+    KernelTimer timer(ctx);
+    k_assemble_elemset<DIM><<<blocks, threads, smem, ctx->stream>>>(P);
+  }
+  ctx->launches++;
+  B2_CUDA(ctx, cudaGetLastError());
+  return B2_OK;
+}
+
+}  // namespace
+
+int launch_assemble_elemset(b2_ctx* ctx, const BasisView& B, const QuadView& Q, const GeomView& G, const SplineGeomView& SG, const ElemSetView& E, const FormView& F,
+                            long long sel_begin, long long sel_end, int max_nq) {
+  ESParams P;
+  P.B = B;
+  P.Q = Q;
+  P.G = G;
+  P.SG = SG;
+  P.E = E;
+  P.F = F;
+  P.sel_begin = sel_begin;
+  P.sel_end = sel_end;
+  P.pm1 = 1;
+  P.pgm1 = 1;
+  P.nbg = 1;
+  for (int d = 0; d < B.ndims; d++) {
+    P.pm1 = std::max(P.pm1, B.p[d] + 1);
+    if (SG.enabled) {
+      P.pgm1 = std::max(P.pgm1, SG.GB.p[d] + 1);
+      P.nbg *= SG.GB.p[d] + 1;
+    }
+  }
+  P.ne = B.nb * B.ncomp;
+  P.qchunk = 1;
+  switch (B.ndims) {
+    case 1: return launch_dim<1>(ctx, P, max_nq);
+    case 2: return launch_dim<2>(ctx, P, max_nq);
+    default: return launch_dim<3>(ctx, P, max_nq);
+  }
+}

@@ -6,11 +6,14 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 OUT="$HERE/../libb200fem.so"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -cudart static"
 mkdir -p "$HERE/_obj"
-for f in api pattern assemble_generic assemble_fast assemble_rows; do
+SRCS="api api_elemset pattern pattern_elemset assemble_generic assemble_elemset assemble_fast assemble_rows"
+OBJS=""
+for f in $SRCS; do
   src="$HERE/$f.cu"; obj="$HERE/_obj/$f.o"
   if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/common.cuh" -nt "$obj" ] || [ "$HERE/../../include/b200fem.h" -nt "$obj" ]; then
     "$NVCC" $FLAGS ${B2_PTXAS_V:+-Xptxas -v} ${B2_EXPERIMENT:+-DB2_EXPERIMENT} -c "$src" -o "$obj"
   fi
+  OBJS="$OBJS $obj"
 done
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o "$OUT" "$HERE"/_obj/api.o "$HERE"/_obj/pattern.o "$HERE"/_obj/assemble_generic.o "$HERE"/_obj/assemble_fast.o "$HERE"/_obj/assemble_rows.o
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o "$OUT" $OBJS
 echo "built $OUT"

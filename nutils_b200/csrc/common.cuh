@@ -47,6 +47,34 @@ struct GeomView {
   long long stride[B2_MAXD]; // node stride per dimension
 };
 
+// Spline (optionally rational) geometry: control points in the scalar basis GB (same element grid).
+struct SplineGeomView {
+  int enabled;               // 0: nodal multilinear geometry (GeomView)
+  int rational;              // weights present: x = sum B w X / sum B w
+  BasisView GB;
+  const double* coeffs[B2_MAXD];  // [nsets][p+1][p+1] local polynomials of GB per dimension (highest power first)
+  const double* ctrl;        // [ndims][nbasis_g]
+  const double* wts;         // [nbasis_g] or null
+  long long nbasis;
+};
+
+// Element set: subset of elements, ragged points, pruned numbering, rational scaling (include/b200fem.h).
+struct ElemSetView {
+  long long nsel;
+  const long long* elem_ids;   // [nsel] or null (all elements)
+  const long long* qoff;       // [nsel+1] or null (tensor rule)
+  const double* qcoords;       // [npoints][ndims]
+  const double* qweights;      // [npoints]
+  const int* renumber;         // [nbasis_parent] -> new index, < 0: dropped; null = identity
+  const double* scale;         // [nbasis_parent] or null
+  int rational;                // 0 none, 1 own weight function, 2 the geometry's weight function
+  long long nbasis_new;
+  const double* coeffs[B2_MAXD];  // local polynomials of the solution basis per dimension
+  // general CSR pattern at basis level (rows = new basis indices)
+  const long long* rowptr_b;   // [nbasis_new+1]
+  const int* colidx_b;         // [nnz_b] new basis indices, sorted per row
+};
+
 // Sparse representation of the coefficient tensors D_m: per (m, c, e) a list of (x, y, value).
 struct FormView {
   int nmat, nvec;
@@ -136,12 +164,43 @@ struct b2_geom {
   int64_t nel[B2_MAXD];
   int64_t nnodes;
   double* d_nodes;
+  // spline geometry (b2_geom_create_spline): control points in gbasis
+  const b2_basis* gbasis = nullptr;
+  double* d_ctrl = nullptr;
+  double* d_wts = nullptr;
+  double* d_gcoeffs[B2_MAXD] = {nullptr, nullptr, nullptr};
+};
+
+struct b2_elemset {
+  b2_ctx* ctx;
+  const b2_basis* basis;
+  int64_t nsel, npoints, nbasis_new;
+  int rational;
+  int max_nq;                // largest number of points of one element (ragged), 0 for tensor rules
+  std::vector<int64_t> elem_ids;   // host copy (empty = all)
+  std::vector<int> renumber;       // host copy (empty = identity)
+  long long* d_elem_ids = nullptr;
+  long long* d_qoff = nullptr;
+  double* d_qcoords = nullptr;
+  double* d_qweights = nullptr;
+  int* d_renumber = nullptr;
+  double* d_scale = nullptr;
+  double* d_coeffs[B2_MAXD] = {nullptr, nullptr, nullptr};
+  unsigned char* d_selmask = nullptr;  // [ntotal] 1 = element selected (pattern construction); null = all
+  long long* d_dofmap = nullptr;       // [nbasis_new] parent index of each kept basis function; null = identity
+  int* d_efirst[B2_MAXD] = {nullptr, nullptr, nullptr};  // [ndofs_d] first / last supporting element of the 1-D functions
+  int* d_elast[B2_MAXD] = {nullptr, nullptr, nullptr};
 };
 
 struct b2_pattern {
   b2_ctx* ctx;
   const b2_basis* basis;
   int64_t nnz, nrows;
+  // general pattern of an element set (b2_pattern_create_elemset); analytic otherwise
+  const b2_elemset* elemset = nullptr;
+  long long* d_rowptr_b = nullptr;  // [nbasis_new+1]
+  int* d_colidx_b = nullptr;        // [nnz_b]
+  std::vector<long long> rowptr_b;  // host copy
 };
 
 // ---- error helpers -------------------------------------------------------------------------------
@@ -164,6 +223,15 @@ int launch_assemble_generic(b2_ctx* ctx, const BasisView& B, const QuadView& Q, 
 // returns B2_EUNSUPPORTED when no specialised kernel covers the request
 int launch_assemble_fast(b2_ctx* ctx, const BasisView& B, const QuadView& Q, const GeomView& G, const FormView& F,
                          const double* const* D_host, const double* const* C_host, long long elem_begin, long long elem_end);
+
+// element-set path (assemble_elemset.cu, pattern_elemset.cu)
+int launch_assemble_elemset(b2_ctx* ctx, const BasisView& B, const QuadView& Q, const GeomView& G, const SplineGeomView& SG, const ElemSetView& E, const FormView& F,
+                            long long sel_begin, long long sel_end, int max_nq);
+// counts[new basis row] = number of coupled columns (pass 0) / fills colidx_b (pass 1)
+int launch_pattern_elemset_impl(b2_ctx* ctx, const BasisView& B, const int* const* efirst, const int* const* elast, const long long* dofmap, const int* renumber,
+                                const unsigned char* selmask, long long nbasis_new, int pass, long long* counts_or_rowptr, int* colidx_b);
+int launch_exclusive_scan(b2_ctx* ctx, long long* data, long long n);  // in place, data[n] receives the total (n+1 entries)
+int launch_pattern_export_general(b2_ctx* ctx, const long long* rowptr_b, const int* colidx_b, long long nbasis, int ncomp, long long* rowptr, long long* colidx);
 
 // owner-computes kernel: WRITES every stored value of the dof planes [plane_begin, plane_end) of dimension 0
 int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad, const BasisView& B, const QuadView& Q, const GeomView& G, const FormView& F,

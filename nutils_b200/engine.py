@@ -254,6 +254,138 @@ class Plan:
                                                             len(Ds), pD, pv, len(Cs), pC, pr))
 
 
+class ElemSetPlan:
+    '''Device-resident description of an assembly problem on an ELEMENT SET of a structured grid (b2_elemset):
+    a subset of the elements (trimmed topologies), per-element point sets of different length (cut cells),
+    the pruned dof numbering, rational (NURBS) scaling, and a nodal or (rational) spline geometry.
+
+    bases     : sequence of bspline.Basis1D of the PARENT tensor space
+    nodes     : float64[ndims, n0+1, ...] nodal geometry, or None when `geom_spline` is given
+    elem_ids  : int64[nsel] selected elements (C-order indices, increasing); None = all
+    qoff, qcoords, qweights : ragged points in element-local coordinates; None = tensor `rules`
+    renumber  : int64[nbasis_parent] -> new index (negative or >= nbasis_new: dropped); None = identity
+    scale     : float64[nbasis_parent] numerator weights c_i; rational: 0 none, 1 divide by sum_j c_j B_j,
+                2 divide by the weight function of the rational spline geometry
+    geom_spline : (bases_g, ctrl[ndims, nbasis_g], weights[nbasis_g] or None)
+    '''
+
+    def __init__(self, ctx, bases, nodes=None, ncomp=1, rules=None, elem_ids=None, qoff=None, qcoords=None, qweights=None,
+                 renumber=None, nbasis_new=None, scale=None, rational=0, geom_spline=None):
+        self.ctx = ctx
+        lib = ctx.lib
+        self.ndims = nd = len(bases)
+        self.ncomp = int(ncomp)
+        self.nelems = tuple(b.nelems for b in bases)
+        self._fin = []
+        self._keep = []
+        self.basis = self._make_basis(bases, self.ncomp)
+        nelems = numpy.array(self.nelems, dtype=numpy.int64)
+        # quadrature
+        self.quad = None
+        if qoff is None:
+            if rules is None:
+                raise ValueError('either ragged points (qoff, qcoords, qweights) or tensor rules are needed')
+            rules = [(as_f64(x), as_f64(w)) for x, w in rules]
+            nq = numpy.array([len(x) for x, w in rules], dtype=numpy.int32)
+            h = c_vp()
+            ctx.check(lib.b2_quad_create_tensor(ctx.handle, nd, nq.ctypes.data_as(_lib.p_i32), _lib.ptr_array([x for x, w in rules], _lib.p_f64),
+                                                _lib.ptr_array([w for x, w in rules], _lib.p_f64), ctypes.byref(h)))
+            self.quad = h
+            self._fin.append(weakref.finalize(self, lib.b2_quad_destroy, h))
+        # geometry
+        h = c_vp()
+        if geom_spline is not None:
+            gbases, ctrl, gw = geom_spline
+            self.gbasis = self._make_basis(gbases, 1)
+            ctrl = as_f64(ctrl)
+            nbg = int(numpy.prod([b.ndofs for b in gbases]))
+            if ctrl.shape != (nd, nbg):
+                raise ValueError('control points must have shape (ndims, nbasis_g)')
+            gw = None if gw is None else as_f64(gw)
+            ctx.check(lib.b2_geom_create_spline(ctx.handle, self.gbasis, ctrl.ctypes.data_as(c_vp), None if gw is None else gw.ctypes.data_as(c_vp), ctypes.byref(h)))
+        else:
+            nodes = as_f64(nodes)
+            if nodes.shape != (nd,) + tuple(n + 1 for n in self.nelems):
+                raise ValueError('nodes must have shape (ndims, nelems_0+1, ...), got {}'.format(nodes.shape))
+            ctx.check(lib.b2_geom_create_nodal(ctx.handle, nd, nelems.ctypes.data_as(_lib.p_i64), nodes.ctypes.data_as(c_vp), ctypes.byref(h)))
+        self.geom = h
+        self._fin.append(weakref.finalize(self, lib.b2_geom_destroy, h))
+        # element set
+        ntot = int(numpy.prod(self.nelems))
+        i64 = lambda a: None if a is None else numpy.ascontiguousarray(a, dtype=numpy.int64)
+        f64 = lambda a: None if a is None else as_f64(a)
+        elem_ids, qoff, renumber = i64(elem_ids), i64(qoff), i64(renumber)
+        qcoords, qweights, scale = f64(qcoords), f64(qweights), f64(scale)
+        nsel = ntot if elem_ids is None else len(elem_ids)
+        nbasis = int(numpy.prod([b.ndofs for b in bases]))
+        if qoff is not None and (len(qoff) != nsel + 1 or qcoords.shape != (int(qoff[-1]), nd) or qweights.shape != (int(qoff[-1]),)):
+            raise ValueError('ragged quadrature arrays do not match the element selection')
+        if renumber is not None and len(renumber) != nbasis:
+            raise ValueError('renumber must have one entry per parent basis function')
+        if scale is not None and len(scale) != nbasis:
+            raise ValueError('scale must have one entry per parent basis function')
+        if renumber is not None and nbasis_new is None:
+            nbasis_new = int(renumber[(renumber >= 0) & (renumber < nbasis)].max()) + 1 if len(renumber) else 0
+        ptr = lambda a: None if a is None else a.ctypes.data_as(c_vp)
+        h = c_vp()
+        ctx.check(lib.b2_elemset_create(ctx.handle, self.basis, nsel, ptr(elem_ids), ptr(qoff), ptr(qcoords), ptr(qweights), ptr(renumber),
+                                        int(nbasis_new or 0), ptr(scale), int(rational), ctypes.byref(h)))
+        self.elemset = h
+        self._fin.append(weakref.finalize(self, lib.b2_elemset_destroy, h))
+        self.nsel = nsel
+        self.npoints = int(lib.b2_elemset_npoints(h))
+        h = c_vp()
+        ctx.check(lib.b2_pattern_create_elemset(ctx.handle, self.elemset, ctypes.byref(h)))
+        self.pattern = h
+        self._fin.append(weakref.finalize(self, lib.b2_pattern_destroy, h))
+        self.nnz = int(lib.b2_pattern_nnz(h))
+        self.ndofs = int(lib.b2_pattern_nrows(h))
+        self._csr = None
+
+    def _make_basis(self, bases, ncomp):
+        ctx, lib, nd = self.ctx, self.ctx.lib, len(bases)
+        if any(b.periodic for b in bases):
+            raise _lib.B200Error('unsupported configuration: periodic bases')
+        nelems = numpy.array([b.nelems for b in bases], dtype=numpy.int64)
+        degree = numpy.array([b.degree for b in bases], dtype=numpy.int32)
+        nsets = numpy.array([len(b.coeffs) for b in bases], dtype=numpy.int32)
+        ndofs = numpy.array([b.ndofs for b in bases], dtype=numpy.int64)
+        coeffs = [as_f64(b.coeffs) for b in bases]
+        setidx = [numpy.ascontiguousarray(b.setidx, dtype=numpy.int32) for b in bases]
+        start = [numpy.ascontiguousarray(b.start, dtype=numpy.int64) for b in bases]
+        h = c_vp()
+        ctx.check(lib.b2_basis_create(ctx.handle, nd, nelems.ctypes.data_as(_lib.p_i64), degree.ctypes.data_as(_lib.p_i32), nsets.ctypes.data_as(_lib.p_i32),
+                                      _lib.ptr_array(coeffs, _lib.p_f64), _lib.ptr_array(setidx, _lib.p_i32), _lib.ptr_array(start, _lib.p_i64),
+                                      ndofs.ctypes.data_as(_lib.p_i64), int(ncomp), ctypes.byref(h)))
+        self._fin.append(weakref.finalize(self, lib.b2_basis_destroy, h))
+        return h
+
+    csr_pattern = Plan.csr_pattern
+    csr_pattern_device = Plan.csr_pattern_device
+    row_offset = Plan.row_offset
+    _form_args = Plan._form_args
+
+    def assemble_host(self, Ds=(), Cs=()):
+        'zero-fill, integrate the selected elements, copy to host: returns ([values...], [rhs...]) (b2_assemble_elemset_host)'
+        Ds, Cs, pD, pC = self._form_args(Ds, Cs)
+        vals = [numpy.empty(self.nnz) for _ in Ds]
+        rhs = [numpy.empty(self.ndofs) for _ in Cs]
+        pv = (c_vp * max(len(vals), 1))(*[v.ctypes.data_as(c_vp) for v in vals])
+        pr = (c_vp * max(len(rhs), 1))(*[r.ctypes.data_as(c_vp) for r in rhs])
+        self.ctx.check(self.ctx.lib.b2_assemble_elemset_host(self.ctx.handle, self.pattern, self.elemset, self.quad, self.geom, len(Ds), pD, pv, len(Cs), pC, pr))
+        return vals, rhs
+
+    def assemble_device(self, Ds=(), Cs=(), values=(), rhs=(), sel_range=None):
+        'accumulate the selected elements [sel_range) into device arrays (b2_assemble_elemset_device); asynchronous'
+        Ds, Cs, pD, pC = self._form_args(Ds, Cs)
+        assert len(values) == len(Ds) and len(rhs) == len(Cs)
+        s0, s1 = sel_range if sel_range is not None else (0, -1)
+        pv = (c_vp * max(len(values), 1))(*[_devptr(v) for v in values])
+        pr = (c_vp * max(len(rhs), 1))(*[_devptr(r) for r in rhs])
+        self.ctx.check(self.ctx.lib.b2_assemble_elemset_device(self.ctx.handle, self.pattern, self.elemset, self.quad, self.geom, c_i64(s0), c_i64(s1),
+                                                               len(Ds), pD, pv, len(Cs), pC, pr))
+
+
 # ---- coefficient tensors of the north-star forms -------------------------------------------------------
 
 def form_mass(ndims, ncomp=1):

@@ -28,6 +28,12 @@ a multilinear nodal geometry, and the sparse post-processing exactly:
                                          evaluable.py:5655-5676 -> numeric.py:687-711
   RHS scatter-add                        evaluable.py:3582-3620 (numpy.add.at)
 
+Element sets (trimmed / subset topologies, SubsetTopology topology.py:1598-1660): the loop runs over the kept
+elements only, with per-element point sets (pointsseq.py:324-332), the pruned numbering of
+function.PrunedBasis (function.py:3118-3133: dofs = renumber[parent dofs]), rational functions
+c_i B_i / W (examples/platewithhole.py:66-83) and a (rational) spline geometry whose Jacobian is the
+derivative of the spline map (function.py:1207-1231, 1266-1295).
+
 Parity pin: tests/test_oracle_golden.py checks this module against the
 golden vectors in tests/golden/*.npz, which were produced by the unmodified
 reference itself (oracle/make_golden.py) -- CSR pattern bit-exact, values to
@@ -53,7 +59,8 @@ class Problem:
     nodes      : float64[ndims, nelems_0+1, ...]  nodal coordinates of the multilinear geometry
     '''
 
-    def __init__(self, nelems, degree, coeffs, setidx, start, ndofs_d, qpts, qwts, nodes, ncomp=1):
+    def __init__(self, nelems, degree, coeffs, setidx, start, ndofs_d, qpts, qwts, nodes, ncomp=1, elem_ids=None, qoff=None, qcoords=None,
+                 qweights=None, renumber=None, nbasis_new=None, scale=None, rational=0, geom_spline=None):
         self.ndims = len(nelems)
         self.nelems = tuple(int(n) for n in nelems)
         self.degree = tuple(int(p) for p in degree)
@@ -65,11 +72,27 @@ class Problem:
         self.qwts = [numpy.asarray(w, dtype=float) for w in qwts]
         self.nodes = numpy.asarray(nodes, dtype=float)
         self.ncomp = int(ncomp)
-        assert self.nodes.shape == (self.ndims,) + tuple(n + 1 for n in self.nelems)
+        # element set (all optional): kept elements, ragged points in element-local coordinates, pruned numbering,
+        # numerator weights c_i and the denominator of rational functions (0 none, 1 own weight function, 2 the geometry's)
+        self.elem_ids = None if elem_ids is None else numpy.asarray(elem_ids, dtype=numpy.int64)
+        self.qoff = None if qoff is None else numpy.asarray(qoff, dtype=numpy.int64)
+        self.qcoords = None if qcoords is None else numpy.asarray(qcoords, dtype=float)
+        self.qweights = None if qweights is None else numpy.asarray(qweights, dtype=float)
+        self.renumber = None if renumber is None else numpy.asarray(renumber, dtype=numpy.int64)
+        self.nbasis_new = None if renumber is None else int(nbasis_new)
+        self.scale = None if scale is None else numpy.asarray(scale, dtype=float)
+        self.rational = int(rational)
+        # spline geometry: dict(degree, coeffs, setidx, start, ndofs_d, ctrl[ndims, nbasis_g], weights[nbasis_g] or None)
+        self.geom_spline = geom_spline
+        assert geom_spline is not None or self.nodes.shape == (self.ndims,) + tuple(n + 1 for n in self.nelems)
 
     @property
     def nbasis(self):
-        return int(numpy.prod(self.ndofs_d))
+        return int(numpy.prod(self.ndofs_d)) if self.renumber is None else self.nbasis_new
+
+    @property
+    def nsel(self):
+        return self.ntotal if self.elem_ids is None else len(self.elem_ids)
 
     @property
     def ndofs(self):
@@ -99,32 +122,84 @@ def _tensor(factors):
     return out
 
 
-def element_data(prob, ielem):
-    '''Everything the generated loop computes for one element before the integrand:
-    dofs[n_e], N[nq,n_e], grad[nq,n_e,ndims] (physical), wdet[nq].'''
-    nd = prob.ndims
-    idx = numpy.unravel_index(ielem, prob.nelems)
+def _tensor_points(factors, npts):
+    'product of per-dim [n_d, npts] tables evaluated at the SAME list of points -> [npts, prod n]'
+    out = numpy.ones((npts, 1))
+    for f in factors:
+        out = (out[:, :, None] * f.T[:, None, :]).reshape(npts, -1)
+    return out
+
+
+def _basis_at(coeffs, setidx, start, degree, ndofs_d, idx, xi):
+    'N[nq, n_e], dN/dxi[nq, n_e, nd] and parent dofs of a tensor-product space on element idx at local points xi[nq, nd]'
+    nd = len(idx)
     vals, ders, ranges = [], [], []
     for d in range(nd):
-        c = prob.coeffs[d][prob.setidx[d][idx[d]]]
-        v, g = _polyval_rows(c, prob.qpts[d])
+        v, g = _polyval_rows(coeffs[d][setidx[d][idx[d]]], xi[:, d])
         vals.append(v)
         ders.append(g)
-        ranges.append((prob.start[d][idx[d]] + numpy.arange(prob.degree[d] + 1)) % prob.ndofs_d[d])
-    N = _tensor(vals)
-    dN = numpy.stack([_tensor([ders[k] if k == d else vals[k] for k in range(nd)]) for d in range(nd)], axis=-1)
+        ranges.append((start[d][idx[d]] + numpy.arange(degree[d] + 1)) % ndofs_d[d])
+    N = _tensor_points(vals, len(xi))
+    dN = numpy.stack([_tensor_points([ders[k] if k == d else vals[k] for k in range(nd)], len(xi)) for d in range(nd)], axis=-1)
     dofs = ranges[0]
     for d in range(1, nd):
-        dofs = (dofs[:, None] * prob.ndofs_d[d] + ranges[d][None, :]).ravel()
-    # multilinear geometry: shape functions of the degree-1 spline on this element are (1-xi, xi) per dim
-    lin_v = [numpy.stack([1 - x, x]) for x in prob.qpts]
-    lin_d = [numpy.stack([-numpy.ones_like(x), numpy.ones_like(x)]) for x in prob.qpts]
-    X = prob.nodes[(slice(None),) + tuple(slice(i, i + 2) for i in idx)].reshape(nd, -1)  # [ndims, 2^nd] C-order vertices
-    J = numpy.stack([_tensor([lin_d[k] if k == d else lin_v[k] for k in range(nd)]) @ X.T for d in range(nd)], axis=-1)  # [nq, i, k] = dx_i/dxi_k
+        dofs = (dofs[:, None] * ndofs_d[d] + ranges[d][None, :]).ravel()
+    return N, dN, dofs
+
+
+def element_data(prob, isel):
+    '''Everything the generated loop computes for one (selected) element before the integrand:
+    dofs[n_e] (-1: dropped by the pruned numbering), N[nq,n_e], grad[nq,n_e,ndims] (physical), wdet[nq].'''
+    nd = prob.ndims
+    ielem = isel if prob.elem_ids is None else int(prob.elem_ids[isel])
+    idx = numpy.unravel_index(ielem, prob.nelems)
+    if prob.qoff is None:
+        # uniform tensor rule, C-order outer product (pointsseq.py:420-428)
+        grids = numpy.meshgrid(*prob.qpts, indexing='ij')
+        xi = numpy.stack([g.ravel() for g in grids], axis=-1)
+        w = _tensor([wq[None, :] for wq in prob.qwts])[:, 0]
+    else:
+        xi = prob.qcoords[prob.qoff[isel]:prob.qoff[isel + 1]]
+        w = prob.qweights[prob.qoff[isel]:prob.qoff[isel + 1]]
+    N, dN, dofs = _basis_at(prob.coeffs, prob.setidx, prob.start, prob.degree, prob.ndofs_d, idx, xi)
+    Wg = dWg = None
+    if prob.geom_spline is None:
+        # multilinear geometry: shape functions of the degree-1 spline on this element are (1-xi, xi) per dim
+        lin_v = [numpy.stack([1 - xi[:, d], xi[:, d]]) for d in range(nd)]
+        lin_d = [numpy.stack([-numpy.ones(len(xi)), numpy.ones(len(xi))]) for d in range(nd)]
+        X = prob.nodes[(slice(None),) + tuple(slice(i, i + 2) for i in idx)].reshape(nd, -1)  # [ndims, 2^nd] C-order vertices
+        J = numpy.stack([_tensor_points([lin_d[k] if k == d else lin_v[k] for k in range(nd)], len(xi)) @ X.T for d in range(nd)], axis=-1)  # [nq, i, k] = dx_i/dxi_k
+    else:
+        g = prob.geom_spline
+        Ng, dNg, gdofs = _basis_at(g['coeffs'], g['setidx'], g['start'], g['degree'], g['ndofs_d'], idx, xi)
+        ctrl = numpy.asarray(g['ctrl'], dtype=float)[:, gdofs]  # [ndims, n_g]
+        if g.get('weights') is None:
+            J = numpy.einsum('qak,ia->qik', dNg, ctrl)
+        else:
+            wts = numpy.asarray(g['weights'], dtype=float)[gdofs]
+            Wg = Ng @ wts
+            dWg = numpy.einsum('qak,a->qk', dNg, wts)
+            Xh = Ng @ (ctrl * wts).T                            # [nq, ndims]
+            dXh = numpy.einsum('qak,ia->qik', dNg, ctrl * wts)
+            x = Xh / Wg[:, None]
+            J = (dXh - x[:, :, None] * dWg[:, None, :]) / Wg[:, None, None]
+    if prob.scale is not None:
+        c = prob.scale[dofs]
+        N = N * c
+        dN = dN * c[None, :, None]
+    if prob.rational:
+        if prob.rational == 1:
+            W, dW = N.sum(1), dN.sum(1)                         # sum_j c_j B_j and its xi-gradient
+        else:
+            W, dW = Wg, dWg
+        N = N / W[:, None]
+        dN = (dN - N[:, :, None] * dW[:, None, :]) / W[:, None, None]
     Jinv = numpy.linalg.inv(J)
     det = numpy.linalg.det(J)
-    w = _tensor([wq[None, :] for wq in prob.qwts])[:, 0]
     grad = numpy.einsum('qak,qki->qai', dN, Jinv)
+    if prob.renumber is not None:
+        dofs = prob.renumber[dofs]
+        dofs = numpy.where((dofs >= 0) & (dofs < prob.nbasis_new), dofs, -1)
     return dofs, N, grad, w * abs(det)
 
 
@@ -202,7 +277,7 @@ def assemble(prob, matrix_forms=(), vector_forms=()):
     Returns ([(values, rowptr, colidx), ...], [rhs, ...]).'''
     nc = prob.ncomp
     n_e = int(numpy.prod([p + 1 for p in prob.degree])) * nc
-    nel = prob.ntotal
+    nel = prob.nsel
     vals = [numpy.empty((nel, n_e, n_e)) for _ in matrix_forms]
     rows = numpy.empty((nel, n_e, n_e), dtype=numpy.int64)
     cols = numpy.empty((nel, n_e, n_e), dtype=numpy.int64)

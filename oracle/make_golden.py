@@ -117,6 +117,118 @@ def elasticity_case(name, n, degree, lmbda=1., poisson=.3, vkind='graded', warp=
                 F=numpy.asarray(res).ravel())
 
 
+# ---- element sets: trimmed topologies (finite cell method) and NURBS -----------------------------------
+
+def _ragged_points(topo, qdegree):
+    'per-element points of topo.sample("gauss", qdegree) in element-local coordinates: qoff, qcoords, qweights'
+    smp = topo.sample('gauss', qdegree)
+    coords, weights, qoff = [], [], [0]
+    for i in range(len(topo)):
+        p = smp.points.get(i)
+        coords.append(numpy.asarray(p.coords))
+        weights.append(numpy.asarray(p.weights))
+        qoff.append(qoff[-1] + len(weights[-1]))
+    return numpy.array(qoff, dtype=numpy.int64), numpy.concatenate(coords), numpy.concatenate(weights)
+
+
+def _elasticity_system(topo, geom, basis, ndims, lmbda, mu, qdegree, load):
+    'jacobian and residual (at u=0) of  int (grad_j(v_i) sigma_ij - v_i q_i) dV  (examples/platewithhole.py:118-151)'
+    ns = Namespace()
+    ns.δ = function.eye(ndims)
+    ns.x = geom
+    ns.define_for('x', gradient='∇', jacobians=('dV',))
+    ns.λ = lmbda
+    ns.μ = mu
+    ns.u = function.field('u', basis, shape=[ndims])
+    ns.v = function.field('v', basis, shape=[ndims])
+    ns.ε_ij = '(∇_j(u_i) + ∇_i(u_j)) / 2'
+    ns.σ_ij = 'λ ε_kk δ_ij + 2 μ ε_ij'
+    ns.q = numpy.asarray(load, dtype=float)
+    res = topo.integral('(∇_j(v_i) σ_ij - v_i q_i) dV' @ ns, degree=qdegree)
+    system = System(res, trial='u', test='v')
+    jac, r = system.assemble_jacobian_residual(arguments={'u': numpy.zeros((len(basis), ndims))})[:2]
+    data, indices, indptr = jac.export('csr')
+    return numpy.asarray(data), numpy.asarray(indptr, dtype=numpy.int64), numpy.asarray(indices, dtype=numpy.int64), numpy.asarray(r).ravel()
+
+
+def fcm_scalar_case(name, n, degree, radius, maxrefine, ball=True):
+    'config 5 at toy size: Poisson on a ball (or a box with a spherical hole) cut out of a structured grid, spline basis'
+    ndims = len(n)
+    verts = [numpy.linspace(-1, 1, ni + 1) for ni in n]
+    topo0, geom = mesh.rectilinear(verts)
+    levelset = radius - numpy.linalg.norm(geom) if ball else numpy.linalg.norm(geom) - radius
+    topo = topo0.trim(levelset, maxrefine=maxrefine)
+    basis = topo.basis('spline', degree=degree)
+    qd = 2 * degree
+    J = function.J(geom)
+    g = basis.grad(geom)
+    K = topo.integral((g[:, None, :] * g[None, :, :]).sum(-1) * J, degree=qd)
+    M = topo.integral(basis[:, None] * basis[None, :] * J, degree=qd)
+    F = topo.integral(basis * J, degree=qd)
+    (kv, krp, kci), (mv, mrp, mci), f = function.eval((function.as_csr(K), function.as_csr(M), F))
+    assert (krp == mrp).all() and (kci == mci).all()
+    qoff, qcoords, qweights = _ragged_points(topo, qd)
+    return dict(kind='elemset_scalar', name=name, ndims=ndims, nelems=numpy.array(n), degree=degree, btype='spline', qdegree=qd,
+                nodes=numpy.stack(numpy.meshgrid(*verts, indexing='ij')), ndofs=len(basis), ncomp=1,
+                elem_ids=numpy.asarray(basis._transmap, dtype=numpy.int64), renumber=numpy.asarray(basis._renumber, dtype=numpy.int64), nbasis_new=len(basis),
+                qoff=qoff, qcoords=qcoords, qweights=qweights, volume=function.eval(topo.integral(J, degree=qd)),
+                K_values=kv, M_values=mv, rowptr=krp, colidx=kci, F=f)
+
+
+def fcm_plate_case(name, nelems=4, degree=2, maxrefine=2, radius=.5, poisson=.3):
+    'examples/platewithhole.py FCM mode (its own unit test uses nelems=4, spline): 2-D plane-strain elasticity on a trimmed square'
+    topo0, geom = mesh.unitsquare(nelems, 'square')
+    topo = topo0.trim(numpy.linalg.norm(geom) - radius, maxrefine=maxrefine, name='hole')
+    basis = topo.basis('spline', degree=degree)
+    lmbda, mu = 2 * poisson, 1 - poisson
+    qd = 2 * degree
+    kv, rp, ci, r = _elasticity_system(topo, geom, basis, 2, lmbda, mu, qd, load=[.3, -1.])
+    qoff, qcoords, qweights = _ragged_points(topo, qd)
+    verts = [numpy.linspace(0, 1, nelems + 1)] * 2
+    return dict(kind='elemset_elasticity', name=name, ndims=2, nelems=numpy.array([nelems] * 2), degree=degree, btype='spline', qdegree=qd,
+                nodes=numpy.stack(numpy.meshgrid(*verts, indexing='ij')), ndofs=2 * len(basis), ncomp=2, lmbda=lmbda, mu=mu, load=numpy.array([.3, -1.]),
+                elem_ids=numpy.asarray(basis._transmap, dtype=numpy.int64), renumber=numpy.asarray(basis._renumber, dtype=numpy.int64), nbasis_new=len(basis),
+                qoff=qoff, qcoords=qcoords, qweights=qweights,
+                K_values=kv, rowptr=rp, colidx=ci, F=r)
+
+
+def nurbs_plate_case(name, nrefine=2, degree=2, radius=.5, poisson=.3, qdegree=10):
+    '''examples/platewithhole.py NURBS mode (:66-86): a 1x2 quadratic NURBS patch mapped onto the quarter plate with hole,
+    refined nrefine times; analysis basis = B-splines of `degree` on the refined topology times projected control weights,
+    divided by the patch's weight function.  degree=2 is the example itself, degree=4 is BASELINE config 4.'''
+    topo, geom0 = mesh.rectilinear([1, 2])
+    bsplinebasis = topo.basis('spline', degree=2)
+    controlweights = numpy.ones(12)
+    controlweights[1:3] = .5 + .25 * numpy.sqrt(2)
+    weightfunc = bsplinebasis @ controlweights
+    nurbsbasis = bsplinebasis * controlweights / weightfunc
+    A = 0, 0, 0
+    B = (2**.5 - 1) * radius, .3 * (radius + 1) / 2, 1
+    C = radius, (radius + 1) / 2, 1
+    controlpoints = numpy.array([[A, B, C, C], [C, C, B, A]]).T.reshape(-1, 2)
+    geom = nurbsbasis @ controlpoints
+    topo = topo.refine(nrefine)
+
+    def project(target, pbasis):
+        sqr = topo.integral((function.field('w', pbasis) - target)**2, degree=9)
+        return System(sqr, trial='w').solve()['w']
+    # the patch's weight function and weighted coordinates in the quadratic B-splines of the refined topology (nested
+    # spaces: the projection is exact) -- this is the representation handed to b2_geom_create_spline
+    fine2 = topo.basis('spline', degree=2)
+    gweights = project(weightfunc, fine2)
+    gctrl = numpy.stack([project(weightfunc * geom[i], fine2) for i in range(2)]) / gweights
+    # analysis basis, as in the example (:79-83)
+    abasis = topo.basis('spline', degree=degree)
+    cw = project(weightfunc, abasis)
+    nbasis = abasis * cw / weightfunc
+    lmbda, mu = 2 * poisson, 1 - poisson
+    kv, rp, ci, r = _elasticity_system(topo, geom, nbasis, 2, lmbda, mu, qdegree, load=[.3, -1.])
+    return dict(kind='elemset_elasticity', name=name, ndims=2, nelems=numpy.array(topo.shape), degree=degree, btype='spline', qdegree=qdegree,
+                ndofs=2 * len(abasis), ncomp=2, lmbda=lmbda, mu=mu, load=numpy.array([.3, -1.]),
+                scale=cw, rational=2, gdegree=2, gctrl=gctrl, gweights=gweights,
+                K_values=kv, rowptr=rp, colidx=ci, F=r)
+
+
 def known_answer_mass_1d():
     # tests/test_function.py:1574-1585 (known-answer COO of a 1-D p=1 mass matrix)
     topo, geom = mesh.line([0, 1, 2], bnames=['a', 'b'], space='X')
@@ -146,6 +258,12 @@ CASES = {
     'hex_p2_underint': lambda: scalar_case('hex_p2_underint', (3, 3, 2), 2, qdegree=2),
     'elast2d_p2_warp': lambda: elasticity_case('elast2d_p2_warp', (4, 5), 2, warp=.3, seed=6),
     'elast3d_p1': lambda: elasticity_case('elast3d_p1', (3, 2, 3), 1),
+    'fcm3d_ball_p2': lambda: fcm_scalar_case('fcm3d_ball_p2', (4, 4, 4), 2, radius=.8, maxrefine=1),                 # config 5 at toy size
+    'fcm3d_hole_p1': lambda: fcm_scalar_case('fcm3d_hole_p1', (3, 4, 3), 1, radius=.7, maxrefine=2, ball=False),
+    'fcm2d_disc_p3': lambda: fcm_scalar_case('fcm2d_disc_p3', (6, 5), 3, radius=.75, maxrefine=2),
+    'fcm2d_plate_p2': lambda: fcm_plate_case('fcm2d_plate_p2'),                                                      # examples/platewithhole.py FCM, its test size
+    'nurbs_plate_p2': lambda: nurbs_plate_case('nurbs_plate_p2', nrefine=2, degree=2),                               # examples/platewithhole.py NURBS
+    'nurbs_plate_p4': lambda: nurbs_plate_case('nurbs_plate_p4', nrefine=2, degree=4),                               # config 4 at toy size
     'elast3d_p2_warp': lambda: elasticity_case('elast3d_p2_warp', (3, 3, 2), 2, warp=.3, seed=7),  # config 3 at toy size
 }
 

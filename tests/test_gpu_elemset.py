@@ -1,0 +1,163 @@
+'''Parity of the element-set CUDA path (b2_elemset_* / b2_pattern_create_elemset / b2_assemble_elemset_*, through the
+C ABI) with the golden vectors of the reference: trimmed topologies with ragged cut-cell quadrature and pruned dof
+numbering (finite cell method, BASELINE config 5; examples/platewithhole.py FCM mode) and rational splines on a
+NURBS geometry (examples/platewithhole.py NURBS mode, degree 2 and BASELINE config 4's degree 4).
+Bar: CSR pattern bit-exact; values: relative Frobenius and row-sum error <= 1e-12; rhs <= 1e-12.'''
+
+import numpy
+import pytest
+
+from tests import util
+from oracle import fem_oracle
+from nutils_b200 import engine, bspline, points
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    import torch
+    c = engine.Context.get(0)
+    c.set_stream(torch.cuda.current_stream().cuda_stream)
+    yield c
+    c.set_stream(None)
+
+
+def _bases(prob):
+    return [bspline.Basis1D(prob.degree[d], prob.nelems[d], prob.coeffs[d], prob.setidx[d], prob.start[d], prob.ndofs_d[d]) for d in range(prob.ndims)]
+
+
+def _plan(ctx, prob):
+    gs = None
+    if prob.geom_spline is not None:
+        g = prob.geom_spline
+        gb = [bspline.Basis1D(g['degree'][d], prob.nelems[d], g['coeffs'][d], g['setidx'][d], g['start'][d], g['ndofs_d'][d]) for d in range(prob.ndims)]
+        gs = gb, g['ctrl'], g['weights']
+    return engine.ElemSetPlan(ctx, _bases(prob), nodes=None if gs else prob.nodes, ncomp=prob.ncomp, rules=list(zip(prob.qpts, prob.qwts)),
+                              elem_ids=prob.elem_ids, qoff=prob.qoff, qcoords=prob.qcoords, qweights=prob.qweights,
+                              renumber=prob.renumber, nbasis_new=prob.nbasis_new, scale=prob.scale, rational=prob.rational, geom_spline=gs)
+
+
+@pytest.mark.parametrize('name', util.elemset_golden_names())
+def test_golden(ctx, name):
+    g = util.load_golden(name)
+    prob = util.elemset_problem_from_golden(g)
+    plan = _plan(ctx, prob)
+    rowptr, colidx = plan.csr_pattern()
+    assert rowptr.dtype == numpy.int64 and colidx.dtype == numpy.int64
+    assert numpy.array_equal(rowptr, g['rowptr'])
+    assert numpy.array_equal(colidx, g['colidx'])
+    assert plan.ndofs == int(g['ndofs']) and plan.nnz == len(g['colidx'])
+    Ds, Cs, expect, F = util.elemset_forms(g, prob.ndims)
+    vals, rhs = plan.assemble_host(Ds, Cs)
+    for v, ref in zip(vals, expect):
+        assert util.relerr(v, ref) <= TOL
+        assert util.rowsum_relerr(v, ref, rowptr) <= TOL
+    assert util.relerr(rhs[0], F) <= TOL
+    if 'volume' in g:
+        assert abs(vals[1].sum() - float(g['volume'])) <= 1e-12 * abs(float(g['volume']))
+    for k in range(plan.ndofs + 1):
+        if k % 37 == 0 or k == plan.ndofs:
+            assert plan.row_offset(k) == rowptr[k]
+
+
+@pytest.mark.parametrize('name', ['hex_p2_warp', 'quad_p3', 'elast3d_p1', 'line_p3_std', 'hex_p2_std'])
+def test_full_selection_equals_structured(ctx, name):
+    # an element set that selects everything (tensor rule, identity numbering) reproduces the structured goldens:
+    # the general pattern construction against the analytic one, the element-set kernel against the reference
+    g = util.load_golden(name)
+    prob = util.problem_from_golden(g)
+    plan = engine.ElemSetPlan(ctx, _bases(prob), nodes=prob.nodes, ncomp=prob.ncomp, rules=list(zip(prob.qpts, prob.qwts)))
+    rowptr, colidx = plan.csr_pattern()
+    assert numpy.array_equal(rowptr, g['rowptr']) and numpy.array_equal(colidx, g['colidx'])
+    nd = prob.ndims
+    if str(g['kind']) == 'scalar':
+        Ds, Cs, expect = [engine.form_stiffness(nd), engine.form_mass(nd)], [engine.form_load(nd)], [g['K_values'], g['M_values']]
+    else:
+        C = numpy.zeros((nd, nd + 1))
+        C[nd - 1, 0] = 1.
+        Ds, Cs, expect = [engine.form_elasticity(nd, float(g['lmbda']), float(g['mu']), scale=2.)], [C], [g['K_values']]
+    vals, rhs = plan.assemble_host(Ds, Cs)
+    for v, ref in zip(vals, expect):
+        assert util.relerr(v, ref) <= TOL
+    assert util.relerr(rhs[0], g['F']) <= TOL
+
+
+def _random_cut(seed, nelems, degree, keep=.6, maxpts=40):
+    'random element subset with random ragged point sets (positive weights), pruned numbering derived like PrunedBasis does'
+    rng = numpy.random.RandomState(seed)
+    nd = len(nelems)
+    b1 = util.bases_1d(nelems, degree, 'spline')
+    ntot = int(numpy.prod(nelems))
+    elem_ids = numpy.sort(rng.choice(ntot, size=max(1, int(keep * ntot)), replace=False))
+    npts = rng.randint(0, maxpts, size=len(elem_ids))     # empty point sets are legal (fully trimmed away but kept)
+    qoff = numpy.concatenate([[0], numpy.cumsum(npts)])
+    qcoords = rng.rand(qoff[-1], nd)
+    qweights = rng.rand(qoff[-1]) / maxpts
+    rules = points.tensor_gauss(nd, 2 * degree)
+    verts = [numpy.sort(rng.rand(n + 1)) + numpy.arange(n + 1) for n in nelems]
+    X = numpy.stack(numpy.meshgrid(*verts, indexing='ij'))
+    X = X + .25 * (rng.rand(*X.shape) - .5)
+    prob = fem_oracle.Problem(nelems, [degree] * nd, [b.coeffs for b in b1], [b.setidx for b in b1], [b.start for b in b1], [b.ndofs for b in b1],
+                              [r[0] for r in rules], [r[1] for r in rules], X)
+    # PrunedBasis (function.py:3121-3122): sorted unique parent dofs of the kept elements, inverse map with missing = len
+    prob.elem_ids = None
+    dofs = numpy.unique(numpy.concatenate([fem_oracle.element_data(prob, int(e))[0] for e in elem_ids]))
+    renumber = numpy.full(int(numpy.prod(prob.ndofs_d)), len(dofs), dtype=numpy.int64)
+    renumber[dofs] = numpy.arange(len(dofs))
+    return fem_oracle.Problem(nelems, [degree] * nd, [b.coeffs for b in b1], [b.setidx for b in b1], [b.start for b in b1], [b.ndofs for b in b1],
+                              [r[0] for r in rules], [r[1] for r in rules], X, elem_ids=elem_ids, qoff=qoff, qcoords=qcoords, qweights=qweights,
+                              renumber=renumber, nbasis_new=len(dofs))
+
+
+@pytest.mark.parametrize('seed,nelems,degree', [(0, (5, 4, 3), 2), (1, (7, 6), 3), (2, (9,), 2), (3, (4, 3, 4), 1), (4, (5, 5), 4), (5, (3, 3, 3), 3)])
+def test_random_cut_against_oracle(ctx, seed, nelems, degree):
+    prob = _random_cut(seed, nelems, degree)
+    nd = prob.ndims
+    rng = numpy.random.RandomState(100 + seed)
+    D = rng.rand(1, nd + 1, 1, nd + 1)        # a full coefficient tensor: values, gradients and the mixed terms
+    C = rng.rand(1, nd + 1)
+    mats, vecs = fem_oracle.assemble(prob, [('generic', D), ('mass',)], [('generic', C)])
+    plan = _plan(ctx, prob)
+    rowptr, colidx = plan.csr_pattern()
+    assert numpy.array_equal(rowptr, mats[0][1]) and numpy.array_equal(colidx, mats[0][2])
+    vals, rhs = plan.assemble_host([D, engine.form_mass(nd)], [C])
+    for v, (ref, _, _) in zip(vals, mats):
+        assert util.relerr(v, ref) <= TOL
+        assert util.rowsum_relerr(v, ref, rowptr) <= TOL
+    assert util.relerr(rhs[0], vecs[0]) <= TOL
+
+
+def test_device_accumulate_in_two_halves(ctx):
+    # b2_assemble_elemset_device accumulates: two halves of the selection add up to the whole (what multi-GPU sharding uses)
+    import torch
+    prob = _random_cut(7, (5, 4, 4), 2)
+    plan = _plan(ctx, prob)
+    nd = prob.ndims
+    Ds, Cs = [engine.form_stiffness(nd)], [engine.form_load(nd)]
+    whole, rhs_whole = plan.assemble_host(Ds, Cs)
+    dev = torch.device('cuda', 0)
+    v = torch.zeros(plan.nnz, dtype=torch.float64, device=dev)
+    r = torch.zeros(plan.ndofs, dtype=torch.float64, device=dev)
+    half = plan.nsel // 2
+    plan.assemble_device(Ds, Cs, [v], [r], sel_range=(0, half))
+    plan.assemble_device(Ds, Cs, [v], [r], sel_range=(half, plan.nsel))
+    torch.cuda.synchronize()
+    assert util.relerr(v.cpu().numpy(), whole[0]) <= TOL
+    assert util.relerr(r.cpu().numpy(), rhs_whole[0]) <= TOL
+
+
+def test_invalid_arguments(ctx):
+    from nutils_b200 import _lib
+    b1 = util.bases_1d((3, 3), 2, 'spline')
+    nodes = numpy.stack(numpy.meshgrid(numpy.arange(4.), numpy.arange(4.), indexing='ij'))
+    rules = points.tensor_gauss(2, 4)
+    with pytest.raises(_lib.B200Error):   # elem_ids not increasing
+        engine.ElemSetPlan(ctx, b1, nodes=nodes, rules=rules, elem_ids=[3, 1])
+    with pytest.raises(_lib.B200Error):   # renumber not monotone
+        ren = numpy.arange(25)[::-1].copy()
+        engine.ElemSetPlan(ctx, b1, nodes=nodes, rules=rules, renumber=ren, nbasis_new=25)
+    with pytest.raises(_lib.B200Error):   # rational mode 2 without a rational geometry
+        plan = engine.ElemSetPlan(ctx, b1, nodes=nodes, rules=rules, scale=numpy.ones(25), rational=2)
+        plan.assemble_host([engine.form_mass(2)], [])

@@ -49,6 +49,25 @@ def test_c_oracle(name):
     _check(g, *c_oracle.assemble(prob, mf, vf))
 
 
+@pytest.mark.parametrize('name', util.elemset_golden_names())
+def test_numpy_oracle_elemset(name):
+    # trimmed topologies (ragged points, pruned numbering), NURBS: the numpy restatement against the reference's output
+    g = util.load_golden(name)
+    prob = util.elemset_problem_from_golden(g)
+    Ds, Cs, expect, F = util.elemset_forms(g, prob.ndims)
+    mats, vecs = fem_oracle.assemble(prob, [('generic', D) for D in Ds], [('generic', C) for C in Cs])
+    for (v, rp, ci), ref in zip(mats, expect):
+        assert rp.dtype == numpy.int64 and ci.dtype == numpy.int64
+        assert numpy.array_equal(rp, g['rowptr'])
+        assert numpy.array_equal(ci, g['colidx'])
+        assert util.relerr(v, ref) <= 1e-12
+        assert util.rowsum_relerr(v, ref, rp) <= 1e-12
+    assert util.relerr(vecs[0], F) <= 1e-12
+    if 'volume' in g:
+        # sum of the mass matrix = volume of the trimmed domain (partition of unity survives the pruning)
+        assert abs(mats[1][0].sum() - float(g['volume'])) <= 1e-13 * abs(float(g['volume']))
+
+
 def test_known_answer_mass_1d():
     # tests/test_function.py:1574-1585 of the reference: exact COO of the 1-D p=1 mass matrix
     g = util.load_golden('mass1d_known')

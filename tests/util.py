@@ -14,8 +14,23 @@ from nutils_b200 import bspline, points  # noqa: E402
 from oracle import fem_oracle  # noqa: E402
 
 
-def golden_names():
+def _all_golden_names():
     return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, '*.npz')))
+
+
+def _kind(name):
+    with numpy.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False) as f:
+        return str(f['kind'])
+
+
+def golden_names():
+    'structured cases: every element of the grid, one tensor rule, multilinear geometry'
+    return [n for n in _all_golden_names() if not _kind(n).startswith('elemset')]
+
+
+def elemset_golden_names():
+    'element-set cases: trimmed topologies with ragged points and pruned numbering, NURBS'
+    return [n for n in _all_golden_names() if _kind(n).startswith('elemset')]
 
 
 def load_golden(name):
@@ -37,6 +52,42 @@ def problem_from_golden(g):
     ncomp = ndims if str(g['kind']) == 'elasticity' else 1
     return fem_oracle.Problem(nelems, [degree] * ndims, [b.coeffs for b in b1], [b.setidx for b in b1], [b.start for b in b1],
                               [b.ndofs for b in b1], [r[0] for r in rules], [r[1] for r in rules], g['nodes'], ncomp=ncomp)
+
+
+def elemset_problem_from_golden(g):
+    'oracle Problem of an element-set golden (kind elemset_scalar / elemset_elasticity)'
+    nelems = tuple(int(n) for n in g['nelems'])
+    degree = int(g['degree'])
+    ndims = len(nelems)
+    b1 = bases_1d(nelems, degree, str(g['btype']))
+    rules = points.tensor_gauss(ndims, int(g['qdegree']))
+    kw = dict(ncomp=int(g['ncomp']))
+    for key in 'elem_ids', 'qoff', 'qcoords', 'qweights', 'renumber', 'scale':
+        if key in g:
+            kw[key] = g[key]
+    if 'renumber' in g:
+        kw['nbasis_new'] = int(g['nbasis_new'])
+    if 'rational' in g:
+        kw['rational'] = int(g['rational'])
+    nodes = g['nodes'] if 'nodes' in g else None
+    if 'gctrl' in g:
+        gb = bases_1d(nelems, int(g['gdegree']), 'spline')
+        kw['geom_spline'] = dict(degree=[b.degree for b in gb], coeffs=[b.coeffs for b in gb], setidx=[b.setidx for b in gb], start=[b.start for b in gb],
+                                 ndofs_d=[b.ndofs for b in gb], ctrl=g['gctrl'], weights=g['gweights'] if 'gweights' in g else None)
+        nodes = numpy.zeros((ndims,) + (0,) * ndims)
+    return fem_oracle.Problem(nelems, [degree] * ndims, [b.coeffs for b in b1], [b.setidx for b in b1], [b.start for b in b1],
+                              [b.ndofs for b in b1], [r[0] for r in rules], [r[1] for r in rules], nodes, **kw)
+
+
+def elemset_forms(g, ndims):
+    '''(matrix coefficient tensors D, vector coefficient tensors C, expected values, expected rhs) of an element-set golden;
+    elasticity goldens hold the jacobian/residual of int (grad_j(v_i) sigma_ij - v_i q_i) dV at u=0'''
+    from nutils_b200 import engine
+    if str(g['kind']) == 'elemset_scalar':
+        return [engine.form_stiffness(ndims), engine.form_mass(ndims)], [engine.form_load(ndims)], [g['K_values'], g['M_values']], g['F']
+    C = numpy.zeros((ndims, ndims + 1))
+    C[:, 0] = -numpy.asarray(g['load'])
+    return [engine.form_elasticity(ndims, float(g['lmbda']), float(g['mu']))], [C], [g['K_values']], g['F']
 
 
 def relerr(a, b):
