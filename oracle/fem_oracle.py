@@ -126,7 +126,7 @@ def _tensor_points(factors, npts):
     'product of per-dim [n_d, npts] tables evaluated at the SAME list of points -> [npts, prod n]'
     out = numpy.ones((npts, 1))
     for f in factors:
-        out = (out[:, :, None] * f.T[:, None, :]).reshape(npts, -1)
+        out = (out[:, :, None] * f.T[:, None, :]).reshape(npts, out.shape[1] * f.shape[0])
     return out
 
 
