@@ -1,0 +1,96 @@
+'''Table extraction from evalf/nutils objects: the reference-side half of the drop-in.
+
+Everything the CUDA path consumes is a plain array that the reference already holds inside its own
+objects; this module reads those arrays out (duck-typed -- nutils is NOT imported here) so that a
+topology built, refined or TRIMMED by the reference's host code (topology.trim and the cut-cell
+mosaics of element.py stay where they are: host Python, outside the measured path) can be integrated
+through the C ABI:
+
+    StructuredBasis._coeffs / _start_dofs / _dofs_shape   function.py:3051-3058   -> bspline.Basis1D per dimension
+    PrunedBasis._transmap / _renumber                     function.py:3118-3123   -> elem_ids, renumber, nbasis_new
+    Sample.points.get(ielem).coords / .weights            pointsseq.py:324-332    -> qoff, qcoords, qweights
+    vertex arrays of mesh.rectilinear                     mesh.py:34-57           -> nodes
+
+`plan_from_reference` turns them into an :class:`engine.ElemSetPlan` (trimmed / pruned) or an
+:class:`engine.Plan` (plain structured).  INTEGRATION.md shows where the reference would call it.
+'''
+
+import numpy
+from . import bspline, engine
+
+
+def bases1d_from_structured_basis(basis):
+    '''per-dimension bspline.Basis1D tables of a nutils ``function.StructuredBasis`` (function.py:3040-3100).
+
+    ``_coeffs[d][e]`` is the (p+1) x (p+1) coefficient array of element e along d, highest power first
+    (topology.py:2327-2361); equal arrays are shared into coefficient sets.'''
+    out = []
+    for coeffs_d, start_d, stop_d, ndofs_d in zip(basis._coeffs, basis._start_dofs, basis._stop_dofs, basis._dofs_shape):
+        sets, setidx, index = [], [], {}
+        for c in coeffs_d:
+            a = numpy.asarray(c, dtype=float)
+            key = a.shape, a.tobytes()
+            k = index.get(key)
+            if k is None:
+                k = index[key] = len(sets)
+                sets.append(a)
+            setidx.append(k)
+        start = numpy.asarray(start_d, dtype=numpy.int64)
+        stop = numpy.asarray(stop_d, dtype=numpy.int64)
+        p = sets[0].shape[0] - 1
+        if any(s.shape != (p + 1, p + 1) for s in sets) or (stop - start != p + 1).any():
+            raise NotImplementedError('elements with a varying number of functions along one dimension')
+        if (start + p >= ndofs_d).any():
+            raise NotImplementedError('periodic bases are outside the accelerated path')
+        out.append(bspline.Basis1D(p, len(setidx), numpy.stack(sets), numpy.array(setidx, dtype=numpy.int32), start, int(ndofs_d)))
+    return out
+
+
+def ragged_points(sample, nelems=None):
+    '(qoff int64[n+1], qcoords float64[npoints, ndims], qweights float64[npoints]) of a nutils Sample, element-local coordinates'
+    n = sample.nelems if nelems is None else nelems
+    coords, weights, qoff = [], [], [0]
+    for i in range(n):
+        p = sample.points.get(i)
+        coords.append(numpy.asarray(p.coords, dtype=float))
+        weights.append(numpy.asarray(p.weights, dtype=float))
+        qoff.append(qoff[-1] + len(weights[-1]))
+    ndims = coords[0].shape[1] if coords else 0
+    return (numpy.array(qoff, dtype=numpy.int64), numpy.concatenate(coords) if coords else numpy.zeros((0, ndims)),
+            numpy.concatenate(weights) if weights else numpy.zeros(0))
+
+
+def tables_from_reference(topo, basis, degree, vertices=None, nodes=None, ischeme='gauss'):
+    '''Arrays describing ``topo.integral(<form in basis> * J(geom), degree=degree)`` for a structured topology or a
+    trimmed / subset topology of one, with a StructuredBasis or a PrunedBasis of one.
+
+    vertices : per-dimension vertex arrays (what was passed to mesh.rectilinear), or
+    nodes    : explicit nodal coordinates float64[ndims, n0+1, ...] of a multilinear geometry.'''
+    parent = getattr(basis, '_parent', basis)
+    if not hasattr(parent, '_start_dofs'):
+        raise NotImplementedError('only (pruned) structured bases are on the accelerated path')
+    bases = bases1d_from_structured_basis(parent)
+    shape = tuple(parent._transforms_shape)
+    if nodes is None:
+        if vertices is None:
+            raise ValueError('either vertices or nodes are needed')
+        nodes = numpy.stack(numpy.meshgrid(*[numpy.asarray(v, dtype=float) for v in vertices], indexing='ij'))
+    t = dict(bases=bases, nelems=shape, nodes=numpy.asarray(nodes, dtype=float))
+    if parent is not basis:
+        t['elem_ids'] = numpy.asarray(basis._transmap, dtype=numpy.int64)
+        t['renumber'] = numpy.asarray(basis._renumber, dtype=numpy.int64)
+        t['nbasis_new'] = len(basis)
+        if len(topo) != len(t['elem_ids']):
+            raise ValueError('basis and topology have different elements')
+        t['qoff'], t['qcoords'], t['qweights'] = ragged_points(topo.sample(ischeme, degree), len(topo))
+    return t
+
+
+def plan_from_reference(ctx, topo, basis, degree, vertices=None, nodes=None, ncomp=1):
+    'engine.Plan (structured) or engine.ElemSetPlan (trimmed / pruned) for reference objects; see tables_from_reference'
+    from . import points
+    t = tables_from_reference(topo, basis, degree, vertices=vertices, nodes=nodes)
+    if 'elem_ids' in t:
+        return engine.ElemSetPlan(ctx, t['bases'], nodes=t['nodes'], ncomp=ncomp, elem_ids=t['elem_ids'], qoff=t['qoff'], qcoords=t['qcoords'],
+                                  qweights=t['qweights'], renumber=t['renumber'], nbasis_new=t['nbasis_new'])
+    return engine.Plan(ctx, t['bases'], points.tensor_gauss(len(t['bases']), degree), t['nodes'], ncomp=ncomp)
