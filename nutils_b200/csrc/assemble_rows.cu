@@ -53,7 +53,10 @@ struct RowParams {
   // (value, derivative) of the local functions of the DOMINANT coefficient set of each dimension at the 1-D points,
   // [dim][q][a][2]: kernel parameters live in the constant bank, so these are free FP64 operands
   int cset[3];
-  double ctab[3][B2_MAX_DEGREE][B2_MAX_DEGREE][2];
+  double ctab[3][B2_MAX_DEGREE + 1][B2_MAX_DEGREE + 1][2];
+  // products of the dimension-2 factors of the dominant set, [q][a][b][va vb, va db, da vb, da db]: S1 multiplies the
+  // coefficient straight into the accumulators (one DFMA with a constant-bank operand per term, no pre-scaling DMULs)
+  double cp2[3][3][3][4];  // degrees 1 and 2 only (larger tables fall out of the constant cache)
   double* valK;
   double* valM;
   double* rhs;
@@ -155,11 +158,40 @@ __device__ __forceinline__ void s1_item(const RowParams& prm, const double* __re
     for (int q2 = 0; q2 < NQ; q2++) {
       const double* g = sG + (e2l * NQ + q2) * LS + L;
       const double* tb = sTb2 + (e2l * NQ + q2) * NB * 2;
-      const double va = CONST ? prm.ctab[2][q2][a][0] : tb[a * 2], da = CONST ? prm.ctab[2][q2][a][1] : tb[a * 2 + 1];
-      double pa[9];
       // component of Ghat[k][l]: symmetric storage (00,01,02,11,12,22) or general k*3+l
       constexpr bool SYM = C::NG == 7;
       constexpr int I00 = 0, I01 = 1, I02 = 2, I10 = SYM ? 1 : 3, I11 = SYM ? 3 : 4, I12 = SYM ? 4 : 5, I20 = SYM ? 2 : 6, I21 = SYM ? 4 : 7, I22 = SYM ? 5 : 8;
+      if (CONST && P <= 2) {
+        // 1-D factor products from the constant bank: every term is one DFMA
+        double G00 = 0., G01 = 0., G11 = 0., G10 = 0., G02 = 0., G12 = 0., G20 = 0., G21 = 0., G22 = 0., Gw = 0.;
+        if (TA) { G00 = g[I00 * GS]; G01 = g[I01 * GS]; G11 = g[I11 * GS]; if (!SYM) G10 = g[I10 * GS]; }
+        if (TB) { G02 = g[I02 * GS]; G12 = g[I12 * GS]; }
+        if (TC) { G20 = SYM && TB ? G02 : g[I20 * GS]; G21 = SYM && TB ? G12 : g[I21 * GS]; G22 = g[I22 * GS]; }
+        if (TM) { Gw = g[(C::NG - 1) * GS]; l1 = fma(prm.ctab[2][q2][a][0], Gw, l1); }
+#pragma unroll
+        for (int b = 0; b <= P; b++) {
+          const double* cp = prm.cp2[q2][a][b];
+          const int d = b + k;
+          if (TA) {
+            t[d][0] = fma(G00, cp[0], t[d][0]);
+            t[d][1] = fma(G01, cp[0], t[d][1]);
+            t[d][2] = fma(G11, cp[0], t[d][2]);
+            if (!SYM) t[d][8] = fma(G10, cp[0], t[d][8]);   // A10 takes the slot of the mass term (general forms carry no mass)
+          }
+          if (TB) {
+            t[d][3] = fma(G02, cp[1], t[d][3]);
+            t[d][4] = fma(G12, cp[1], t[d][4]);
+          }
+          if (TC) {
+            t[d][5] = fma(G20, cp[2], t[d][5]);
+            t[d][6] = fma(G21, cp[2], t[d][6]);
+            t[d][7] = fma(G22, cp[3], t[d][7]);
+          }
+          if (TM && FM) t[d][8] = fma(Gw, cp[0], t[d][8]);
+        }
+      } else {
+      const double va = CONST ? prm.ctab[2][q2][a][0] : tb[a * 2], da = CONST ? prm.ctab[2][q2][a][1] : tb[a * 2 + 1];
+      double pa[9];
       double pw = 0., p10 = 0.;
       if (TA) { pa[0] = va * g[I00 * GS]; pa[1] = va * g[I01 * GS]; pa[2] = va * g[I11 * GS]; if (!SYM) p10 = va * g[I10 * GS]; }
       if (TB) { pa[3] = va * g[I02 * GS]; pa[4] = va * g[I12 * GS]; }
@@ -173,7 +205,7 @@ __device__ __forceinline__ void s1_item(const RowParams& prm, const double* __re
           t[d][0] = fma(pa[0], vb, t[d][0]);
           t[d][1] = fma(pa[1], vb, t[d][1]);
           t[d][2] = fma(pa[2], vb, t[d][2]);
-          if (!SYM) t[d][8] = fma(p10, vb, t[d][8]);   // A10 takes the slot of the mass term (general forms carry no mass)
+          if (!SYM) t[d][8] = fma(p10, vb, t[d][8]);
         }
         if (TB) {
           t[d][3] = fma(pa[3], db, t[d][3]);
@@ -185,6 +217,7 @@ __device__ __forceinline__ void s1_item(const RowParams& prm, const double* __re
           t[d][7] = fma(pa[7], db, t[d][7]);
         }
         if (TM && FM) t[d][8] = fma(pw, vb, t[d][8]);
+      }
       }
     }
   }
@@ -275,6 +308,17 @@ __device__ __noinline__ void s2_item_tab(const RowParams& prm, const double* sT1
   s2_item<C, FK, FM, PART, NPARTS, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, want_f);
 }
 
+// 1/a for the normal, positive |det J| of a valid mesh: hardware seed (>= 20 bits) + two Newton steps (error < 2 ulp);
+// replaces the IEEE division sequence (slow-path checks included) at every quadrature point
+__device__ __forceinline__ double rcp_pos(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  double e = fma(-a, r, 1.);
+  r = fma(r, e, r);
+  e = fma(-a, r, 1.);
+  return fma(r, e, r);
+}
+
 // ---- G: geometry of one (Q1, Q2) column of the halo, the QC points q0 = qc.. of the current chunk ----
 // Trilinear map x = sum_v phi_v X_v of the element: the interpolations along dimensions 2 and 1 are shared by the points of the
 // column (J[:,0] does not depend on xi0; J[:,1], J[:,2] are linear in xi0); adj(J), det and Ghat = w/|det| adj K adj^T per point.
@@ -324,7 +368,7 @@ __device__ __forceinline__ void g_column(const RowParams& prm, int form, const d
   for (int q0 = 0; q0 < QC; q0++) {
     const double det = J0[0] * A0[q0][0] + J0[1] * A0[q0][1] + J0[2] * A0[q0][2];
     const double adet = fabs(det), w = sWt[qc + q0] * w12;
-    sc[q0] = w / adet;
+    sc[q0] = w * rcp_pos(adet);
     wd[q0] = w * adet;
   }
   // pass 2: the other two adjugate rows A[1] = J[:,2] x J[:,0], A[2] = J[:,0] x J[:,1] and Ghat = s A K A^T
@@ -839,7 +883,7 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
                          const double* const* D_host, const double* const* C_host, long long plane_begin, long long plane_end) {
   if (B.ndims != 3 || (B.ncomp != 1 && B.ncomp != 3)) return B2_EUNSUPPORTED;
   const int P = B.p[0];
-  if (B.p[1] != P || B.p[2] != P || P < 1 || P > 3) return B2_EUNSUPPORTED;
+  if (B.p[1] != P || B.p[2] != P || P < 1 || P > 4) return B2_EUNSUPPORTED;
   for (int d = 0; d < 3; d++) {
     if (Q.nq[d] != P + 1) return B2_EUNSUPPORTED;
     // maximal smoothness: element e carries dofs e..e+P
@@ -874,6 +918,15 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
         prm.ctab[d][q][a][1] = g;
       }
   }
+  for (int q = 0; q <= P && P <= 2; q++)
+    for (int a = 0; a <= P; a++)
+      for (int b = 0; b <= P; b++) {
+        const double va = prm.ctab[2][q][a][0], da = prm.ctab[2][q][a][1], vb = prm.ctab[2][q][b][0], db = prm.ctab[2][q][b][1];
+        prm.cp2[q][a][b][0] = va * vb;
+        prm.cp2[q][a][b][1] = va * db;
+        prm.cp2[q][a][b][2] = da * vb;
+        prm.cp2[q][a][b][3] = da * db;
+      }
   if (B.ncomp == 3) return launch_rows_vector(ctx, prm, F, D_host, C_host, P);
   bool fk = false, fm = false;
   for (int m = 0; m < F.nmat; m++) {
@@ -914,6 +967,20 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
   const int64_t variant = ctx->opts.count("rows_variant") ? ctx->opts["rows_variant"] : 0;
   (void)variant;
   if (P == 1) return launch_rows_forms<RCfg<1, 8, 8, 2, 256, false>>(ctx, prm, fk, fm);
+  if (P == 4) {
+    // degree 4 (the high-order IGA case): 2 x 2 dof columns per CTA, one point-plane per pipeline step, S1/S2 items split
+    // in term groups; K and M in separate launches (25 accumulators per dof pair and form, two dof pairs per thread)
+    using C4 = RCfg<4, 2, 2, 1, 256, true>;
+    if (!(fk && fm)) return launch_rows_forms<C4>(ctx, prm, fk, fm);
+    RowParams pk = prm;
+    pk.valM = nullptr;
+    int rc = launch_rows_cfg<C4, true, false>(ctx, pk);
+    if (rc != B2_OK) return rc;
+    RowParams pm = prm;
+    pm.valK = nullptr;
+    pm.has_f = 0;
+    return launch_rows_cfg<C4, false, true>(ctx, pm);
+  }
   if (P == 3) {
     // two chunks of two point-planes per layer; K and M in separate launches: 2 x 16 accumulators per dof pair and form
     // for two dof pairs per thread would not fit the register file together
