@@ -819,7 +819,7 @@ int launch_rows_forms(b2_ctx* ctx, RowParams& prm, bool fk, bool fm) {
 // forms (D[c][0][e][0]) run the scalar mass chain once and store rho[c][e] M; the load vector rides along.
 int launch_rows_vector(b2_ctx* ctx, RowParams& base, const FormView& F, const double* const* D_host, const double* const* C_host, int P) {
   constexpr int nc = 3, na = 4;
-  if (P != 1 && P != 2) return B2_EUNSUPPORTED;
+  if (P < 1 || P > 4) return B2_EUNSUPPORTED;
   if (F.nvec > 1 || (F.nmat == 0 && F.nvec == 0)) return B2_EUNSUPPORTED;
   int kind[B2_MAX_FORMS];  // 0 stiffness-like, 1 mass-like
   for (int m = 0; m < F.nmat; m++) {
@@ -859,7 +859,20 @@ int launch_rows_vector(b2_ctx* ctx, RowParams& base, const FormView& F, const do
           for (int x = 0; x < 3; x++)
             for (int y = 0; y < 3; y++) prm.dm[e][x * 3 + y] = D_host[m][((c * na + 1 + x) * nc + e) * na + 1 + y];
         prm.valK = F.values[m];
-        rc = P == 1 ? launch_rows_cfg<RCfg<1, 8, 8, 2, 256, false, 10>, true, false, 3, true>(ctx, prm) : launch_rows_cfg<RCfg<2, 4, 4, 3, 256, false, 10>, true, false, 3, true>(ctx, prm);
+        if (P <= 2) {
+          rc = P == 1 ? launch_rows_cfg<RCfg<1, 8, 8, 2, 256, false, 10>, true, false, 3, true>(ctx, prm) : launch_rows_cfg<RCfg<2, 4, 4, 3, 256, false, 10>, true, false, 3, true>(ctx, prm);
+        } else {
+          // degrees 3 and 4: the accumulators of three column components do not fit the register file together --
+          // one launch per column component e, writing the slots (J, e) of the rows (I, crow)
+          rc = B2_OK;
+          for (int e = 0; e < nc && rc == B2_OK; e++) {
+            RowParams pe = prm;
+            for (int t = 0; t < 9; t++) pe.dm[0][t] = prm.dm[e][t];
+            pe.valK = F.values[m] + e;
+            if (e) pe.has_f = 0;
+            rc = P == 3 ? launch_rows_cfg<RCfg<3, 3, 3, 2, 256, true, 10>, true, false, 1, true>(ctx, pe) : launch_rows_cfg<RCfg<4, 2, 2, 1, 256, true, 10>, true, false, 1, true>(ctx, pe);
+          }
+        }
       } else {
         // mass-like form, or the load vector alone (mass chain without a matrix)
         prm.valM = nullptr;
@@ -867,7 +880,10 @@ int launch_rows_vector(b2_ctx* ctx, RowParams& base, const FormView& F, const do
           for (int e = 0; e < nc; e++) prm.rhoe[e] = D_host[m][((c * na) * nc + e) * na];
           prm.valM = F.values[m];
         }
-        rc = P == 1 ? launch_rows_cfg<RCfg<1, 8, 8, 2, 256, false>, false, true, 1, true>(ctx, prm) : launch_rows_cfg<RCfg<2, 4, 4, 3, 256, false>, false, true, 1, true>(ctx, prm);
+        rc = P == 1   ? launch_rows_cfg<RCfg<1, 8, 8, 2, 256, false>, false, true, 1, true>(ctx, prm)
+             : P == 2 ? launch_rows_cfg<RCfg<2, 4, 4, 3, 256, false>, false, true, 1, true>(ctx, prm)
+             : P == 3 ? launch_rows_cfg<RCfg<3, 3, 3, 2, 256, true>, false, true, 1, true>(ctx, prm)
+                      : launch_rows_cfg<RCfg<4, 2, 2, 1, 256, true>, false, true, 1, true>(ctx, prm);
       }
       if (rc != B2_OK) return rc;
     }

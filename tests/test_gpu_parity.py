@@ -86,7 +86,7 @@ CASES = [
     dict(nelems=(6, 5, 4), degree=2, btype='std'), dict(nelems=(6, 5, 4), degree=2, qdegree=6),
     dict(nelems=(9, 7), degree=2, ncomp=2), dict(nelems=(5, 4, 5), degree=2, ncomp=3), dict(nelems=(4, 3, 3), degree=3, ncomp=3),
     dict(nelems=(1, 1, 1), degree=2), dict(nelems=(3, 13, 18), degree=2), dict(nelems=(7, 11, 5), degree=1), dict(nelems=(1, 2, 9), degree=2), dict(nelems=(7, 9, 8), degree=3), dict(nelems=(2, 1, 3), degree=3),
-    dict(nelems=(6, 5, 7), degree=4), dict(nelems=(1, 1, 1), degree=4), dict(nelems=(2, 7, 1), degree=4),
+    dict(nelems=(6, 5, 7), degree=4), dict(nelems=(1, 1, 1), degree=4), dict(nelems=(2, 7, 1), degree=4), dict(nelems=(3, 2, 3), degree=4, ncomp=3),
 ]
 
 
@@ -140,6 +140,7 @@ ROWS_CASES = [
     dict(nelems=(6, 7, 5), degree=2, ncomp=3, vector_forms=True), dict(nelems=(9, 4, 9), degree=1, ncomp=3, vector_forms=True),
     dict(nelems=(1, 1, 1), degree=2, ncomp=3, vector_forms=True), dict(nelems=(3, 3, 2), degree=3, ncomp=3, vector_forms=True),
     dict(nelems=(5, 6, 4), degree=4), dict(nelems=(1, 1, 1), degree=4), dict(nelems=(9, 3, 5), degree=4),
+    dict(nelems=(4, 3, 3), degree=4, ncomp=3, vector_forms=True), dict(nelems=(7, 4, 5), degree=3, ncomp=3, vector_forms=True),
 ]
 
 
