@@ -36,6 +36,7 @@ extern "C" {
 #define B2_ECUDA -3       /* CUDA runtime error (see b2_last_error) */
 #define B2_ENODEV -4      /* no usable sm_100 device */
 #define B2_EUNSUPPORTED -5 /* valid request outside the implemented path */
+#define B2_ENOTCONVERGED -6 /* iterative solve stopped above the requested tolerance (cf. nutils.matrix.ToleranceNotReached) */
 
 #define B2_MAX_DIMS 3
 #define B2_MAX_DEGREE 4
@@ -219,6 +220,24 @@ int b2_assemble_elemset_device(b2_ctx* ctx, const b2_pattern* pattern, const b2_
 int b2_assemble_elemset_host(b2_ctx* ctx, const b2_pattern* pattern, const b2_elemset* elemset, const b2_quad* quad, const b2_geom* geom,
                              int nmat, const double* const* D_host, double* const* values_host,
                              int nvec, const double* const* C_host, double* const* rhs_host);
+
+/* ---- device-resident matrix operations -------------------------------------------------------------
+ * The assembled values stay in HBM (a 128^3 p=2 matrix is 2.1 GB: copying it to the host costs 10x the assembly);
+ * these entry points are what nutils.matrix.Matrix offers on the result (src/nutils/matrix/_base.py), for BOTH kinds
+ * of pattern, without ever materialising colidx for the analytic one:
+ *   b2_spmv_device      y = A x                      Matrix.__matmul__            (_base.py:62-75)
+ *   b2_diagonal_device  diag(A)                      Matrix.diagonal              (_base.py:86-90)
+ *   b2_cg_device        Jacobi-preconditioned CG     Matrix.solve(rhs, lhs0=..., constrain=..., solver='cg', precon='diag',
+ *                       atol=..., rtol=...)          (_base.py:100-173, 199-213; used by solver.System.solve, solver.py:318-425)
+ * b2_cg_device: x_dev holds lhs0 on entry -- INCLUDING the values of the constrained dofs -- and the solution on return;
+ * constrained_dev (uint8[nrows], may be NULL) marks constrained dofs (rows and columns), rhs_dev may be NULL (zero).
+ * Solves A_ff dx = (b - A lhs0)_f and stops when |r| <= max(atol, rtol |(b - A lhs0)_f|); atol = rtol = 0 means "to
+ * machine precision" (1e-13 relative) like the reference.  maxiter 0 = automatic.  Returns B2_ENOTCONVERGED (x holds the
+ * best iterate, the reference's ToleranceNotReached.best) if an explicit tolerance was not reached. */
+int b2_spmv_device(b2_ctx* ctx, const b2_pattern* pattern, const double* values_dev, const double* x_dev, double* y_dev);
+int b2_diagonal_device(b2_ctx* ctx, const b2_pattern* pattern, const double* values_dev, double* diag_dev);
+int b2_cg_device(b2_ctx* ctx, const b2_pattern* pattern, const double* values_dev, const double* rhs_dev, double* x_dev,
+                 const unsigned char* constrained_dev, double atol, double rtol, int maxiter, int* iterations, double* resnorm);
 
 /* Experiments and profiling.  "kernel": 0 = automatic, 1 = generic (coverage) kernel only, 2 = specialised kernel or
  * B2_EUNSUPPORTED.  "path": 0 = b2_assemble_host uses the owner-computes rows path for the whole topology, 1 = always

@@ -19,6 +19,14 @@ class B200Error(Exception):
     'error reported by libb200fem (the MatrixError of this backend)'
 
 
+class ToleranceNotReached(B200Error):
+    'iterative solve stopped above the requested tolerance; ``best`` holds the last iterate (nutils.matrix.ToleranceNotReached)'
+
+    def __init__(self, msg, best=None):
+        super().__init__(msg)
+        self.best = best
+
+
 class BackendNotAvailable(B200Error):
     'libb200fem.so or a usable sm_100 device is missing (cf. nutils.matrix.BackendNotAvailable)'
 
@@ -82,6 +90,9 @@ SIGNATURES = {
     'b2_pattern_create_elemset': (ctypes.c_int, [c_vp, c_vp, p_vp]),
     'b2_assemble_elemset_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
     'b2_assemble_elemset_host': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
+    'b2_spmv_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'b2_diagonal_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    'b2_cg_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)]),
     'b2_assemble_host': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
 }
 
@@ -117,6 +128,8 @@ def check(status, ctx=None):
             msg = '{}: {}'.format(msg, detail)
     if status == -4:
         raise BackendNotAvailable(msg)
+    if status == -6:
+        raise ToleranceNotReached(msg)
     raise B200Error(msg)
 
 

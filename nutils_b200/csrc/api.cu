@@ -19,6 +19,7 @@ extern "C" const char* b2_strerror(int code) {
     case B2_ECUDA: return "CUDA runtime error";
     case B2_ENODEV: return "no usable CUDA device";
     case B2_EUNSUPPORTED: return "unsupported configuration";
+    case B2_ENOTCONVERGED: return "tolerance not reached";
     default: return "unknown error";
   }
 }

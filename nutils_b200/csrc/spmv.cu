@@ -1,0 +1,375 @@
+// Device-resident matrix operations on the assembled CSR values: y = A x, diag(A), and a Jacobi-preconditioned
+// conjugate-gradient solve with constraints -- so that a matrix assembled in HBM never has to cross PCIe.
+//
+// What it replaces in the reference: nutils.matrix.Matrix.__matmul__ / diagonal / solve with
+// constrain + lhs0 (src/nutils/matrix/_base.py:62-75, 100-173: "solve A dx = b - A lhs0 on the free dofs", tolerance
+// |A x - b| <= max(atol, rtol |b_reduced|)), as used by solver.System.solve (solver.py:318-425) right after assembly.
+//
+// The structured pattern is ANALYTIC: the SpMV kernel never reads a column index.  One warp owns the rows of one
+// basis function; lanes stride over the row's box of coupled dofs (decoded with multiply-shift divisions by the box
+// widths), values are streamed with evict-first loads (read once: 8 B per stored entry is the algorithmic traffic and
+// the HBM bound), x is gathered through L2.  Element-set patterns use their materialised basis-level column list.
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-level sum of one double per thread into *target (one atomic per block)
+__device__ __forceinline__ void block_accumulate(double v, double* target) {
+  __shared__ double sh[32];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < nw ? sh[lane] : 0.;
+    v = warp_sum(v);
+    if (lane == 0 && v != 0.) atomicAdd(target, v);
+  }
+}
+
+struct RowBox {
+  long long base;   // first slot of dof row (I, 0)
+  int lo[3], wid[3], w;
+  unsigned m1, m2;  // multiply-shift reciprocals of wid[1], wid[2]: n / d == (n * m) >> 20 for n < 8192, d <= 9
+};
+
+template <int DIM>
+__device__ __forceinline__ RowBox row_box(const BasisView& B, long long I, int* idx) {
+  RowBox r;
+  int i[3] = {0, 0, 0};
+  for (int d = DIM - 1; d >= 0; d--) {
+    i[d] = (int)(I % B.ndofs[d]);
+    I /= B.ndofs[d];
+  }
+  for (int d = 0; d < 3; d++) {
+    r.lo[d] = d < DIM ? B.lo[d][i[d]] : 0;
+    r.wid[d] = d < DIM ? B.wid[d][i[d]] : 1;
+    idx[d] = i[d];
+  }
+  r.w = r.wid[0] * r.wid[1] * r.wid[2];
+  r.base = row_start_basis<DIM>(B, i) * B.ncomp * B.ncomp;
+  r.m1 = ((1u << 20) + r.wid[1] - 1) / max(r.wid[1], 1);
+  r.m2 = ((1u << 20) + r.wid[2] - 1) / max(r.wid[2], 1);
+  return r;
+}
+
+// column (basis index) of position pos in the row's box, C order
+template <int DIM>
+__device__ __forceinline__ long long box_column(const BasisView& B, const RowBox& r, int pos) {
+  if (DIM == 1) return r.lo[0] + pos;
+  if (DIM == 2) {
+    const int q = (int)(((unsigned)pos * r.m1) >> 20);
+    return (long long)(r.lo[0] + q) * B.ndofs[1] + r.lo[1] + (pos - q * r.wid[1]);
+  }
+  const int q2 = (int)(((unsigned)pos * r.m2) >> 20), j2 = pos - q2 * r.wid[2];
+  const int q1 = (int)(((unsigned)q2 * r.m1) >> 20), j1 = q2 - q1 * r.wid[1];
+  return ((long long)(r.lo[0] + q1) * B.ndofs[1] + r.lo[1] + j1) * B.ndofs[2] + r.lo[2] + j2;
+}
+
+// y = A x.  mask (optional): rows with mask != 0 are constrained: y = 0 there (the caller keeps x = 0 on constrained
+// columns, so the product is the one of the free-free submatrix).  dot (optional): *dot += x . y.
+template <int DIM>
+__global__ void __launch_bounds__(256) k_spmv(const BasisView B, const long long nbasis, const double* __restrict__ values, const double* __restrict__ x,
+                                               double* __restrict__ y, const unsigned char* __restrict__ mask, double* dot) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nc = B.ncomp;
+  double local = 0.;
+  for (long long I = warp0; I < nbasis; I += nwarps) {
+    int idx[3];
+    const RowBox r = row_box<DIM>(B, I, idx);
+    const int rowlen = r.w * nc;
+    for (int c = 0; c < nc; c++) {
+      const long long row = I * nc + c;
+      if (mask && mask[row]) {
+        if (lane == 0) y[row] = 0.;
+        continue;
+      }
+      const double* v = values + r.base + (long long)c * rowlen;
+      double s = 0.;
+      if (nc == 1) {
+        for (int k = lane; k < rowlen; k += 32) s = fma(ld_stream(v + k), x[box_column<DIM>(B, r, k)], s);
+      } else {
+        for (int k = lane; k < rowlen; k += 32) {
+          const int pos = k / nc, e = k - pos * nc;
+          s = fma(ld_stream(v + k), x[box_column<DIM>(B, r, pos) * nc + e], s);
+        }
+      }
+      s = warp_sum(s);
+      if (lane == 0) {
+        y[row] = s;
+        if (dot) local = fma(x[row], s, local);
+      }
+    }
+  }
+  if (dot) block_accumulate(local, dot);
+}
+
+// the same on the materialised basis-level pattern of an element set
+__global__ void __launch_bounds__(256) k_spmv_general(const long long* __restrict__ rowptr_b, const int* __restrict__ colidx_b, const long long nbasis, const int nc,
+                                                       const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y,
+                                                       const unsigned char* __restrict__ mask, double* dot) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  double local = 0.;
+  for (long long I = warp0; I < nbasis; I += nwarps) {
+    const long long r0 = rowptr_b[I];
+    const int len = (int)(rowptr_b[I + 1] - r0), rowlen = len * nc;
+    for (int c = 0; c < nc; c++) {
+      const long long row = I * nc + c;
+      if (mask && mask[row]) {
+        if (lane == 0) y[row] = 0.;
+        continue;
+      }
+      const double* v = values + (r0 * nc + (long long)c * len) * nc;
+      double s = 0.;
+      for (int k = lane; k < rowlen; k += 32) {
+        const int pos = k / nc, e = k - pos * nc;
+        s = fma(ld_stream(v + k), x[(long long)colidx_b[r0 + pos] * nc + e], s);
+      }
+      s = warp_sum(s);
+      if (lane == 0) {
+        y[row] = s;
+        if (dot) local = fma(x[row], s, local);
+      }
+    }
+  }
+  if (dot) block_accumulate(local, dot);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_diagonal(const BasisView B, const long long nbasis, const double* __restrict__ values, double* __restrict__ diag) {
+  const int nc = B.ncomp;
+  for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < nbasis * nc; row += (long long)gridDim.x * blockDim.x) {
+    const long long I = row / nc;
+    const int c = (int)(row - I * nc);
+    int idx[3];
+    const RowBox r = row_box<DIM>(B, I, idx);
+    const int pos = ((idx[0] - r.lo[0]) * r.wid[1] + (idx[1] - r.lo[1])) * r.wid[2] + (idx[2] - r.lo[2]);
+    diag[row] = r.w ? values[r.base + (long long)c * r.w * nc + (long long)pos * nc + c] : 0.;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_diagonal_general(const long long* __restrict__ rowptr_b, const int* __restrict__ colidx_b, const long long nbasis, const int nc,
+                                                           const double* __restrict__ values, double* __restrict__ diag) {
+  for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < nbasis * nc; row += (long long)gridDim.x * blockDim.x) {
+    const long long I = row / nc;
+    const int c = (int)(row - I * nc);
+    const long long r0 = rowptr_b[I];
+    const int len = (int)(rowptr_b[I + 1] - r0);
+    int lo = 0, hi = len;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (colidx_b[r0 + mid] < I) lo = mid + 1;
+      else hi = mid;
+    }
+    diag[row] = (lo < len && colidx_b[r0 + lo] == I) ? values[(r0 * nc + (long long)c * len) * nc + (long long)lo * nc + c] : 0.;
+  }
+}
+
+// ---- conjugate gradients: device scalars, no host round trip inside an iteration ----
+// S[0] rz_old  S[1] rz_new  S[2] p.q  S[3] r.r (current)  S[4] r.r (last completed iteration)
+struct CgVec {
+  double *x, *r, *p, *q, *dinv;
+  const unsigned char* mask;
+  long long n;
+};
+
+// r = (b - q) on free rows, 0 on constrained; dinv = 1 / diag (1 where the diagonal vanishes); p = dinv r; S[0] = r.p; S[4] = r.r
+__global__ void __launch_bounds__(256) k_cg_init(const CgVec V, const double* __restrict__ b, const double* diag, double* S) {
+  double rz = 0., rr = 0.;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < V.n; i += (long long)gridDim.x * blockDim.x) {
+    const bool fixed = V.mask && V.mask[i];
+    const double r = fixed ? 0. : (b ? b[i] : 0.) - V.q[i];
+    const double d = diag[i], di = d != 0. ? 1. / d : 1.;
+    V.r[i] = r;
+    V.dinv[i] = di;
+    V.p[i] = di * r;
+    rz = fma(r * di, r, rz);
+    rr = fma(r, r, rr);
+  }
+  block_accumulate(rz, S + 0);
+  __syncthreads();
+  block_accumulate(rr, S + 4);
+}
+
+// alpha = rz_old / p.q;  x += alpha p;  r -= alpha q;  rz_new += r.dinv.r;  rr += r.r
+__global__ void __launch_bounds__(256) k_cg_update1(const CgVec V, double* S) {
+  const double pq = S[2], alpha = pq != 0. ? S[0] / pq : 0.;
+  double rz = 0., rr = 0.;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < V.n; i += (long long)gridDim.x * blockDim.x) {
+    V.x[i] = fma(alpha, V.p[i], V.x[i]);
+    const double r = fma(-alpha, V.q[i], V.r[i]);
+    V.r[i] = r;
+    rz = fma(r * V.dinv[i], r, rz);
+    rr = fma(r, r, rr);
+  }
+  block_accumulate(rz, S + 1);
+  __syncthreads();
+  block_accumulate(rr, S + 3);
+}
+
+// beta = rz_new / rz_old;  p = dinv r + beta p
+__global__ void __launch_bounds__(256) k_cg_update2(const CgVec V, const double* S) {
+  const double beta = S[0] != 0. ? S[1] / S[0] : 0.;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < V.n; i += (long long)gridDim.x * blockDim.x)
+    V.p[i] = fma(beta, V.p[i], V.dinv[i] * V.r[i]);
+}
+
+__global__ void k_cg_rotate(double* S) {
+  S[0] = S[1];
+  S[1] = 0.;
+  S[2] = 0.;
+  S[4] = S[3];
+  S[3] = 0.;
+}
+
+int grid_for(b2_ctx* ctx, long long work_items, int per_block) {
+  const long long want = (work_items + per_block - 1) / per_block;
+  return (int)std::min<long long>(std::max<long long>(want, 1), (long long)ctx->sm_count * 16);
+}
+
+int spmv_launch(b2_ctx* ctx, const b2_pattern* p, const double* values, const double* x, double* y, const unsigned char* mask, double* dot) {
+  const b2_basis* basis = p->basis;
+  const int nc = basis->ncomp;
+  const long long nbasis = p->nrows / nc;
+  const int blocks = grid_for(ctx, nbasis, 8);  // 8 warps per block, one basis row per warp and step
+  {
+    KernelTimer timer(ctx);
+    if (p->elemset) {
+      k_spmv_general<<<blocks, 256, 0, ctx->stream>>>(p->d_rowptr_b, p->d_colidx_b, nbasis, nc, values, x, y, mask, dot);
+    } else {
+      const BasisView B = basis->view();
+      switch (basis->ndims) {
+        case 1: k_spmv<1><<<blocks, 256, 0, ctx->stream>>>(B, nbasis, values, x, y, mask, dot); break;
+        case 2: k_spmv<2><<<blocks, 256, 0, ctx->stream>>>(B, nbasis, values, x, y, mask, dot); break;
+        default: k_spmv<3><<<blocks, 256, 0, ctx->stream>>>(B, nbasis, values, x, y, mask, dot); break;
+      }
+    }
+  }
+  ctx->launches++;
+  B2_CUDA(ctx, cudaGetLastError());
+  return B2_OK;
+}
+
+int diagonal_launch(b2_ctx* ctx, const b2_pattern* p, const double* values, double* diag) {
+  const b2_basis* basis = p->basis;
+  const int nc = basis->ncomp;
+  const long long nbasis = p->nrows / nc;
+  const int blocks = grid_for(ctx, p->nrows, 256);
+  if (p->elemset) {
+    k_diagonal_general<<<blocks, 256, 0, ctx->stream>>>(p->d_rowptr_b, p->d_colidx_b, nbasis, nc, values, diag);
+  } else {
+    const BasisView B = basis->view();
+    switch (basis->ndims) {
+      case 1: k_diagonal<1><<<blocks, 256, 0, ctx->stream>>>(B, nbasis, values, diag); break;
+      case 2: k_diagonal<2><<<blocks, 256, 0, ctx->stream>>>(B, nbasis, values, diag); break;
+      default: k_diagonal<3><<<blocks, 256, 0, ctx->stream>>>(B, nbasis, values, diag); break;
+    }
+  }
+  ctx->launches++;
+  B2_CUDA(ctx, cudaGetLastError());
+  return B2_OK;
+}
+
+}  // namespace
+
+extern "C" int b2_spmv_device(b2_ctx* ctx, const b2_pattern* pattern, const double* values_dev, const double* x_dev, double* y_dev) {
+  if (!ctx || !pattern || !values_dev || !x_dev || !y_dev) return b2_fail(ctx, B2_EINVAL, "null argument");
+  if (x_dev == y_dev) return b2_fail(ctx, B2_EINVAL, "x and y must not alias");
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
+  return spmv_launch(ctx, pattern, values_dev, x_dev, y_dev, nullptr, nullptr);
+}
+
+extern "C" int b2_diagonal_device(b2_ctx* ctx, const b2_pattern* pattern, const double* values_dev, double* diag_dev) {
+  if (!ctx || !pattern || !values_dev || !diag_dev) return b2_fail(ctx, B2_EINVAL, "null argument");
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
+  return diagonal_launch(ctx, pattern, values_dev, diag_dev);
+}
+
+extern "C" int b2_cg_device(b2_ctx* ctx, const b2_pattern* pattern, const double* values_dev, const double* rhs_dev, double* x_dev,
+                            const unsigned char* constrained_dev, double atol, double rtol, int maxiter, int* iterations, double* resnorm) {
+  if (!ctx || !pattern || !values_dev || !x_dev) return b2_fail(ctx, B2_EINVAL, "null argument");
+  if (atol < 0. || rtol < 0. || maxiter < 0) return b2_fail(ctx, B2_EINVAL, "negative tolerance or iteration count");
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long long n = pattern->nrows;
+  if (iterations) *iterations = 0;
+  if (resnorm) *resnorm = 0.;
+  if (n == 0) return B2_OK;
+  double* work = nullptr;
+  B2_CUDA(ctx, cudaMalloc((void**)&work, sizeof(double) * (size_t)(4 * n + 8)));
+  CgVec V;
+  V.x = x_dev;
+  V.r = work;
+  V.p = work + n;
+  V.q = work + 2 * n;
+  V.dinv = work + 3 * n;
+  V.mask = constrained_dev;
+  V.n = n;
+  double* S = work + 4 * n;
+  const int vblocks = grid_for(ctx, n, 256 * 4);
+  int rc = B2_OK, it = 0;
+  double rr = 0., target = 0.;
+  bool explicit_tol = atol > 0. || rtol > 0.;
+  auto fail = [&](cudaError_t e, const char* what) { rc = b2_cuda_fail(ctx, e, what); };
+  do {
+    cudaError_t e = cudaMemsetAsync(S, 0, sizeof(double) * 8, ctx->stream);
+    if (e != cudaSuccess) { fail(e, "cudaMemsetAsync"); break; }
+    // q = A x0 with ALL columns (constrained values included), then r = b - q on the free rows
+    rc = spmv_launch(ctx, pattern, values_dev, x_dev, V.q, nullptr, nullptr);
+    if (rc != B2_OK) break;
+    rc = diagonal_launch(ctx, pattern, values_dev, V.dinv);  // dinv holds the diagonal until k_cg_init inverts it in place
+    if (rc != B2_OK) break;
+    k_cg_init<<<vblocks, 256, 0, ctx->stream>>>(V, rhs_dev, V.dinv, S);
+    ctx->launches++;
+    e = cudaMemcpyAsync(&rr, S + 4, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { fail(e, "cg init"); break; }
+    const double r0 = std::sqrt(rr);
+    // matrix/_base.py:199-206: tolerance max(atol, rtol |b_reduced|); both zero = "machine precision"
+    target = explicit_tol ? std::max(atol, rtol * r0) : 1e-13 * r0;
+    if (maxiter == 0) maxiter = (int)std::min<long long>(10 * n + 100, 100000);
+    const int check = 10;
+    while (std::sqrt(rr) > target && it < maxiter) {
+      for (int k = 0; k < check && it < maxiter; k++, it++) {
+        rc = spmv_launch(ctx, pattern, values_dev, V.p, V.q, constrained_dev, S + 2);
+        if (rc != B2_OK) break;
+        k_cg_update1<<<vblocks, 256, 0, ctx->stream>>>(V, S);
+        k_cg_update2<<<vblocks, 256, 0, ctx->stream>>>(V, S);
+        k_cg_rotate<<<1, 1, 0, ctx->stream>>>(S);
+        ctx->launches += 3;
+      }
+      if (rc != B2_OK) break;
+      e = cudaMemcpyAsync(&rr, S + 4, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) { fail(e, "cg iteration"); break; }
+      if (!(rr == rr)) { rc = b2_fail(ctx, B2_ENOTCONVERGED, "conjugate gradients broke down (matrix not positive definite on the free dofs?)"); break; }
+    }
+  } while (false);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(work);
+  if (iterations) *iterations = it;
+  if (resnorm) *resnorm = std::sqrt(rr);
+  if (rc != B2_OK) return rc;
+  if (explicit_tol && std::sqrt(rr) > target) return b2_fail(ctx, B2_ENOTCONVERGED, "tolerance not reached");
+  return B2_OK;
+}

@@ -205,6 +205,27 @@ class Plan:
             raise ValueError('row out of range')
         return off
 
+    # device-resident matrix operations (b2_spmv_device, b2_diagonal_device, b2_cg_device) ------------
+
+    def spmv_device(self, values, x, y):
+        'y = A x for device arrays (DeviceBuffer / torch tensor / pointer); asynchronous on the context stream'
+        self.ctx.check(self.ctx.lib.b2_spmv_device(self.ctx.handle, self.pattern, _devptr(values), _devptr(x), _devptr(y)))
+
+    def diagonal_device(self, values, diag):
+        self.ctx.check(self.ctx.lib.b2_diagonal_device(self.ctx.handle, self.pattern, _devptr(values), _devptr(diag)))
+
+    def cg_device(self, values, rhs, x, constrained=None, atol=0., rtol=0., maxiter=0):
+        '''Jacobi-preconditioned CG on the device: x holds lhs0 (constrained values included) on entry, the solution on return.
+        Returns (iterations, residual norm); raises ToleranceNotReached if an explicit tolerance is not met.'''
+        it = ctypes.c_int()
+        res = ctypes.c_double()
+        status = self.ctx.lib.b2_cg_device(self.ctx.handle, self.pattern, _devptr(values), None if rhs is None else _devptr(rhs), _devptr(x),
+                                           None if constrained is None else _devptr(constrained), float(atol), float(rtol), int(maxiter),
+                                           ctypes.byref(it), ctypes.byref(res))
+        self.last_cg = int(it.value), float(res.value)
+        self.ctx.check(status)
+        return self.last_cg
+
     def update_nodes(self, nodes):
         nodes = as_f64(nodes)
         assert nodes.shape == self.nodes.shape
@@ -362,6 +383,9 @@ class ElemSetPlan:
 
     csr_pattern = Plan.csr_pattern
     csr_pattern_device = Plan.csr_pattern_device
+    spmv_device = Plan.spmv_device
+    diagonal_device = Plan.diagonal_device
+    cg_device = Plan.cg_device
     row_offset = Plan.row_offset
     _form_args = Plan._form_args
 

@@ -58,6 +58,71 @@ class Matrix:
         return Matrix(A.data, A.indptr.astype(numpy.int64), A.indices.astype(numpy.int64), self.shape[0])
 
 
+class DeviceMatrix:
+    '''Matrix whose values stay in HBM: the device-resident counterpart of ``nutils.matrix.Matrix``
+    (matrix/_base.py:33-302) for what ``solver.System`` does with an assembled matrix -- products and constrained
+    solves (solver.py:318-425) -- so that a multi-GB result never crosses PCIe.  ``plan`` is the engine.Plan /
+    engine.ElemSetPlan that owns the pattern, ``values`` an engine.DeviceBuffer (or torch tensor) of nnz float64.'''
+
+    def __init__(self, plan, values):
+        self.plan = plan
+        self.values = values
+        self.shape = plan.ndofs, plan.ndofs
+
+    def _vec(self, host=None):
+        buf = self.plan.ctx.device_alloc(8 * self.shape[0])
+        if host is not None:
+            buf.from_host(numpy.ascontiguousarray(host, dtype=numpy.float64))
+        return buf
+
+    def __matmul__(self, other):
+        other = numpy.asarray(other, dtype=float)
+        if other.shape != (self.shape[1],):
+            raise MatrixError('shape mismatch')
+        x, y = self._vec(other), self._vec()
+        self.plan.spmv_device(self.values, x, y)
+        return y.to_host()
+
+    def diagonal(self):
+        d = self._vec()
+        self.plan.diagonal_device(self.values, d)
+        return d.to_host()
+
+    def solve(self, rhs=None, *, lhs0=None, constrain=None, solver='cg', atol=0., rtol=0., precon='diag', maxiter=0):
+        '''``Matrix.solve`` (matrix/_base.py:100-173) with the one solver this backend carries: Jacobi-preconditioned CG on the
+        device.  constrain: float array (NaN = free, number = constrained to that value) or bool array (True = constrained to
+        lhs0).  Raises ToleranceNotReached (with ``.best``) if an explicit atol/rtol is not reached.'''
+        from ._lib import ToleranceNotReached
+        if solver != 'cg' or precon != 'diag':
+            raise MatrixError('invalid solver {!r}/{!r} for DeviceMatrix'.format(solver, precon))
+        n = self.shape[0]
+        lhs = numpy.zeros(n) if lhs0 is None else numpy.array(lhs0, dtype=float)
+        mask = None
+        if constrain is not None:
+            constrain = numpy.asarray(constrain)
+            if constrain.shape != (n,):
+                raise MatrixError('constrain has the wrong shape')
+            if constrain.dtype == bool:
+                fixed = constrain
+            else:
+                fixed = ~numpy.isnan(constrain)
+                lhs[fixed] = constrain[fixed]
+            mask = self.plan.ctx.device_alloc(n)
+            mask.from_host(fixed.astype(numpy.uint8))
+        x = self._vec(lhs)
+        b = None if rhs is None else self._vec(rhs)
+        try:
+            self.plan.cg_device(self.values, b, x, constrained=mask, atol=atol, rtol=rtol, maxiter=maxiter)
+        except ToleranceNotReached as e:
+            raise ToleranceNotReached(str(e), best=x.to_host()) from None
+        return x.to_host()
+
+    def export(self, form):
+        values = self.values.to_host() if hasattr(self.values, 'to_host') else self.values.cpu().numpy()
+        rowptr, colidx = self.plan.csr_pattern()
+        return Matrix(values, rowptr, colidx, self.shape[1]).export(form)
+
+
 def assemble_csr(values, rowptr, colidx, ncols):
     'validate and wrap, with the checks of matrix/__init__.py:50-70'
     values = numpy.asarray(values)

@@ -40,6 +40,31 @@ class Sample:
         res = tuple(matrix.assemble_csr(*o, ncols=len(o[1]) - 1) if i.kind == 'matrix' else o for i, o in zip(integrals, outs))
         return res[0] if single else res
 
+    def integrate_device(self, funcs, arguments=None):
+        '''like integrate_sparse, but the values of 2-D integrands STAY in HBM: matrices come back as matrix.DeviceMatrix
+        (products and constrained CG solves on the device), vectors as numpy arrays.'''
+        from . import matrix
+        if arguments:
+            raise NotImplementedError('integrands with arguments are outside the accelerated path')
+        single = not isinstance(funcs, (tuple, list))
+        integrals = [self.integral(f) for f in ((funcs,) if single else funcs)]
+        res = [None] * len(integrals)
+        groups = {}
+        for k, integral in enumerate(integrals):
+            groups.setdefault((id(integral.func.space), id(integral.func.jac)), []).append(k)
+        for ks in groups.values():
+            plan = self.plan(integrals[ks[0]].func.space, integrals[ks[0]].func.jac)
+            mats = [k for k in ks if integrals[k].kind == 'matrix']
+            vecs = [k for k in ks if integrals[k].kind == 'vector']
+            vbufs = [plan.ctx.device_alloc(8 * plan.nnz) for _ in mats]
+            rbufs = [plan.ctx.device_alloc(8 * plan.ndofs) for _ in vecs]
+            plan.assemble_rows_device([integrals[k].tensor for k in mats], [integrals[k].tensor for k in vecs], vbufs, rbufs)
+            for k, buf in zip(mats, vbufs):
+                res[k] = matrix.DeviceMatrix(plan, buf)
+            for k, buf in zip(vecs, rbufs):
+                res[k] = buf.to_host()
+        return res[0] if single else tuple(res)
+
     # -- engine --------------------------------------------------------------------------------------
 
     def plan(self, space, geom):
