@@ -18,11 +18,8 @@
 
 namespace {
 
-__device__ __forceinline__ double ld_stream(const double* p) {
-  double v;
-  asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
+// evict-first load of a value that is read exactly once (keeps x resident in L2)
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -85,38 +82,298 @@ __device__ __forceinline__ long long box_column(const BasisView& B, const RowBox
 
 // y = A x.  mask (optional): rows with mask != 0 are constrained: y = 0 there (the caller keeps x = 0 on constrained
 // columns, so the product is the one of the free-free submatrix).  dot (optional): *dot += x . y.
+// all ncomp dof rows of basis function I, one warp (any pattern shape; the coverage path of the kernels below)
+template <int DIM>
+__device__ __noinline__ void spmv_basis_row(const BasisView& B, const long long I, const double* __restrict__ values, const double* __restrict__ x,
+                                            double* __restrict__ y, const unsigned char* __restrict__ mask, const bool want_dot, double& local) {
+  const int lane = threadIdx.x & 31;
+  const int nc = B.ncomp;
+  int idx[3];
+  const RowBox r = row_box<DIM>(B, I, idx);
+  const int rowlen = r.w * nc;
+  for (int c = 0; c < nc; c++) {
+    const long long row = I * nc + c;
+    if (mask && mask[row]) {
+      if (lane == 0) y[row] = 0.;
+      continue;
+    }
+    const double* v = values + r.base + (long long)c * rowlen;
+    double s = 0.;
+    for (int k0 = 0; k0 < rowlen; k0 += 128) {
+      double a[4], b[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int k = k0 + t * 32 + lane;
+        a[t] = k < rowlen ? ld_stream(v + k) : 0.;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int k = k0 + t * 32 + lane;
+        b[t] = 0.;
+        if (k < rowlen) {
+          if (nc == 1) b[t] = x[box_column<DIM>(B, r, k)];
+          else {
+            const int pos = k / nc, e = k - pos * nc;
+            b[t] = x[box_column<DIM>(B, r, pos) * nc + e];
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 4; t++) s = fma(a[t], b[t], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      y[row] = s;
+      if (want_dot) local = fma(x[row], s, local);
+    }
+  }
+}
+
+// y = A x.  mask (optional): rows with mask != 0 are constrained: y = 0 there (the caller keeps x = 0 on constrained
+// columns, so the product is the one of the free-free submatrix).  dot (optional): *dot += x . y.
 template <int DIM>
 __global__ void __launch_bounds__(256) k_spmv(const BasisView B, const long long nbasis, const double* __restrict__ values, const double* __restrict__ x,
                                                double* __restrict__ y, const unsigned char* __restrict__ mask, double* dot) {
-  const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int nc = B.ncomp;
   double local = 0.;
-  for (long long I = warp0; I < nbasis; I += nwarps) {
-    int idx[3];
-    const RowBox r = row_box<DIM>(B, I, idx);
-    const int rowlen = r.w * nc;
-    for (int c = 0; c < nc; c++) {
-      const long long row = I * nc + c;
-      if (mask && mask[row]) {
-        if (lane == 0) y[row] = 0.;
-        continue;
+  for (long long I = warp0; I < nbasis; I += nwarps) spmv_basis_row<DIM>(B, I, values, x, y, mask, dot != nullptr, local);
+  if (dot) block_accumulate(local, dot);
+}
+
+// Scalar spaces with rows of at most 128 entries (degree <= 2 in 3-D): RUNS of eight consecutive rows per warp.
+// The plain kernel is bound by instruction issue, not by memory (ncu: issue slots 75 % busy at 24 % of the DRAM bandwidth:
+// ~440 instructions per row for index decoding, slot arithmetic and a 5-step butterfly per row).  Eight consecutive rows
+// along the last dimension whose boxes are translates of each other (all interior rows) share everything but a shift:
+// values base += w, first column += 1 -- so per row a lane issues 4 streamed value loads + 4 gathers of x (L1) + 4 DFMA,
+// and the eight row sums are reduced TOGETHER by a transposing butterfly (9 shuffles for 8 rows instead of 40).  Runs that
+// touch the boundary of the box structure take the plain per-row code.
+template <int DIM>
+__global__ void __launch_bounds__(256, 3) k_spmv_run(const BasisView B, const int nbasis, const double* __restrict__ values, const double* __restrict__ x,
+                                                      double* __restrict__ y, const unsigned char* __restrict__ mask, double* dot) {
+  constexpr int LD = DIM - 1, R = 8;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nd1 = DIM > 1 ? B.ndofs[1] : 1, nd2 = DIM > 2 ? B.ndofs[2] : 1, ndl = B.ndofs[LD];
+  double local = 0.;
+  int sig = -1, coff[4] = {0, 0, 0, 0};
+  for (long long g = blockIdx.x; g * (8 * R) < nbasis; g += gridDim.x) {
+    const int I0 = (int)(g * (8 * R)) + warp * R;
+    if (I0 >= nbasis) continue;
+    int i[3] = {0, 0, 0};
+    {
+      unsigned r = (unsigned)I0;
+      if (DIM > 2) { i[2] = r % (unsigned)nd2; r /= (unsigned)nd2; }
+      if (DIM > 1) { i[1] = r % (unsigned)nd1; r /= (unsigned)nd1; }
+      i[0] = r;
+    }
+    // are the boxes of the eight rows translates of the first one along the last dimension?
+    bool run = I0 + R <= nbasis && i[LD] + R <= ndl;
+    if (run) {
+      const int rr = lane & (R - 1);
+      const int lo_l = B.lo[LD][i[LD] + rr], wid_l = B.wid[LD][i[LD] + rr];
+      const int lo_0 = __shfl_sync(FULL, lo_l, 0), wid_0 = __shfl_sync(FULL, wid_l, 0);
+      run = __all_sync(FULL, lo_l == lo_0 + rr && wid_l == wid_0 && wid_l > 0);
+    }
+    if (!run) {
+      const int nrows = min(R, nbasis - I0);
+      for (int r = 0; r < nrows; r++) spmv_basis_row<DIM>(B, I0 + r, values, x, y, mask, dot != nullptr, local);
+      continue;
+    }
+    int lo[3] = {0, 0, 0}, wid[3] = {1, 1, 1};
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      lo[d] = B.lo[d][i[d]];
+      wid[d] = B.wid[d][i[d]];
+    }
+    const int w = wid[0] * wid[1] * wid[2];
+    const int nsig = wid[0] | wid[1] << 8 | wid[2] << 16;
+    if (nsig != sig) {
+      sig = nsig;
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int k = min(t * 32 + lane, max(w - 1, 0));
+        const int j2 = k % wid[2], q = k / wid[2], j1 = q % wid[1], j0 = q / wid[1];
+        coff[t] = (j0 * nd1 + j1) * nd2 + j2;
       }
-      const double* v = values + r.base + (long long)c * rowlen;
-      double s = 0.;
-      if (nc == 1) {
-        for (int k = lane; k < rowlen; k += 32) s = fma(ld_stream(v + k), x[box_column<DIM>(B, r, k)], s);
-      } else {
-        for (int k = lane; k < rowlen; k += 32) {
+    }
+    if (w == 0) {  // functions without support: empty rows
+      if (lane < R) y[I0 + lane] = 0.;
+      continue;
+    }
+    const long long base = row_start_basis<DIM>(B, i);
+    const long long c0 = ((long long)lo[0] * nd1 + lo[1]) * nd2 + lo[2];
+    bool ok[4];
+    const double* pv[4];
+    const double* px[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      ok[t] = t * 32 + lane < w;
+      pv[t] = values + base + (ok[t] ? t * 32 + lane : w - 1);  // clamped into the row: loads need no predicate
+      px[t] = x + c0 + coff[t];
+    }
+    double s[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      double a0, a1, a2, a3, b0, b1, b2, b3;
+      asm volatile(
+          "ld.global.cs.f64 %0, [%8];\n\t"
+          "ld.global.cs.f64 %1, [%9];\n\t"
+          "ld.global.cs.f64 %2, [%10];\n\t"
+          "ld.global.cs.f64 %3, [%11];\n\t"
+          "ld.global.nc.f64 %4, [%12];\n\t"
+          "ld.global.nc.f64 %5, [%13];\n\t"
+          "ld.global.nc.f64 %6, [%14];\n\t"
+          "ld.global.nc.f64 %7, [%15];"
+          : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3), "=d"(b0), "=d"(b1), "=d"(b2), "=d"(b3)
+          : "l"(pv[0] + r * w), "l"(pv[1] + r * w), "l"(pv[2] + r * w), "l"(pv[3] + r * w), "l"(px[0] + r), "l"(px[1] + r), "l"(px[2] + r), "l"(px[3] + r));
+      double t = (ok[0] ? a0 : 0.) * b0;
+      t = fma(ok[1] ? a1 : 0., b1, t);
+      t = fma(ok[2] ? a2 : 0., b2, t);
+      s[r] = fma(ok[3] ? a3 : 0., b3, t);
+    }
+    // transposing butterfly: after the xor-16/8/4 steps a lane holds ONE row (row = lane >> 2), then two plain steps
+    double t4[4], t2[2], v;
+    {
+      const bool hi = lane & 16;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double send = hi ? s[j] : s[j + 4], keep = hi ? s[j + 4] : s[j];
+        t4[j] = keep + __shfl_xor_sync(FULL, send, 16);
+      }
+    }
+    {
+      const bool hi = lane & 8;
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const double send = hi ? t4[j] : t4[j + 2], keep = hi ? t4[j + 2] : t4[j];
+        t2[j] = keep + __shfl_xor_sync(FULL, send, 8);
+      }
+    }
+    {
+      const bool hi = lane & 4;
+      const double send = hi ? t2[0] : t2[1], keep = hi ? t2[1] : t2[0];
+      v = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+    v += __shfl_xor_sync(FULL, v, 2);
+    v += __shfl_xor_sync(FULL, v, 1);
+    if ((lane & 3) == 0) {
+      const int row = I0 + (lane >> 2);
+      const bool fixed = mask && mask[row];
+      y[row] = fixed ? 0. : v;
+      if (dot && !fixed) local = fma(x[row], v, local);
+    }
+  }
+  if (dot) block_accumulate(local, dot);
+}
+
+// Fast variant for rows of at most 32 NCH entries (scalar spaces up to degree 2 with NCH = 4, three components / degree 3
+// with NCH = 12).  The instruction count per entry is what bounds the plain kernel (ncu: issue slots 75 % busy at 24 % of
+// the DRAM bandwidth), so here (a) a warp walks rows I, I+8, I+16, ... and advances the dof multi-index incrementally (no
+// 64-bit divisions), and (b) the column OFFSETS of a lane's entries relative to the first coupled dof depend only on the
+// box widths (wid0, wid1, wid2), which are the same for all interior rows: they are kept in registers and recomputed only
+// when the widths change.  Per entry: one streamed load, one add, one gather, one DFMA.
+template <int DIM, int NCH>
+__global__ void __launch_bounds__(256, 3) k_spmv_fast(const BasisView B, const int nbasis, const int rows_per_warp, const double* __restrict__ values,
+                                                    const double* __restrict__ x, double* __restrict__ y, const unsigned char* __restrict__ mask, double* dot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nc = B.ncomp, nd1 = DIM > 1 ? B.ndofs[1] : 1, nd2 = DIM > 2 ? B.ndofs[2] : 1;
+  const int rb = 8 * rows_per_warp;
+  double local = 0.;
+  for (long long row0 = (long long)blockIdx.x * rb; row0 < nbasis; row0 += (long long)gridDim.x * rb) {
+    int I = (int)row0 + warp;
+    if (I >= nbasis) continue;
+    int i[3] = {0, 0, 0};
+    {
+      unsigned r = (unsigned)I;
+      if (DIM > 2) { i[2] = r % (unsigned)nd2; r /= (unsigned)nd2; }
+      if (DIM > 1) { i[1] = r % (unsigned)nd1; r /= (unsigned)nd1; }
+      i[0] = r;
+      if (DIM == 1) i[0] = I;
+    }
+    int sig = -1, coff[NCH];
+#pragma unroll
+    for (int t = 0; t < NCH; t++) coff[t] = 0;
+    for (int j = 0; j < rows_per_warp && I < nbasis; j++, I += 8) {
+      int lo[3] = {0, 0, 0}, wid[3] = {1, 1, 1};
+#pragma unroll
+      for (int d = 0; d < DIM; d++) {
+        lo[d] = B.lo[d][i[d]];
+        wid[d] = B.wid[d][i[d]];
+      }
+      const int w = wid[0] * wid[1] * wid[2], rowlen = w * nc;
+      const int nsig = wid[0] | wid[1] << 8 | wid[2] << 16;
+      if (nsig != sig) {
+        sig = nsig;
+#pragma unroll
+        for (int t = 0; t < NCH; t++) {
+          const int k = t * 32 + lane;
           const int pos = k / nc, e = k - pos * nc;
-          s = fma(ld_stream(v + k), x[box_column<DIM>(B, r, pos) * nc + e], s);
+          const int j2 = pos % wid[2], q = pos / wid[2], j1 = q % wid[1], j0 = q / wid[1];
+          coff[t] = ((j0 * nd1 + j1) * nd2 + j2) * nc + e;
         }
       }
-      s = warp_sum(s);
-      if (lane == 0) {
-        y[row] = s;
-        if (dot) local = fma(x[row], s, local);
+      const long long base = row_start_basis<DIM>(B, i) * nc * nc;
+      const long long c0 = (((long long)lo[0] * nd1 + lo[1]) * nd2 + lo[2]) * nc;
+      const double* xr = x + c0;
+      for (int c = 0; c < nc; c++) {
+        const long long row = (long long)I * nc + c;
+        if (mask && mask[row]) {
+          if (lane == 0) y[row] = 0.;
+          continue;
+        }
+        const double* v = values + base + (long long)c * rowlen;
+        double s = 0.;
+        if (rowlen > 0) {
+          // Addresses are clamped into the row instead of predicating the loads, and the eight loads of a group of four
+          // chunks sit in ONE asm block: they are issued back to back and are all in flight before the first product waits
+          // (ptxas otherwise serialises load pair -> DFMA -> load pair: four HBM round trips per row instead of one).
+#pragma unroll
+          for (int t0 = 0; t0 < NCH; t0 += 4) {
+            const double* pa[4];
+            const double* pb[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int k = (t0 + u) * 32 + lane;
+              ok[u] = k < rowlen;
+              pa[u] = v + (ok[u] ? k : rowlen - 1);
+              pb[u] = xr + (ok[u] ? coff[t0 + u] : 0);
+            }
+            double a0, a1, a2, a3, b0, b1, b2, b3;
+            asm volatile(
+                "ld.global.cs.f64 %0, [%8];\n\t"
+                "ld.global.cs.f64 %1, [%9];\n\t"
+                "ld.global.cs.f64 %2, [%10];\n\t"
+                "ld.global.cs.f64 %3, [%11];\n\t"
+                "ld.global.nc.f64 %4, [%12];\n\t"
+                "ld.global.nc.f64 %5, [%13];\n\t"
+                "ld.global.nc.f64 %6, [%14];\n\t"
+                "ld.global.nc.f64 %7, [%15];"
+                : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3), "=d"(b0), "=d"(b1), "=d"(b2), "=d"(b3)
+                : "l"(pa[0]), "l"(pa[1]), "l"(pa[2]), "l"(pa[3]), "l"(pb[0]), "l"(pb[1]), "l"(pb[2]), "l"(pb[3]));
+            s = fma(ok[0] ? a0 : 0., b0, s);
+            s = fma(ok[1] ? a1 : 0., b1, s);
+            s = fma(ok[2] ? a2 : 0., b2, s);
+            s = fma(ok[3] ? a3 : 0., b3, s);
+          }
+        }
+        s = warp_sum(s);
+        if (lane == 0) {
+          y[row] = s;
+          if (dot) local = fma(x[row], s, local);
+        }
+      }
+      // next row of this warp: I + 8
+      if (DIM == 1) i[0] += 8;
+      else {
+        i[DIM - 1] += 8;
+        if (DIM == 3) {
+          while (i[2] >= nd2) { i[2] -= nd2; i[1]++; }
+          while (i[1] >= nd1) { i[1] -= nd1; i[0]++; }
+        } else {
+          while (i[1] >= nd1) { i[1] -= nd1; i[0]++; }
+        }
       }
     }
   }
@@ -259,10 +516,35 @@ int spmv_launch(b2_ctx* ctx, const b2_pattern* p, const double* values, const do
       k_spmv_general<<<blocks, 256, 0, ctx->stream>>>(p->d_rowptr_b, p->d_colidx_b, nbasis, nc, values, x, y, mask, dot);
     } else {
       const BasisView B = basis->view();
-      switch (basis->ndims) {
-        case 1: k_spmv<1><<<blocks, 256, 0, ctx->stream>>>(B, nbasis, values, x, y, mask, dot); break;
-        case 2: k_spmv<2><<<blocks, 256, 0, ctx->stream>>>(B, nbasis, values, x, y, mask, dot); break;
-        default: k_spmv<3><<<blocks, 256, 0, ctx->stream>>>(B, nbasis, values, x, y, mask, dot); break;
+      int maxrow = nc;  // longest row: product of the largest box widths
+      for (int d = 0; d < basis->ndims; d++) maxrow *= *std::max_element(basis->wid[d].begin(), basis->wid[d].end());
+      const bool plain = ctx->opts.count("spmv_plain") && ctx->opts["spmv_plain"];
+      if (nc == 1 && maxrow <= 128 && !plain) {
+        const int rblocks = grid_for(ctx, nbasis, 64);
+        switch (basis->ndims) {
+          case 1: k_spmv_run<1><<<rblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, values, x, y, mask, dot); break;
+          case 2: k_spmv_run<2><<<rblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, values, x, y, mask, dot); break;
+          default: k_spmv_run<3><<<rblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, values, x, y, mask, dot); break;
+        }
+      } else if (maxrow <= 384 && !plain) {
+        const int rpw = 16, fblocks = grid_for(ctx, nbasis, 8 * rpw);
+        const bool small = maxrow <= 128;
+        switch (basis->ndims) {
+          case 1: k_spmv_fast<1, 4><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot); break;
+          case 2:
+            if (small) k_spmv_fast<2, 4><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot);
+            else k_spmv_fast<2, 12><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot);
+            break;
+          default:
+            if (small) k_spmv_fast<3, 4><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot);
+            else k_spmv_fast<3, 12><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot);
+        }
+      } else {
+        switch (basis->ndims) {
+          case 1: k_spmv<1><<<blocks, 256, 0, ctx->stream>>>(B, nbasis, values, x, y, mask, dot); break;
+          case 2: k_spmv<2><<<blocks, 256, 0, ctx->stream>>>(B, nbasis, values, x, y, mask, dot); break;
+          default: k_spmv<3><<<blocks, 256, 0, ctx->stream>>>(B, nbasis, values, x, y, mask, dot); break;
+        }
       }
     }
   }

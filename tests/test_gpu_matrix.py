@@ -21,8 +21,10 @@ def _poisson(n, degree, warp=.2, seed=0, ncomp=1):
     return topo, geom, basis
 
 
-@pytest.mark.parametrize('n,degree', [((9,), 2), ((7, 6), 3), ((6, 5, 7), 2), ((4, 3, 3), 4), ((5, 4, 6), 1)])
-def test_spmv_and_diagonal(n, degree):
+@pytest.mark.parametrize('plain', [0, 1], ids=['fast', 'plain'])
+@pytest.mark.parametrize('n,degree', [((9,), 2), ((7, 6), 3), ((6, 5, 7), 2), ((4, 3, 3), 4), ((5, 4, 6), 1), ((3, 2, 9), 3), ((1, 1, 1), 2), ((40, 3), 1), ((13, 9, 11), 2)])
+def test_spmv_and_diagonal(n, degree, plain):
+    engine.Context.get(0).set_option('spmv_plain', plain)
     topo, geom, basis = _poisson(n, degree)
     g = basis.grad(geom)
     smp = topo.sample('gauss', 2 * degree)
@@ -34,6 +36,7 @@ def test_spmv_and_diagonal(n, degree):
         ref = scipy.sparse.csr_matrix((data, indices, indptr), shape=A.shape)
         assert util.relerr(A @ x, ref @ x) <= 1e-13
         assert util.relerr(A.diagonal(), ref.diagonal()) <= 1e-15
+    engine.Context.get(0).set_option('spmv_plain', 0)
 
 
 def test_spmv_vector_valued():
