@@ -570,10 +570,30 @@ int b2_upload_forms(b2_ctx* ctx, int nd, int nc, int nmat, const double* const* 
   for (int v = 0; v < nvec; v++) {
     vcoef.insert(vcoef.end(), C_host[v], C_host[v] + nc * na);
   }
+  // dense 4x4 blocks per (m, c, e) for the tensor-core path
+  std::vector<double> jobD;
+  std::vector<int> jobinfo;
+  for (int m = 0; m < nmat; m++)
+    for (int c = 0; c < nc; c++)
+      for (int e = 0; e < nc; e++) {
+        double blk[16] = {0};
+        bool any = false, only00 = true;
+        for (int x = 0; x < na; x++)
+          for (int y = 0; y < na; y++) {
+            const double v = D_host[m][((c * na + x) * nc + e) * na + y];
+            blk[x * 4 + y] = v;
+            if (v != 0.) { any = true; if (x || y) only00 = false; }
+          }
+        if (!any) continue;
+        jobD.insert(jobD.end(), blk, blk + 16);
+        jobinfo.push_back(m | c << 8 | e << 16 | (only00 ? 1 : 0) << 24);
+      }
   const size_t b_ptr = termptr.size() * sizeof(int), b_xy = std::max<size_t>(termxy.size(), 1) * sizeof(int);
   const size_t b_val = std::max<size_t>(termval.size(), 1) * sizeof(double), b_vc = std::max<size_t>(vcoef.size(), 1) * sizeof(double);
-  const size_t off_val = 0, off_vc = off_val + b_val, off_ptr = off_vc + b_vc, off_xy = off_ptr + ((b_ptr + 7) & ~size_t(7));
-  const size_t total = off_xy + b_xy;
+  const size_t b_jd = std::max<size_t>(jobD.size(), 1) * sizeof(double), b_ji = std::max<size_t>(jobinfo.size(), 1) * sizeof(int);
+  const size_t off_val = 0, off_vc = off_val + b_val, off_jd = off_vc + b_vc, off_ptr = off_jd + b_jd, off_xy = off_ptr + ((b_ptr + 7) & ~size_t(7));
+  const size_t off_ji = off_xy + ((b_xy + 7) & ~size_t(7));
+  const size_t total = off_ji + b_ji;
   if (ctx->formbuf_bytes < total) {
     if (ctx->formbuf) cudaFree(ctx->formbuf);
     ctx->formbuf = nullptr;
@@ -586,6 +606,8 @@ int b2_upload_forms(b2_ctx* ctx, int nd, int nc, int nmat, const double* const* 
   if (!vcoef.empty()) memcpy(&stage[off_vc], vcoef.data(), vcoef.size() * sizeof(double));
   memcpy(&stage[off_ptr], termptr.data(), b_ptr);
   if (!termxy.empty()) memcpy(&stage[off_xy], termxy.data(), termxy.size() * sizeof(int));
+  if (!jobD.empty()) memcpy(&stage[off_jd], jobD.data(), jobD.size() * sizeof(double));
+  if (!jobinfo.empty()) memcpy(&stage[off_ji], jobinfo.data(), jobinfo.size() * sizeof(int));
   // synchronous small copy: the staging vector dies at return
   B2_CUDA(ctx, cudaMemcpyAsync(ctx->formbuf, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
   B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -599,6 +621,9 @@ int b2_upload_forms(b2_ctx* ctx, int nd, int nc, int nmat, const double* const* 
   F.vcoef = (const double*)(fb + off_vc);
   F.termptr = (const int*)(fb + off_ptr);
   F.termxy = (const int*)(fb + off_xy);
+  F.jobD = (const double*)(fb + off_jd);
+  F.jobinfo = (const int*)(fb + off_ji);
+  F.njobs = (int)jobinfo.size();
   for (int m = 0; m < nmat; m++) F.values[m] = values_dev[m];
   for (int v = 0; v < nvec; v++) F.rhs[v] = rhs_dev[v];
 

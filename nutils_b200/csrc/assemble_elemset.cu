@@ -18,6 +18,15 @@
 // Mapping: one CTA per selected element (grid-stride), quadrature points in chunks through shared memory:
 //   P0 points of the chunk -> P1 1-D values/derivatives (Horner) -> P2 geometry per point -> P3 (N, grad N) per
 //   (point, function) -> P4 block entries in registers; scatter at the end of the element.
+//
+// P4 on the tensor cores (2-D and 3-D; the default).  For one coefficient block D_m[c][.][e][.] the element block is a
+// dense GEMM  C[a][b] = sum_q sum_y ( w_q sum_x B[q][a][x] D[x][y] ) B[q][b][y]  with M = N = n_e and K = nq (d+1):
+// FP64 mma.sync.m8n8k4 (SASS DMMA.8x8x4), one warp per row of 8x8 tiles, one k-block per quadrature point (k = y; mass-like
+// blocks batch four points per k-block instead).  A DMMA carries 256 FMAs per issue slot against 32 of a DFMA and
+// tolerates the low occupancy of a big-shared-memory kernel (profiles/microbench/ubench3.cu: 37 TFLOP/s with 4 warps per
+// SM and two accumulator tiles per warp; DFMA 34 TFLOP/s only with 16 independent chains per thread) -- this is the
+// "genuinely dense per-element GEMM" case of the high-order / many-point elements (p = 4: 125 x 125 x 500; cut cells:
+// thousands of points per element).  Context option "elemset_mma" = 0 selects the scalar FMA loop (kept for A/B parity).
 
 #include <algorithm>
 
@@ -91,8 +100,15 @@ __device__ __forceinline__ void tensor_eval(const double* tab, int pm1, const in
   }
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(512) k_assemble_elemset(const ESParams P) {
+// D(8x8) += A(8x4) B(4x8) in FP64 on the tensor cores: lane holds A[lane/4][lane%4], B[lane%4][lane/4], C[lane/4][2 (lane%4) + {0,1}]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// TCMAX = 0: block entries by scalar FMAs (any dimension).  TCMAX > 0: tensor-core path, up to TCMAX tile columns
+// (n_e <= 8 TCMAX) and NJ coefficient blocks per pass over the points.
+template <int DIM, int TCMAX, int NJ>
+__global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(const ESParams P) {
   constexpr int NA = DIM + 1;
   constexpr int NV = 1 << DIM;
   constexpr int JS = DIM * DIM + 1;
@@ -118,6 +134,9 @@ __global__ void __launch_bounds__(512) k_assemble_elemset(const ESParams P) {
   long long* sRow = reinterpret_cast<long long*>(sV + B2_MAX_FORMS * ne);  // [nb] first slot of the basis row
   int* sLen = reinterpret_cast<int*>(sRow + nb);        // [nb] columns of the basis row
   int* sDof = sLen + nb;                                // [nb] new basis index, -1: dropped
+  double* sD = reinterpret_cast<double*>(sDof + nb);  // [NJ][16] coefficient blocks of the current pass (tensor-core path)
+  constexpr bool MMA = TCMAX > 0;
+  const int ntr = (nb + 7) / 8;                          // rows / columns of 8x8 tiles
 
   for (long long sel = P.sel_begin + blockIdx.x; sel < P.sel_end; sel += gridDim.x) {
     const long long elem = E.elem_ids ? E.elem_ids[sel] : sel;
@@ -182,12 +201,24 @@ __global__ void __launch_bounds__(512) k_assemble_elemset(const ESParams P) {
     for (int t = tid; t < P.F.nvec * ne; t += T) sV[t] = 0.;
     __syncthreads();
 
-    for (int pass0 = 0; pass0 < ne2 || pass0 == 0; pass0 += T * EPT) {
-      double acc[B2_MAX_FORMS][EPT];
+    // a pass = one sweep over the points: EPT block entries per thread (FMA path) or NJ coefficient blocks (tensor cores)
+    const int pass_step = MMA ? NJ : T * EPT, pass_end = MMA ? P.F.njobs : ne2;
+    for (int pass0 = 0; pass0 < pass_end || pass0 == 0; pass0 += pass_step) {
+      double acc[MMA ? 1 : B2_MAX_FORMS][MMA ? 1 : EPT];
+      double cacc[MMA ? NJ : 1][MMA ? TCMAX : 1][2];
+      if constexpr (MMA) {
 #pragma unroll
-      for (int m = 0; m < B2_MAX_FORMS; m++)
+        for (int j = 0; j < NJ; j++)
 #pragma unroll
-        for (int e = 0; e < EPT; e++) acc[m][e] = 0.;
+          for (int tc = 0; tc < TCMAX; tc++) cacc[j][tc][0] = cacc[j][tc][1] = 0.;
+        __syncthreads();  // the previous pass has read sD
+        for (int t = tid; t < NJ * 16; t += T) sD[t] = pass0 + t / 16 < P.F.njobs ? P.F.jobD[(pass0 + t / 16) * 16 + t % 16] : 0.;
+      } else {
+#pragma unroll
+        for (int m = 0; m < (MMA ? 1 : B2_MAX_FORMS); m++)
+#pragma unroll
+          for (int e = 0; e < (MMA ? 1 : EPT); e++) acc[m][e] = 0.;
+      }
 
       for (int q0 = 0; q0 < nqt; q0 += qc) {
         const int nqc = min(qc, nqt - q0);
@@ -352,6 +383,54 @@ __global__ void __launch_bounds__(512) k_assemble_elemset(const ESParams P) {
         }
         __syncthreads();
         // P4: block entries
+        if constexpr (MMA) {
+          const int warp = tid >> 5, lane = tid & 31;
+          if (warp < ntr) {
+            const int arow = warp * 8 + (lane >> 2), kk = lane & 3;
+#pragma unroll
+            for (int j = 0; j < NJ; j++) {
+              if (pass0 + j < P.F.njobs) {
+                const double* Dj = sD + j * 16;
+                if ((P.F.jobinfo[pass0 + j] >> 24) == 0) {
+                  // k-block = one point, k = y: A[a][y] = w sum_x B[q][a][x] D[x][y],  B[y][b] = B[q][b][y]
+                  for (int ql = 0; ql < nqc; ql++) {
+                    double af = 0.;
+                    if (arow < nb && kk < NA) {
+                      const double* Ba = sB + (ql * nb + arow) * NA;
+#pragma unroll
+                      for (int x = 0; x < NA; x++) af = fma(Ba[x], Dj[x * 4 + kk], af);
+                      af *= sJ[ql * JS + DIM * DIM];
+                    }
+#pragma unroll
+                    for (int tc = 0; tc < TCMAX; tc++) {
+                      if (tc < ntr) {
+                        const int bcol = tc * 8 + (lane >> 2);
+                        const double bf = (bcol < nb && kk < NA) ? sB[(ql * nb + bcol) * NA + kk] : 0.;
+                        dmma884(cacc[j][tc][0], cacc[j][tc][1], af, bf);
+                      }
+                    }
+                  }
+                } else {
+                  // mass-like block (only D[0][0]): k-block = four points
+                  const double d00 = Dj[0];
+                  for (int q4 = 0; q4 < nqc; q4 += 4) {
+                    const int ql = q4 + kk;
+                    const bool okq = ql < nqc;
+                    const double af = (okq && arow < nb) ? sB[(ql * nb + arow) * NA] * sJ[ql * JS + DIM * DIM] * d00 : 0.;
+#pragma unroll
+                    for (int tc = 0; tc < TCMAX; tc++) {
+                      if (tc < ntr) {
+                        const int bcol = tc * 8 + (lane >> 2);
+                        const double bf = (okq && bcol < nb) ? sB[(ql * nb + bcol) * NA] : 0.;
+                        dmma884(cacc[j][tc][0], cacc[j][tc][1], af, bf);
+                      }
+                    }
+                  }
+                }
+              }
+            }
+          }
+        } else {
 #pragma unroll
         for (int e = 0; e < EPT; e++) {
           const int entry = pass0 + e * T + tid;
@@ -389,6 +468,7 @@ __global__ void __launch_bounds__(512) k_assemble_elemset(const ESParams P) {
             }
           }
         }
+        }
         // linear forms: thread r owns sV[.][r]
         if (pass0 == 0) {
           for (int r = tid; r < ne; r += T) {
@@ -409,6 +489,44 @@ __global__ void __launch_bounds__(512) k_assemble_elemset(const ESParams P) {
         __syncthreads();
       }
       // scatter: bisection of the column in the row's sorted list
+      if constexpr (MMA) {
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp < ntr) {
+          const int a = warp * 8 + (lane >> 2);
+          const int In = a < nb ? sDof[a] : -1;
+          if (In >= 0) {
+            const int len = sLen[a];
+            const int* cols = E.colidx_b + sRow[a];
+#pragma unroll
+            for (int tc = 0; tc < TCMAX; tc++) {
+              if (tc < ntr) {
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                  const int b = tc * 8 + (lane & 3) * 2 + i;
+                  const int Jn = b < nb ? sDof[b] : -1;
+                  if (Jn < 0) continue;
+                  int lo = 0, hi = len;
+                  while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (cols[mid] < Jn) lo = mid + 1;
+                    else hi = mid;
+                  }
+                  if (lo < len && cols[lo] == Jn) {
+#pragma unroll
+                    for (int j = 0; j < NJ; j++) {
+                      if (pass0 + j < P.F.njobs) {
+                        const int info = P.F.jobinfo[pass0 + j];
+                        const int m = info & 255, ci = (info >> 8) & 255, cj = (info >> 16) & 255;
+                        atomicAdd(P.F.values[m] + (sRow[a] * nc + (long long)ci * len) * nc + (long long)lo * nc + cj, cacc[j][tc][i]);
+                      }
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+      } else {
 #pragma unroll
       for (int e = 0; e < EPT; e++) {
         const int entry = pass0 + e * T + tid;
@@ -434,6 +552,7 @@ __global__ void __launch_bounds__(512) k_assemble_elemset(const ESParams P) {
           }
         }
       }
+          }
     }
     for (int t = tid; t < P.F.nvec * ne; t += T) {
       const int v = t / ne, r = t % ne;
@@ -443,35 +562,48 @@ __global__ void __launch_bounds__(512) k_assemble_elemset(const ESParams P) {
   }
 }
 
-template <int DIM>
-int launch_dim(b2_ctx* ctx, ESParams& P, int max_nq) {
+template <int DIM, int TCMAX, int NJ>
+int launch_cfg(b2_ctx* ctx, ESParams& P, int max_nq) {
   const int nb = P.B.nb, ne = P.ne, ne2 = ne * ne;
   constexpr int NA = DIM + 1, NV = 1 << DIM, JS = DIM * DIM + 1;
   int threads = (ne2 + EPT - 1) / EPT;
   threads = std::min(512, std::max(64, (threads + 31) / 32 * 32));
+  if (TCMAX > 0) threads = std::min(512, std::max(64, 32 * ((nb + 7) / 8)));  // one warp per row of 8x8 tiles
   const bool spline = P.SG.enabled != 0;
-  const size_t fixed = sizeof(double) * (DIM * P.pm1 * P.pm1 + DIM * P.pgm1 * P.pgm1 + (spline ? (DIM + 1) * P.nbg : DIM * NV) + nb + B2_MAX_FORMS * ne) +
+  const size_t fixed = sizeof(double) * (DIM * P.pm1 * P.pm1 + DIM * P.pgm1 * P.pgm1 + (spline ? (DIM + 1) * P.nbg : DIM * NV) + nb + B2_MAX_FORMS * ne + NJ * 16) +
                        sizeof(long long) * nb + sizeof(int) * 2 * nb;
   const size_t per_q = sizeof(double) * (NA + DIM * P.pm1 * 2 + DIM * P.pgm1 * 2 + JS + NA + nb * NA);
   const size_t budget = 96 * 1024;
   int qc = (int)std::max<size_t>(1, (budget > fixed ? (budget - fixed) / per_q : 1));
   qc = std::min(qc, std::max(max_nq, 1));
+  if (TCMAX > 0 && qc >= 4) qc &= ~3;  // mass-like blocks batch four points per k-block
   P.qchunk = qc;
   const size_t smem = fixed + per_q * qc + 16;
   if (smem > 200 * 1024) return b2_fail(ctx, B2_EUNSUPPORTED, "element too large for the element-set kernel");
-  B2_CUDA(ctx, cudaFuncSetAttribute(k_assemble_elemset<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = k_assemble_elemset<DIM, TCMAX, NJ>;
+  B2_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
-  B2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_elemset<DIM>, threads, smem));
+  B2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   per_sm = std::max(per_sm, 1);
   const long long nel = P.sel_end - P.sel_begin;
   const int blocks = (int)std::min<long long>(nel, (long long)ctx->sm_count * per_sm * 4);
   {
     KernelTimer timer(ctx);
-    k_assemble_elemset<DIM><<<blocks, threads, smem, ctx->stream>>>(P);
+    kern<<<blocks, threads, smem, ctx->stream>>>(P);
   }
   ctx->launches++;
   B2_CUDA(ctx, cudaGetLastError());
   return B2_OK;
+}
+
+template <int DIM>
+int launch_dim(b2_ctx* ctx, ESParams& P, int max_nq) {
+  const bool mma = DIM > 1 && P.F.njobs > 0 && P.B.nb <= 128 && !(ctx->opts.count("elemset_mma") && ctx->opts["elemset_mma"] == 0);
+  if (DIM > 1 && mma) {
+    if (P.B.nb <= 32) return launch_cfg<DIM == 1 ? 2 : DIM, 4, 3>(ctx, P, max_nq);
+    return launch_cfg<DIM == 1 ? 2 : DIM, 16, 1>(ctx, P, max_nq);
+  }
+  return launch_cfg<DIM, 0, 1>(ctx, P, max_nq);
 }
 
 }  // namespace

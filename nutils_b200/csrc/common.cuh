@@ -82,6 +82,12 @@ struct FormView {
   const int* termxy;      // [nterms] x | y<<8
   const double* termval;  // [nterms]
   const double* vcoef;    // [nvec][ncomp][ndims+1]
+  // dense view of the same tensors for the tensor-core path: job j = (matrix m, row component c, column component e) with a
+  // non-zero block D_m[c][.][e][.]; jobD[j][x*4+y] (zero padded to 4x4), jobinfo[j] = m | c << 8 | e << 16 | mode << 24
+  // (mode 1: only the value-value entry D[0][0] is non-zero -- mass-like)
+  const double* jobD;
+  const int* jobinfo;
+  int njobs;
   double* values[B2_MAX_FORMS];
   double* rhs[B2_MAX_FORMS];
 };

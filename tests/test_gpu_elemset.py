@@ -39,8 +39,16 @@ def _plan(ctx, prob):
                               renumber=prob.renumber, nbasis_new=prob.nbasis_new, scale=prob.scale, rational=prob.rational, geom_spline=gs)
 
 
+@pytest.fixture(params=[1, 0], ids=['mma', 'fma'])
+def mma(request, ctx):
+    'block entries on the FP64 tensor cores (default) or by the scalar FMA loop'
+    ctx.set_option('elemset_mma', request.param)
+    yield request.param
+    ctx.set_option('elemset_mma', 1)
+
+
 @pytest.mark.parametrize('name', util.elemset_golden_names())
-def test_golden(ctx, name):
+def test_golden(ctx, name, mma):
     g = util.load_golden(name)
     prob = util.elemset_problem_from_golden(g)
     plan = _plan(ctx, prob)
@@ -62,8 +70,8 @@ def test_golden(ctx, name):
             assert plan.row_offset(k) == rowptr[k]
 
 
-@pytest.mark.parametrize('name', ['hex_p2_warp', 'quad_p3', 'elast3d_p1', 'line_p3_std', 'hex_p2_std'])
-def test_full_selection_equals_structured(ctx, name):
+@pytest.mark.parametrize('name', ['hex_p2_warp', 'quad_p3', 'elast3d_p1', 'line_p3_std', 'hex_p2_std', 'quad_p4_warp', 'hex_p3_warp', 'elast3d_p2_warp', 'elast2d_p2_warp'])
+def test_full_selection_equals_structured(ctx, name, mma):
     # an element set that selects everything (tensor rule, identity numbering) reproduces the structured goldens:
     # the general pattern construction against the analytic one, the element-set kernel against the reference
     g = util.load_golden(name)
@@ -112,7 +120,7 @@ def _random_cut(seed, nelems, degree, keep=.6, maxpts=40):
 
 
 @pytest.mark.parametrize('seed,nelems,degree', [(0, (5, 4, 3), 2), (1, (7, 6), 3), (2, (9,), 2), (3, (4, 3, 4), 1), (4, (5, 5), 4), (5, (3, 3, 3), 3)])
-def test_random_cut_against_oracle(ctx, seed, nelems, degree):
+def test_random_cut_against_oracle(ctx, seed, nelems, degree, mma):
     prob = _random_cut(seed, nelems, degree)
     nd = prob.ndims
     rng = numpy.random.RandomState(100 + seed)
