@@ -75,13 +75,10 @@ __device__ __forceinline__ void inv_det(const double* J, double* Ji, double& det
 
 // value and xi-gradient of local function `a` (C-order multi-index over per-dimension degrees p[]) at chunk point ql,
 // from the 1-D table tab[ql][d][pm1][2]
+// `mi` = packed multi-index of the function (a_0 | a_1 << 8 | a_2 << 16, tabulated once per CTA: no integer divisions here)
 template <int DIM>
-__device__ __forceinline__ void tensor_eval(const double* tab, int pm1, const int* p, int a, double& N, double* dxi) {
-  int ad[3] = {0, 0, 0};
-  for (int d = DIM - 1; d >= 0; d--) {
-    ad[d] = a % (p[d] + 1);
-    a /= p[d] + 1;
-  }
+__device__ __forceinline__ void tensor_eval(const double* tab, int pm1, int mi, double& N, double* dxi) {
+  const int ad[3] = {mi & 255, (mi >> 8) & 255, (mi >> 16) & 255};
   double val[DIM], der[DIM];
 #pragma unroll
   for (int d = 0; d < DIM; d++) {
@@ -135,8 +132,20 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(con
   int* sLen = reinterpret_cast<int*>(sRow + nb);        // [nb] columns of the basis row
   int* sDof = sLen + nb;                                // [nb] new basis index, -1: dropped
   double* sD = reinterpret_cast<double*>(sDof + nb);  // [NJ][16] coefficient blocks of the current pass (tensor-core path)
+  int* sMi = reinterpret_cast<int*>(sD + NJ * 16);      // [nb] packed multi-index of the local functions
+  int* sMg = sMi + nb;                                  // [nbg] same for the geometry basis
   constexpr bool MMA = TCMAX > 0;
   const int ntr = (nb + 7) / 8;                          // rows / columns of 8x8 tiles
+  for (int a = tid; a < nb + (spline ? nbg : 0); a += T) {
+    const bool geo = a >= nb;
+    const int* pp = geo ? P.SG.GB.p : B.p;
+    int r = geo ? a - nb : a, mi = 0;
+    for (int d = DIM - 1; d >= 0; d--) {
+      mi |= (r % (pp[d] + 1)) << (8 * d);
+      r /= pp[d] + 1;
+    }
+    (geo ? sMg : sMi)[geo ? a - nb : a] = mi;
+  }
 
   for (long long sel = P.sel_begin + blockIdx.x; sel < P.sel_end; sel += gridDim.x) {
     const long long elem = E.elem_ids ? E.elem_ids[sel] : sel;
@@ -289,7 +298,7 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(con
             double W = 0.;
             for (int a = 0; a < nbg; a++) {
               double N, dxi[DIM];
-              tensor_eval<DIM>(sAg + ql * DIM * pgm1 * 2, pgm1, P.SG.GB.p, a, N, dxi);
+              tensor_eval<DIM>(sAg + ql * DIM * pgm1 * 2, pgm1, sMg[a], N, dxi);
               const double w = sX[DIM * nbg + a];
               W = fma(N, w, W);
 #pragma unroll
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(con
             for (int k = 0; k < DIM; k++) dW[k] = 0.;
             for (int a = 0; a < nb; a++) {
               double N, dxi[DIM];
-              tensor_eval<DIM>(sA + ql * DIM * pm1 * 2, pm1, B.p, a, N, dxi);
+              tensor_eval<DIM>(sA + ql * DIM * pm1 * 2, pm1, sMi[a], N, dxi);
               W = fma(N, sS[a], W);
 #pragma unroll
               for (int k = 0; k < DIM; k++) dW[k] = fma(dxi[k], sS[a], dW[k]);
@@ -359,7 +368,7 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(con
         for (int t = tid; t < nqc * nb; t += T) {
           const int a = t % nb, ql = t / nb;
           double N, dxi[DIM];
-          tensor_eval<DIM>(sA + ql * DIM * pm1 * 2, pm1, B.p, a, N, dxi);
+          tensor_eval<DIM>(sA + ql * DIM * pm1 * 2, pm1, sMi[a], N, dxi);
           const double c = sS[a];
           N *= c;
 #pragma unroll
@@ -393,20 +402,35 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(con
                 const double* Dj = sD + j * 16;
                 if ((P.F.jobinfo[pass0 + j] >> 24) == 0) {
                   // k-block = one point, k = y: A[a][y] = w sum_x B[q][a][x] D[x][y],  B[y][b] = B[q][b][y]
-                  for (int ql = 0; ql < nqc; ql++) {
-                    double af = 0.;
-                    if (arow < nb && kk < NA) {
-                      const double* Ba = sB + (ql * nb + arow) * NA;
+                  // (four points per trip: their shared-memory loads and the A fragments overlap; padding points add zeros)
+                  double dcol[NA];
 #pragma unroll
-                      for (int x = 0; x < NA; x++) af = fma(Ba[x], Dj[x * 4 + kk], af);
-                      af *= sJ[ql * JS + DIM * DIM];
+                  for (int x = 0; x < NA; x++) dcol[x] = kk < NA ? Dj[x * 4 + kk] : 0.;
+                  const bool arow_ok = arow < nb && kk < NA;
+                  for (int ql0 = 0; ql0 < nqc; ql0 += 4) {
+                    double af[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                      const int ql = ql0 + u;
+                      af[u] = 0.;
+                      if (arow_ok && ql < nqc) {
+                        const double* Ba = sB + (ql * nb + arow) * NA;
+                        double t = 0.;
+#pragma unroll
+                        for (int x = 0; x < NA; x++) t = fma(Ba[x], dcol[x], t);
+                        af[u] = t * sJ[ql * JS + DIM * DIM];
+                      }
                     }
 #pragma unroll
                     for (int tc = 0; tc < TCMAX; tc++) {
                       if (tc < ntr) {
                         const int bcol = tc * 8 + (lane >> 2);
-                        const double bf = (bcol < nb && kk < NA) ? sB[(ql * nb + bcol) * NA + kk] : 0.;
-                        dmma884(cacc[j][tc][0], cacc[j][tc][1], af, bf);
+                        const bool bok = bcol < nb && kk < NA;
+                        double bf[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) bf[u] = (bok && ql0 + u < nqc) ? sB[((ql0 + u) * nb + bcol) * NA + kk] : 0.;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) dmma884(cacc[j][tc][0], cacc[j][tc][1], af[u], bf[u]);
                       }
                     }
                   }
@@ -571,9 +595,10 @@ int launch_cfg(b2_ctx* ctx, ESParams& P, int max_nq) {
   if (TCMAX > 0) threads = std::min(512, std::max(64, 32 * ((nb + 7) / 8)));  // one warp per row of 8x8 tiles
   const bool spline = P.SG.enabled != 0;
   const size_t fixed = sizeof(double) * (DIM * P.pm1 * P.pm1 + DIM * P.pgm1 * P.pgm1 + (spline ? (DIM + 1) * P.nbg : DIM * NV) + nb + B2_MAX_FORMS * ne + NJ * 16) +
-                       sizeof(long long) * nb + sizeof(int) * 2 * nb;
+                       sizeof(long long) * nb + sizeof(int) * (3 * nb + P.nbg);
   const size_t per_q = sizeof(double) * (NA + DIM * P.pm1 * 2 + DIM * P.pgm1 * 2 + JS + NA + nb * NA);
-  const size_t budget = 96 * 1024;
+  // shared memory per CTA: small CTAs (tensor-core path at low degree: 4 warps) want several CTAs per SM
+  const size_t budget = (TCMAX == 4 ? 52 : 96) * 1024;
   int qc = (int)std::max<size_t>(1, (budget > fixed ? (budget - fixed) / per_q : 1));
   qc = std::min(qc, std::max(max_nq, 1));
   if (TCMAX > 0 && qc >= 4) qc &= ~3;  // mass-like blocks batch four points per k-block
