@@ -62,14 +62,14 @@ struct RowParams {
   double* rhs;
 };
 
-template <int P_, int T1_, int T2_, int QC_, int NT_, bool SPLIT_, int NG_ = 7>
+template <int P_, int T1_, int T2_, int QC_, int NT_, int SPLIT_, int NG_ = 7>
 struct RCfg {
   static constexpr int NG = NG_;  // components of the coefficient per point: 7 = symmetric Ghat (6) + w|det|, 10 = general Ghat (9) + w|det|
   static constexpr int P = P_, NB = P + 1, NQ = P + 1, WD = 2 * P + 1;
   static constexpr int T1 = T1_, T2 = T2_, QC = QC_, NT = NT_, NW = NT / 32;
   // one CTA per SM; the register file is split over the 4 sub-partitions (16384 each), warps are dealt round-robin
   static constexpr int MAXREG = (16384 / ((NW + 3) / 4) / 32 / 8 * 8) > 255 ? 255 : (16384 / ((NW + 3) / 4) / 32 / 8 * 8);
-  static constexpr bool SPLIT = SPLIT_;                   // S1/S2 warp items split in two term groups (more warps, fewer registers)
+  static constexpr int SPLIT = SPLIT_;                    // bit 0: S1 warp items split in three term groups, bit 1: S2 items in two (true = both)
   static constexpr int H1 = T1 + P, H2 = T2 + P;          // halo elements per tile dimension
   static constexpr int NQ1 = H1 * NQ, NQ2 = H2 * NQ;      // halo points
   static constexpr int NP1 = T1 * WD, NP2 = T2 * WD;      // dof pairs (i, i-P..i+P)
@@ -440,7 +440,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
   constexpr int NP2 = C::NP2, LS = C::LS, L2S = C::L2S;
   constexpr int N12 = C::N12, N12P = C::N12P, IPT = C::IPT;
   constexpr int NGK = FK ? 4 : 0;  // S2 output groups: DD DV VD VV [M]
-  constexpr int NPARTS1 = (C::SPLIT && FK) ? 3 : 1, NPARTS = (C::SPLIT && FK) ? 2 : 1;  // term groups of S1 / S2 items
+  constexpr int NPARTS1 = ((C::SPLIT & 1) && FK) ? 3 : 1, NPARTS = ((C::SPLIT & 2) && FK) ? 2 : 1;  // term groups of S1 / S2 items
   static_assert(NQ % QC == 0, "the points q0 of a layer are processed in NQ/QC chunks");
   constexpr int NCH = NQ / QC, NSUB = NCH * NFORM;
   constexpr int NS1 = T2 * C::WPI1 * NPARTS1, NS2 = T1 * C::WPI2 * NPARTS, NGC = (NQ1 * NQ2 + 31) / 32;
@@ -860,7 +860,7 @@ int launch_rows_vector(b2_ctx* ctx, RowParams& base, const FormView& F, const do
             for (int y = 0; y < 3; y++) prm.dm[e][x * 3 + y] = D_host[m][((c * na + 1 + x) * nc + e) * na + 1 + y];
         prm.valK = F.values[m];
         if (P <= 2) {
-          rc = P == 1 ? launch_rows_cfg<RCfg<1, 8, 8, 2, 256, false, 10>, true, false, 3, true>(ctx, prm) : launch_rows_cfg<RCfg<2, 4, 4, 3, 256, false, 10>, true, false, 3, true>(ctx, prm);
+          rc = P == 1 ? launch_rows_cfg<RCfg<1, 8, 8, 2, 256, 0, 10>, true, false, 3, true>(ctx, prm) : launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 0, 10>, true, false, 3, true>(ctx, prm);
         } else {
           // degrees 3 and 4: the accumulators of three column components do not fit the register file together --
           // one launch per column component e, writing the slots (J, e) of the rows (I, crow)
@@ -870,7 +870,7 @@ int launch_rows_vector(b2_ctx* ctx, RowParams& base, const FormView& F, const do
             for (int t = 0; t < 9; t++) pe.dm[0][t] = prm.dm[e][t];
             pe.valK = F.values[m] + e;
             if (e) pe.has_f = 0;
-            rc = P == 3 ? launch_rows_cfg<RCfg<3, 3, 3, 2, 256, true, 10>, true, false, 1, true>(ctx, pe) : launch_rows_cfg<RCfg<4, 2, 2, 1, 256, true, 10>, true, false, 1, true>(ctx, pe);
+            rc = P == 3 ? launch_rows_cfg<RCfg<3, 3, 3, 2, 256, 3, 10>, true, false, 1, true>(ctx, pe) : launch_rows_cfg<RCfg<4, 2, 2, 1, 256, 3, 10>, true, false, 1, true>(ctx, pe);
           }
         }
       } else {
@@ -880,10 +880,10 @@ int launch_rows_vector(b2_ctx* ctx, RowParams& base, const FormView& F, const do
           for (int e = 0; e < nc; e++) prm.rhoe[e] = D_host[m][((c * na) * nc + e) * na];
           prm.valM = F.values[m];
         }
-        rc = P == 1   ? launch_rows_cfg<RCfg<1, 8, 8, 2, 256, false>, false, true, 1, true>(ctx, prm)
-             : P == 2 ? launch_rows_cfg<RCfg<2, 4, 4, 3, 256, false>, false, true, 1, true>(ctx, prm)
-             : P == 3 ? launch_rows_cfg<RCfg<3, 3, 3, 2, 256, true>, false, true, 1, true>(ctx, prm)
-                      : launch_rows_cfg<RCfg<4, 2, 2, 1, 256, true>, false, true, 1, true>(ctx, prm);
+        rc = P == 1   ? launch_rows_cfg<RCfg<1, 8, 8, 2, 256, 0>, false, true, 1, true>(ctx, prm)
+             : P == 2 ? launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 0>, false, true, 1, true>(ctx, prm)
+             : P == 3 ? launch_rows_cfg<RCfg<3, 3, 3, 2, 256, 3>, false, true, 1, true>(ctx, prm)
+                      : launch_rows_cfg<RCfg<4, 2, 2, 1, 256, 3>, false, true, 1, true>(ctx, prm);
       }
       if (rc != B2_OK) return rc;
     }
@@ -982,11 +982,11 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
   // S1/S2 items (256 threads, 230 registers, no spills) beat more, thinner warps (512 threads cap at 128 registers and spill).
   const int64_t variant = ctx->opts.count("rows_variant") ? ctx->opts["rows_variant"] : 0;
   (void)variant;
-  if (P == 1) return launch_rows_forms<RCfg<1, 8, 8, 2, 256, false>>(ctx, prm, fk, fm);
+  if (P == 1) return launch_rows_forms<RCfg<1, 8, 8, 2, 256, 0>>(ctx, prm, fk, fm);
   if (P == 4) {
     // degree 4 (the high-order IGA case): 2 x 2 dof columns per CTA, one point-plane per pipeline step, S1/S2 items split
     // in term groups; K and M in separate launches (25 accumulators per dof pair and form, two dof pairs per thread)
-    using C4 = RCfg<4, 2, 2, 1, 256, true>;
+    using C4 = RCfg<4, 2, 2, 1, 256, 3>;
     if (!(fk && fm)) return launch_rows_forms<C4>(ctx, prm, fk, fm);
     RowParams pk = prm;
     pk.valM = nullptr;
@@ -1000,7 +1000,7 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
   if (P == 3) {
     // two chunks of two point-planes per layer; K and M in separate launches: 2 x 16 accumulators per dof pair and form
     // for two dof pairs per thread would not fit the register file together
-    using C3 = RCfg<3, 3, 3, 2, 256, true>;
+    using C3 = RCfg<3, 3, 3, 2, 256, 3>;
     if (!(fk && fm)) return launch_rows_forms<C3>(ctx, prm, fk, fm);
     RowParams pk = prm;
     pk.valM = nullptr;
@@ -1013,14 +1013,17 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
   }
 #ifdef B2_EXPERIMENT
   if (fk && fm) {
-    if (variant == 1) return launch_rows_cfg<RCfg<2, 4, 4, 3, 512, true>, true, true>(ctx, prm);
-    if (variant == 2) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, true>, true, true>(ctx, prm);
-    if (variant == 3) return launch_rows_cfg<RCfg<2, 5, 3, 3, 384, true>, true, true>(ctx, prm);
-    if (variant == 4) return launch_rows_cfg<RCfg<2, 3, 5, 3, 384, true>, true, true>(ctx, prm);
-    if (variant == 5) return launch_rows_cfg<RCfg<2, 4, 4, 3, 384, true>, true, true>(ctx, prm);
-    if (variant == 6) return launch_rows_cfg<RCfg<2, 4, 4, 3, 320, false>, true, true>(ctx, prm);
-    if (variant == 7) return launch_rows_cfg<RCfg<2, 4, 4, 3, 384, false>, true, true>(ctx, prm);
+    if (variant == 1) return launch_rows_cfg<RCfg<2, 4, 4, 3, 512, 3>, true, true>(ctx, prm);
+    if (variant == 2) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 3>, true, true>(ctx, prm);
+    if (variant == 3) return launch_rows_cfg<RCfg<2, 5, 3, 3, 384, 3>, true, true>(ctx, prm);
+    if (variant == 4) return launch_rows_cfg<RCfg<2, 3, 5, 3, 384, 3>, true, true>(ctx, prm);
+    if (variant == 5) return launch_rows_cfg<RCfg<2, 4, 4, 3, 384, 3>, true, true>(ctx, prm);
+    if (variant == 6) return launch_rows_cfg<RCfg<2, 4, 4, 3, 320, 0>, true, true>(ctx, prm);
+    if (variant == 7) return launch_rows_cfg<RCfg<2, 4, 4, 3, 384, 0>, true, true>(ctx, prm);
+    if (variant == 8) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 2>, true, true>(ctx, prm);
+    if (variant == 9) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 1>, true, true>(ctx, prm);
+    if (variant == 10) return launch_rows_cfg<RCfg<2, 4, 4, 3, 320, 2>, true, true>(ctx, prm);
   }
 #endif
-  return launch_rows_forms<RCfg<2, 4, 4, 3, 256, false>>(ctx, prm, fk, fm);
+  return launch_rows_forms<RCfg<2, 4, 4, 3, 256, 0>>(ctx, prm, fk, fm);
 }
