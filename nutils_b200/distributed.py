@@ -103,6 +103,77 @@ class SlabLayout:
         self.own_rows = slice(0, (min(own_hi, hi) - lo) * nrest_d) if rank + 1 < world else slice(0, self.nrows)
 
 
+def balanced_cuts(cost, world):
+    'cut a sequence of non-negative costs into `world` contiguous ranges of (nearly) equal total cost: world+1 offsets'
+    cum = numpy.concatenate([[0.], numpy.cumsum(numpy.asarray(cost, dtype=float))])
+    targets = cum[-1] * numpy.arange(1, world) / world
+    cuts = numpy.searchsorted(cum, targets, side='left')
+    cuts = numpy.concatenate([[0], cuts, [len(cost)]]).astype(int)
+    return numpy.maximum.accumulate(cuts)
+
+
+class ElemSetLayout:
+    '''Decomposition of an ELEMENT SET (trimmed topology, ragged quadrature; engine.ElemSetPlan) over the ranks.
+
+    The selected elements are cut into contiguous ranges of equal COST -- points times block entries, the balance
+    criterion SURVEY.md 8e names for trimmed meshes: cut cells carry hundreds of points, full cells a few dozen.  A rank
+    integrates its range (ElemSetPlan.assemble_device(sel_range=...)) into a window of the global CSR -- the rows
+    between the smallest and the largest dof its elements touch -- and adjacent ranks then add the rows they share with
+    :func:`exchange_interfaces` (one batched NCCL send/recv; the single collective of the path).
+
+    sel_range   : positions [s0, s1) in elem_ids integrated by this rank
+    row_lo/hi, off_lo/hi, nvalues, nrows, neighbours, own_rows : as in SlabLayout
+    '''
+
+    def __init__(self, bases1d, ncomp, rank, world, row_offset, elem_ids=None, qoff=None, renumber=None, nbasis_new=None, points_per_element=None):
+        self.rank, self.world = rank, world
+        shape = tuple(b.nelems for b in bases1d)
+        ntot = int(numpy.prod(shape))
+        elem_ids = numpy.arange(ntot) if elem_ids is None else numpy.asarray(elem_ids, dtype=numpy.int64)
+        nsel = len(elem_ids)
+        if qoff is not None:
+            npts = numpy.diff(numpy.asarray(qoff, dtype=numpy.int64))
+        else:
+            npts = numpy.full(nsel, 1 if points_per_element is None else int(points_per_element))
+        n_e = int(numpy.prod([b.degree + 1 for b in bases1d])) * ncomp
+        cost = npts.astype(float) * n_e * n_e + 64. * n_e  # integration + the fixed per-element work (tables, scatter)
+        cuts = balanced_cuts(cost, world)
+        if (numpy.diff(cuts) <= 0).any():
+            raise ValueError('more ranks than selected elements')
+        self.sel_range = int(cuts[rank]), int(cuts[rank + 1])
+        self.cost_share = float(cost[cuts[rank]:cuts[rank + 1]].sum() / cost.sum())
+        # dof range touched by every rank: first / last parent function of an element, renumbered (monotone)
+        idx = numpy.unravel_index(elem_ids, shape)
+        first = numpy.zeros(nsel, dtype=numpy.int64)
+        last = numpy.zeros(nsel, dtype=numpy.int64)
+        for b, i in zip(bases1d, idx):
+            st = numpy.asarray(b.start, dtype=numpy.int64)[i]
+            first = first * b.ndofs + st
+            last = last * b.ndofs + st + b.degree
+        if renumber is not None:
+            renumber = numpy.asarray(renumber, dtype=numpy.int64)
+            first, last = renumber[first], renumber[last]
+            if nbasis_new is not None and ((first < 0) | (last >= nbasis_new)).any():
+                raise ValueError('renumber drops a function of a selected element')
+        windows = [(int(first[a:b].min()) * ncomp, (int(last[a:b].max()) + 1) * ncomp) for a, b in zip(cuts[:-1], cuts[1:])]
+        self.row_lo, self.row_hi = windows[rank]
+        self.off_lo, self.off_hi = row_offset(self.row_lo), row_offset(self.row_hi)
+        self.nvalues = self.off_hi - self.off_lo
+        self.nrows = self.row_hi - self.row_lo
+        self.neighbours = []
+        for peer in range(world):
+            if peer == rank:
+                continue
+            a, b = max(windows[rank][0], windows[peer][0]), min(windows[rank][1], windows[peer][1])
+            if b <= a:
+                continue
+            if abs(peer - rank) > 1:
+                raise ValueError('element ranges thinner than the basis support: rows would be shared by non-adjacent ranks')
+            self.neighbours.append((peer, slice(row_offset(a) - self.off_lo, row_offset(b) - self.off_lo), slice(a - self.row_lo, b - self.row_lo)))
+        own_hi = min(windows[rank + 1][0], self.row_hi) if rank + 1 < world else self.row_hi
+        self.own_rows = slice(0, max(own_hi - self.row_lo, 0))
+
+
 def exchange_interfaces(layout, matrices, vectors, group=None):
     '''Add the neighbours' contributions on the shared rows, in place.
 

@@ -106,3 +106,62 @@ def test_plane_layout_arithmetic():
             assert l.elem_layers == (max(0, p0 - 2), min(prob.nelems[0], p1))
     with pytest.raises(ValueError):
         distributed.PlaneLayout(b1, 1, 0, 100, lambda row: 0)
+
+
+# ---- element sets (trimmed topologies): cost-balanced element ranges + the same neighbour exchange ---------------
+
+def _cut_problem():
+    from tests.test_gpu_elemset import _random_cut
+    return _random_cut(11, (8, 3, 3), 2, keep=.7, maxpts=30)
+
+
+def _elemset_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        prob = _cut_problem()
+        b1 = util.bases_1d(prob.nelems, prob.degree[0], 'spline')
+        mats, vecs = fem_oracle.assemble(prob, [('stiffness',)], [('load',)])
+        K_full, rowptr, colidx = mats[0]
+        lay = distributed.ElemSetLayout(b1, 1, rank, world, lambda r: int(rowptr[r]), elem_ids=prob.elem_ids, qoff=prob.qoff,
+                                        renumber=prob.renumber, nbasis_new=prob.nbasis_new)
+        win = numpy.zeros(lay.nvalues)
+        fwin = numpy.zeros(lay.nrows)
+        for isel in range(*lay.sel_range):     # the per-rank integrator: what b2_assemble_elemset_device(sel_begin, sel_end) does
+            dofs, N, grad, wdet = fem_oracle.element_data(prob, isel)
+            blk = fem_oracle.element_matrix(('stiffness',), N, grad, wdet)
+            assert dofs.min() >= lay.row_lo and dofs.max() < lay.row_hi
+            slots = _slot_lookup(rowptr, colidx, numpy.repeat(dofs, len(dofs)), numpy.tile(dofs, len(dofs)))
+            numpy.add.at(win, slots - lay.off_lo, blk.ravel())
+            numpy.add.at(fwin, dofs - lay.row_lo, fem_oracle.element_vector(('load',), N, grad, wdet))
+        tw, tf = torch.from_numpy(win), torch.from_numpy(fwin)
+        distributed.exchange_interfaces(lay, [tw], [tf])
+        ok = numpy.allclose(tw.numpy(), K_full[lay.off_lo:lay.off_hi], rtol=1e-12, atol=1e-15)
+        ok &= numpy.allclose(tf.numpy(), vecs[0][lay.row_lo:lay.row_hi], rtol=1e-12, atol=1e-15)
+        ok &= abs(lay.cost_share - 1 / world) < .2
+        flag = torch.tensor([1 if ok else 0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            out.put(int(flag))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_elemset():
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = 29400 + os.getpid() % 500 + 13
+    procs = [ctx.Process(target=_elemset_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) == 1
+
+
+def test_balanced_cuts():
+    cost = numpy.array([1., 1, 1, 1, 100, 1, 1, 1])
+    cuts = distributed.balanced_cuts(cost, 2)
+    assert cuts[0] == 0 and cuts[-1] == 8 and 4 <= cuts[1] <= 5
+    assert list(distributed.balanced_cuts(numpy.ones(9), 3)) == [0, 3, 6, 9]
