@@ -196,6 +196,18 @@ int b2_elemset_destroy(b2_elemset* elemset);
 int64_t b2_elemset_ndofs(const b2_elemset* elemset);   /* nbasis_new * ncomp */
 int64_t b2_elemset_npoints(const b2_elemset* elemset); /* total number of quadrature points (0 for tensor rules) */
 
+/* Boundary integrals and pointwise coefficients (Neumann terms and the boundary projections of
+ * solve_constraints integrate over boundary topologies, src/nutils/topology.py:2049-2057, sample.py:944-956 on a
+ * (d-1)-dimensional sample; coefficient functions are evaluated at the points, function.py:2291-2316 for the measure):
+ *   b2_elemset_set_faces: face_dim[k] (int8[nsel]) = -1 for a volume element set entry, or the reference direction normal
+ *     to the face the entry's points lie on (their local coordinate along that direction is 0 or 1).  The weight of such a
+ *     point is multiplied by the SURFACE measure |det J| |J^-T e_dim| instead of |det J| (function.J on a boundary sample).
+ *   b2_elemset_set_coefficient: a scalar per point that multiplies one form of the next assembly calls: which = m for
+ *     matrix form m, B2_MAX_FORMS + v for vector form v; coef float64[npoints] in point order (element sets with a tensor
+ *     rule: [nsel][nq]), NULL removes it.  The array is copied. */
+int b2_elemset_set_faces(b2_elemset* elemset, const int8_t* face_dim);
+int b2_elemset_set_coefficient(b2_elemset* elemset, int which, const double* coef, int64_t npoints);
+
 /* Spline geometry x(xi) = sum_i B_i(xi) X_i, or the rational map sum_i B_i w_i X_i / sum_i B_i w_i (the NURBS map of
  * examples/platewithhole.py:66-78 represented in the basis of the refined topology): gbasis is a scalar b2_basis on
  * the same element grid, ctrl_host float64[ndims][nbasis] the control points X_i, weights_host float64[nbasis] or NULL.

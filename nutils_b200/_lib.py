@@ -84,6 +84,8 @@ SIGNATURES = {
     'b2_assemble_rows_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
     'b2_elemset_create': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, ctypes.c_int, p_vp]),
     'b2_elemset_destroy': (ctypes.c_int, [c_vp]),
+    'b2_elemset_set_faces': (ctypes.c_int, [c_vp, c_vp]),
+    'b2_elemset_set_coefficient': (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_i64]),
     'b2_elemset_ndofs': (c_i64, [c_vp]),
     'b2_elemset_npoints': (c_i64, [c_vp]),
     'b2_geom_create_spline': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, p_vp]),

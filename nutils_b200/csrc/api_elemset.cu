@@ -113,9 +113,34 @@ extern "C" int b2_elemset_create(b2_ctx* ctx, const b2_basis* basis, int64_t nse
   return B2_OK;
 }
 
+extern "C" int b2_elemset_set_faces(b2_elemset* es, const int8_t* face_dim) {
+  if (!es) return B2_EINVAL;
+  b2_ctx* ctx = es->ctx;
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (es->d_face_dim) { cudaFree(es->d_face_dim); es->d_face_dim = nullptr; }
+  if (!face_dim) return B2_OK;
+  for (int64_t k = 0; k < es->nsel; k++)
+    if (face_dim[k] < -1 || face_dim[k] >= es->basis->ndims) return b2_fail(ctx, B2_EINVAL, "face_dim must be -1 or a reference direction");
+  return upload_n(ctx, (const signed char*)face_dim, (size_t)es->nsel, &es->d_face_dim);
+}
+
+extern "C" int b2_elemset_set_coefficient(b2_elemset* es, int which, const double* coef, int64_t npoints) {
+  if (!es || which < 0 || which >= 2 * B2_MAX_FORMS) return B2_EINVAL;
+  b2_ctx* ctx = es->ctx;
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (es->d_coef[which]) { cudaFree(es->d_coef[which]); es->d_coef[which] = nullptr; es->coef_len[which] = 0; }
+  if (!coef) return B2_OK;
+  if (npoints < 0 || (es->d_qoff && npoints != es->npoints)) return b2_fail(ctx, B2_EINVAL, "one coefficient per quadrature point is needed");
+  es->coef_len[which] = npoints;
+  return upload_n(ctx, coef, (size_t)npoints, &es->d_coef[which]);
+}
+
 extern "C" int b2_elemset_destroy(b2_elemset* es) {
   if (!es) return B2_OK;
   cudaSetDevice(es->ctx->device);
+  if (es->d_face_dim) cudaFree(es->d_face_dim);
+  for (double* p : es->d_coef)
+    if (p) cudaFree(p);
   void* ptrs[] = {es->d_elem_ids, es->d_qoff, es->d_qcoords, es->d_qweights, es->d_renumber, es->d_scale, es->d_selmask, es->d_dofmap,
                   es->d_coeffs[0], es->d_coeffs[1], es->d_coeffs[2], es->d_efirst[0], es->d_efirst[1], es->d_efirst[2], es->d_elast[0], es->d_elast[1], es->d_elast[2]};
   for (void* p : ptrs)
@@ -251,6 +276,12 @@ extern "C" int b2_assemble_elemset_device(b2_ctx* ctx, const b2_pattern* pattern
   E.renumber = es->d_renumber;
   E.scale = es->d_scale;
   E.rational = es->rational;
+  E.face_dim = es->d_face_dim;
+  E.nq_uniform = Q.nqt;
+  for (int k = 0; k < 2 * B2_MAX_FORMS; k++) {
+    E.coef[k] = es->d_coef[k];
+    if (es->d_coef[k] && !es->d_qoff && es->coef_len[k] != es->nsel * (int64_t)Q.nqt) return b2_fail(ctx, B2_EINVAL, "coefficient array does not match nsel x points of the tensor rule");
+  }
   E.nbasis_new = es->nbasis_new;
   for (int d = 0; d < nd; d++) E.coeffs[d] = es->d_coeffs[d];
   E.rowptr_b = pattern->d_rowptr_b;

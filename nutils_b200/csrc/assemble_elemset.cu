@@ -105,7 +105,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, 
 // TCMAX = 0: block entries by scalar FMAs (any dimension).  TCMAX > 0: tensor-core path, up to TCMAX tile columns
 // (n_e <= 8 TCMAX) and NJ coefficient blocks per pass over the points.
 template <int DIM, int TCMAX, int NJ>
-__global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(const ESParams P) {
+__global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512, TCMAX == 4 ? 4 : 1) k_assemble_elemset(const ESParams P) {
   constexpr int NA = DIM + 1;
   constexpr int NV = 1 << DIM;
   constexpr int JS = DIM * DIM + 1;
@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(con
   double* sAg = sA + qc * DIM * pm1 * 2;                // [qc][DIM][pgm1][2]
   double* sJ = sAg + qc * DIM * pgm1 * 2;               // [qc][JS]  J^-1 (k,i) then w|det|
   double* sW = sJ + qc * JS;                            // [qc][NA]  W, dW/dxi (rational functions)
-  double* sB = sW + qc * NA;                            // [qc][nb][NA]
+  double* sK = sW + qc * NA;                            // [qc][2 B2_MAX_FORMS] pointwise coefficient of every form (1 if none)
+  double* sB = sK + qc * 2 * B2_MAX_FORMS;              // [qc][nb][NA]
   double* sV = sB + qc * nb * NA;                       // [nvec][ne]
   long long* sRow = reinterpret_cast<long long*>(sV + B2_MAX_FORMS * ne);  // [nb] first slot of the basis row
   int* sLen = reinterpret_cast<int*>(sRow + nb);        // [nb] columns of the basis row
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(con
         r /= B.nel[d];
       }
     }
-    const long long qbeg = E.qoff ? E.qoff[sel] : 0;
+    const int fdim = E.face_dim ? E.face_dim[sel] : -1;   // >= 0: the points lie on a face, surface measure
+    const long long qbeg = E.qoff ? E.qoff[sel] : sel * E.nq_uniform;
     const int nqt = E.qoff ? (int)(E.qoff[sel + 1] - qbeg) : P.Q.nqt;
     __syncthreads();  // previous element fully scattered before shared memory is reused
     for (int t = tid; t < DIM * pm1 * pm1; t += T) {
@@ -250,6 +252,8 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(con
             }
             pt[DIM] = w;
           }
+#pragma unroll
+          for (int k = 0; k < 2 * B2_MAX_FORMS; k++) sK[ql * 2 * B2_MAX_FORMS + k] = E.coef[k] ? E.coef[k][qbeg + q0 + ql] : 1.;
         }
         __syncthreads();
         // P1: 1-D values and derivatives (Horner with derivative; rows are highest power first)
@@ -342,7 +346,18 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(con
           inv_det<DIM>(J, Ji, det);
 #pragma unroll
           for (int i = 0; i < DIM * DIM; i++) sJ[ql * JS + i] = Ji[i];
-          sJ[ql * JS + DIM * DIM] = pt[DIM] * fabs(det);
+          double meas = fabs(det);
+          if (fdim >= 0) {
+            // surface measure of the face normal to reference direction fdim: |det J| |J^-T e_fdim| (row fdim of J^-1)
+            double nn = 0.;
+#pragma unroll
+            for (int k = 0; k < DIM; k++)
+#pragma unroll
+              for (int i = 0; i < DIM; i++)
+                if (k == fdim) nn = fma(Ji[k * DIM + i], Ji[k * DIM + i], nn);
+            meas *= sqrt(nn);
+          }
+          sJ[ql * JS + DIM * DIM] = pt[DIM] * meas;
           if (E.rational == 1) {
             double W = 0., dW[DIM];
 #pragma unroll
@@ -407,6 +422,7 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(con
 #pragma unroll
                   for (int x = 0; x < NA; x++) dcol[x] = kk < NA ? Dj[x * 4 + kk] : 0.;
                   const bool arow_ok = arow < nb && kk < NA;
+                  const int fm = P.F.jobinfo[pass0 + j] & 255;  // matrix form of the block: its pointwise coefficient
                   for (int ql0 = 0; ql0 < nqc; ql0 += 4) {
                     double af[4];
 #pragma unroll
@@ -418,7 +434,7 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(con
                         double t = 0.;
 #pragma unroll
                         for (int x = 0; x < NA; x++) t = fma(Ba[x], dcol[x], t);
-                        af[u] = t * sJ[ql * JS + DIM * DIM];
+                        af[u] = t * sJ[ql * JS + DIM * DIM] * sK[ql * 2 * B2_MAX_FORMS + fm];
                       }
                     }
 #pragma unroll
@@ -437,10 +453,11 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(con
                 } else {
                   // mass-like block (only D[0][0]): k-block = four points
                   const double d00 = Dj[0];
+                  const int fm = P.F.jobinfo[pass0 + j] & 255;
                   for (int q4 = 0; q4 < nqc; q4 += 4) {
                     const int ql = q4 + kk;
                     const bool okq = ql < nqc;
-                    const double af = (okq && arow < nb) ? sB[(ql * nb + arow) * NA] * sJ[ql * JS + DIM * DIM] * d00 : 0.;
+                    const double af = (okq && arow < nb) ? sB[(ql * nb + arow) * NA] * sJ[ql * JS + DIM * DIM] * sK[ql * 2 * B2_MAX_FORMS + fm] * d00 : 0.;
 #pragma unroll
                     for (int tc = 0; tc < TCMAX; tc++) {
                       if (tc < ntr) {
@@ -486,7 +503,7 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(con
                     }
                     s += P.F.termval[t] * ax * by;
                   }
-                  acc[m][e] += s;
+                  acc[m][e] += s * sK[ql * 2 * B2_MAX_FORMS + m];
                 }
               }
             }
@@ -504,7 +521,7 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512) k_assemble_elemset(con
                 double t = 0.;
 #pragma unroll
                 for (int x = 0; x < NA; x++) t += P.F.vcoef[(v * nc + ci) * NA + x] * Ba[x];
-                s += t * sJ[ql * JS + DIM * DIM];
+                s += t * sJ[ql * JS + DIM * DIM] * sK[ql * 2 * B2_MAX_FORMS + B2_MAX_FORMS + v];
               }
               sV[v * ne + r] += s;
             }
@@ -596,7 +613,7 @@ int launch_cfg(b2_ctx* ctx, ESParams& P, int max_nq) {
   const bool spline = P.SG.enabled != 0;
   const size_t fixed = sizeof(double) * (DIM * P.pm1 * P.pm1 + DIM * P.pgm1 * P.pgm1 + (spline ? (DIM + 1) * P.nbg : DIM * NV) + nb + B2_MAX_FORMS * ne + NJ * 16) +
                        sizeof(long long) * nb + sizeof(int) * (3 * nb + P.nbg);
-  const size_t per_q = sizeof(double) * (NA + DIM * P.pm1 * 2 + DIM * P.pgm1 * 2 + JS + NA + nb * NA);
+  const size_t per_q = sizeof(double) * (NA + DIM * P.pm1 * 2 + DIM * P.pgm1 * 2 + JS + NA + 2 * B2_MAX_FORMS + nb * NA);
   // shared memory per CTA: small CTAs (tensor-core path at low degree: 4 warps) want several CTAs per SM
   const size_t budget = (TCMAX == 4 ? 52 : 96) * 1024;
   int qc = (int)std::max<size_t>(1, (budget > fixed ? (budget - fixed) / per_q : 1));

@@ -60,7 +60,7 @@ __device__ __forceinline__ void inverse_det(const double* J, double* Ji, double&
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(512) k_assemble_generic(const GenericParams P) {
+__global__ void __launch_bounds__(512, 1) k_assemble_generic(const GenericParams P) {
   constexpr int NA = DIM + 1;
   constexpr int NV = 1 << DIM;
   constexpr int JS = DIM * DIM + 1;

@@ -363,6 +363,24 @@ class ElemSetPlan:
         self.ndofs = int(lib.b2_pattern_nrows(h))
         self._csr = None
 
+    def set_faces(self, face_dim):
+        '''boundary integrals: face_dim[k] = -1 (volume) or the reference direction normal to the face the points of selected
+        element k lie on; their weights are multiplied by the surface measure (b2_elemset_set_faces).  None resets.'''
+        fd = None if face_dim is None else numpy.ascontiguousarray(face_dim, dtype=numpy.int8)
+        if fd is not None and fd.shape != (self.nsel,):
+            raise ValueError('one face code per selected element is needed')
+        self.ctx.check(self.ctx.lib.b2_elemset_set_faces(self.elemset, None if fd is None else fd.ctypes.data_as(c_vp)))
+
+    def set_coefficient(self, kind, index, coef):
+        '''a scalar per quadrature point multiplying matrix form `index` (kind 'matrix') or vector form `index` (kind 'vector') of
+        the following assembly calls (b2_elemset_set_coefficient); coef None removes it.'''
+        which = int(index) + (0 if kind == 'matrix' else 4)
+        if coef is None:
+            self.ctx.check(self.ctx.lib.b2_elemset_set_coefficient(self.elemset, which, None, 0))
+            return
+        coef = as_f64(coef).ravel()
+        self.ctx.check(self.ctx.lib.b2_elemset_set_coefficient(self.elemset, which, coef.ctypes.data_as(c_vp), len(coef)))
+
     def _make_basis(self, bases, ncomp):
         ctx, lib, nd = self.ctx, self.ctx.lib, len(bases)
         if any(b.periodic for b in bases):

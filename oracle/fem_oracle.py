@@ -60,7 +60,7 @@ class Problem:
     '''
 
     def __init__(self, nelems, degree, coeffs, setidx, start, ndofs_d, qpts, qwts, nodes, ncomp=1, elem_ids=None, qoff=None, qcoords=None,
-                 qweights=None, renumber=None, nbasis_new=None, scale=None, rational=0, geom_spline=None):
+                 qweights=None, renumber=None, nbasis_new=None, scale=None, rational=0, geom_spline=None, face_dim=None):
         self.ndims = len(nelems)
         self.nelems = tuple(int(n) for n in nelems)
         self.degree = tuple(int(p) for p in degree)
@@ -84,6 +84,9 @@ class Problem:
         self.rational = int(rational)
         # spline geometry: dict(degree, coeffs, setidx, start, ndofs_d, ctrl[ndims, nbasis_g], weights[nbasis_g] or None)
         self.geom_spline = geom_spline
+        # boundary integrals: face_dim[isel] = -1 (volume) or the reference direction normal to the face the element's points lie
+        # on; the measure is then the surface measure |det J| |J^-T e_dim| (function.J on a boundary sample, function.py:2291-2316)
+        self.face_dim = None if face_dim is None else numpy.asarray(face_dim, dtype=numpy.int64)
         assert geom_spline is not None or self.nodes.shape == (self.ndims,) + tuple(n + 1 for n in self.nelems)
 
     @property
@@ -197,10 +200,13 @@ def element_data(prob, isel):
     Jinv = numpy.linalg.inv(J)
     det = numpy.linalg.det(J)
     grad = numpy.einsum('qak,qki->qai', dN, Jinv)
+    meas = abs(det)
+    if prob.face_dim is not None and prob.face_dim[isel] >= 0:
+        meas = meas * numpy.linalg.norm(Jinv[:, prob.face_dim[isel], :], axis=-1)
     if prob.renumber is not None:
         dofs = prob.renumber[dofs]
         dofs = numpy.where((dofs >= 0) & (dofs < prob.nbasis_new), dofs, -1)
-    return dofs, N, grad, w * abs(det)
+    return dofs, N, grad, w * meas
 
 
 def _vector_dofs(dofs, ncomp):
@@ -271,9 +277,10 @@ def coo_to_csr(values, rows, cols, nrows, ncols):
     return data, rowptr, ucols.astype(numpy.int64)
 
 
-def assemble(prob, matrix_forms=(), vector_forms=()):
+def assemble(prob, matrix_forms=(), vector_forms=(), matrix_coefs=None, vector_coefs=None):
     '''Run the element loop and the sparse post-processing.
 
+    matrix_coefs / vector_coefs: per form None or one scalar per quadrature point (in point order) multiplying the integrand.
     Returns ([(values, rowptr, colidx), ...], [rhs, ...]).'''
     nc = prob.ncomp
     n_e = int(numpy.prod([p + 1 for p in prob.degree])) * nc
@@ -282,14 +289,19 @@ def assemble(prob, matrix_forms=(), vector_forms=()):
     rows = numpy.empty((nel, n_e, n_e), dtype=numpy.int64)
     cols = numpy.empty((nel, n_e, n_e), dtype=numpy.int64)
     rhs = [numpy.zeros(prob.ndofs) for _ in vector_forms]
+    qpos = 0
     for ielem in range(nel):
         dofs, N, grad, wdet = element_data(prob, ielem)
+        pts = slice(qpos, qpos + len(wdet))
+        qpos += len(wdet)
         vdofs = _vector_dofs(dofs, nc)
         rows[ielem] = vdofs[:, None]
         cols[ielem] = vdofs[None, :]
         for k, form in enumerate(matrix_forms):
-            vals[k][ielem] = element_matrix(form, N, grad, wdet, nc)
+            c = 1. if matrix_coefs is None or matrix_coefs[k] is None else numpy.asarray(matrix_coefs[k])[pts]
+            vals[k][ielem] = element_matrix(form, N, grad, wdet * c, nc)
         for k, form in enumerate(vector_forms):
-            numpy.add.at(rhs[k], vdofs, element_vector(form, N, grad, wdet, nc))
+            c = 1. if vector_coefs is None or vector_coefs[k] is None else numpy.asarray(vector_coefs[k])[pts]
+            numpy.add.at(rhs[k], vdofs, element_vector(form, N, grad, wdet * c, nc))
     mats = [coo_to_csr(v.ravel(), rows.ravel(), cols.ravel(), prob.ndofs, prob.ndofs) for v in vals]
     return mats, rhs

@@ -229,6 +229,116 @@ def nurbs_plate_case(name, nrefine=2, degree=2, radius=.5, poisson=.3, qdegree=1
                 K_values=kv, rowptr=rp, colidx=ci, F=r)
 
 
+# ---- boundary integrals and pointwise coefficients --------------------------------------------------------
+
+BNAMES = {1: ['left', 'right'], 2: ['left', 'right', 'bottom', 'top'], 3: ['left', 'right', 'bottom', 'top', 'front', 'back']}
+
+
+def _face_tables(shape, bname, qdegree):
+    '''volume elements adjacent to a boundary of a structured grid and the face Gauss points in their local coordinates:
+    elem_ids (increasing), face_dim, qoff, qcoords, qweights'''
+    from nutils import points as refpoints
+    ndims = len(shape)
+    k = BNAMES[ndims].index(bname)
+    dim, side = k // 2, k % 2
+    grids = [numpy.arange(n) for n in shape]
+    grids[dim] = numpy.array([shape[dim] - 1 if side else 0])
+    idx = numpy.stack(numpy.meshgrid(*grids, indexing='ij'), -1).reshape(-1, ndims)
+    elem_ids = numpy.sort(numpy.ravel_multi_index(idx.T, shape))
+    rx, rw = refpoints.gauss1(qdegree)
+    x1, w1 = numpy.asarray(rx)[:, 0], numpy.asarray(rw)
+    tang = [d for d in range(ndims) if d != dim]
+    if tang:
+        mesh_ = numpy.stack(numpy.meshgrid(*[x1] * len(tang), indexing='ij'), -1).reshape(-1, len(tang))
+        wts = numpy.ones(len(mesh_))
+        for j in range(len(tang)):
+            wts = wts * w1[numpy.stack(numpy.meshgrid(*[numpy.arange(len(x1))] * len(tang), indexing='ij'), -1).reshape(-1, len(tang))[:, j]]
+    else:
+        mesh_, wts = numpy.zeros((1, 0)), numpy.ones(1)
+    xi = numpy.empty((len(mesh_), ndims))
+    xi[:, dim] = float(side)
+    for j, d in enumerate(tang):
+        xi[:, d] = mesh_[:, j]
+    nq = len(xi)
+    return (elem_ids, numpy.full(len(elem_ids), dim, dtype=numpy.int8), numpy.arange(len(elem_ids) + 1, dtype=numpy.int64) * nq,
+            numpy.tile(xi, (len(elem_ids), 1)), numpy.tile(wts, len(elem_ids)))
+
+
+def _physical_points(nodes, shape, elem_ids, qoff, qcoords):
+    'x at the points: multilinear map of the nodal geometry'
+    ndims = len(shape)
+    out = numpy.empty_like(qcoords)
+    for k, e in enumerate(elem_ids):
+        idx = numpy.unravel_index(e, shape)
+        xi = qcoords[qoff[k]:qoff[k + 1]]
+        X = nodes[(slice(None),) + tuple(slice(i, i + 2) for i in idx)]  # (ndims, 2, 2, ...)
+        acc = X
+        for d in range(ndims):   # contract one reference direction at a time
+            x = xi[:, d]
+            if d == 0:
+                acc = acc[:, 0][None] * (1 - x).reshape((-1,) + (1,) * (acc.ndim - 1)) + acc[:, 1][None] * x.reshape((-1,) + (1,) * (acc.ndim - 1))
+            else:
+                acc = acc[:, :, 0] * (1 - x).reshape((-1,) + (1,) * (acc.ndim - 2)) + acc[:, :, 1] * x.reshape((-1,) + (1,) * (acc.ndim - 2))
+        out[qoff[k]:qoff[k + 1]] = acc
+    return out
+
+
+def _coef_g(x):
+    'the coefficient function of the boundary / variable-coefficient goldens, numpy and nutils spelling'
+    ndims = x.shape[-1]
+    return 1. + .5 * numpy.prod(x, axis=-1) + numpy.cosh(x[..., 0])
+
+
+def boundary_case(name, n, degree, bname, btype='spline', warp=0., seed=0):
+    '''boundary mass matrix and boundary load vector with a coefficient function, the two ingredients of Neumann terms and of the
+    boundary projections of solve_constraints (examples/laplace.py:60-86): int_G g N_i N_j dS, int_G g N_i dS'''
+    ndims = len(n)
+    verts = _verts(n, 'graded', seed)
+    X = _nodes(verts, warp, seed)
+    topo, geom0 = mesh.rectilinear(verts)
+    geom = _geom(topo, X) if warp else geom0
+    basis = topo.basis(btype, degree=degree)
+    qd = 2 * degree
+    btopo = topo.boundary[bname]
+    g = 1. + .5 * numpy.prod(geom, axis=0) + numpy.cosh(geom[0])
+    J = function.J(geom)
+    B = btopo.integral(basis[:, None] * basis[None, :] * g * J, degree=qd)
+    F = btopo.integral(basis * g * J, degree=qd)
+    area = function.eval(btopo.integral(J, degree=qd))
+    (bv, rp, ci), f = function.eval((function.as_csr(B), F))
+    elem_ids, face_dim, qoff, qcoords, qweights = _face_tables(tuple(n), bname, qd)
+    xq = _physical_points(X, tuple(n), elem_ids, qoff, qcoords)
+    return dict(kind='elemset_boundary', name=name, ndims=ndims, nelems=numpy.array(n), degree=degree, btype=btype, qdegree=qd, nodes=X, ndofs=len(basis), ncomp=1,
+                elem_ids=elem_ids, face_dim=face_dim, qoff=qoff, qcoords=qcoords, qweights=qweights, coef=_coef_g(xq), area=area,
+                M_values=bv, rowptr=rp, colidx=ci, F=f)
+
+
+def varcoef_case(name, n, degree, warp=.25, seed=0):
+    'volume integrals with a coefficient function: int g grad N_i . grad N_j dV, int g N_i dV (SURVEY 8d: variable coefficient)'
+    ndims = len(n)
+    verts = _verts(n, 'graded', seed)
+    X = _nodes(verts, warp, seed)
+    topo, geom0 = mesh.rectilinear(verts)
+    geom = _geom(topo, X) if warp else geom0
+    basis = topo.basis('spline', degree=degree)
+    qd = 2 * degree
+    g = 1. + .5 * numpy.prod(geom, axis=0) + numpy.cosh(geom[0])
+    J = function.J(geom)
+    gr = basis.grad(geom)
+    K = topo.integral((gr[:, None, :] * gr[None, :, :]).sum(-1) * g * J, degree=qd)
+    F = topo.integral(basis * g * J, degree=qd)
+    (kv, rp, ci), f = function.eval((function.as_csr(K), F))
+    from nutils import points as refpoints
+    rx, rw = refpoints.gauss1(qd)
+    x1 = numpy.asarray(rx)[:, 0]
+    xi = numpy.stack(numpy.meshgrid(*[x1] * ndims, indexing='ij'), -1).reshape(-1, ndims)
+    nel = int(numpy.prod(n))
+    qoff = numpy.arange(nel + 1, dtype=numpy.int64) * len(xi)
+    xq = _physical_points(X, tuple(n), numpy.arange(nel), qoff, numpy.tile(xi, (nel, 1)))
+    return dict(kind='elemset_varcoef', name=name, ndims=ndims, nelems=numpy.array(n), degree=degree, btype='spline', qdegree=qd, nodes=X, ndofs=len(basis), ncomp=1,
+                coef=_coef_g(xq), K_values=kv, rowptr=rp, colidx=ci, F=f)
+
+
 def known_answer_mass_1d():
     # tests/test_function.py:1574-1585 (known-answer COO of a 1-D p=1 mass matrix)
     topo, geom = mesh.line([0, 1, 2], bnames=['a', 'b'], space='X')
@@ -264,6 +374,13 @@ CASES = {
     'fcm2d_plate_p2': lambda: fcm_plate_case('fcm2d_plate_p2'),                                                      # examples/platewithhole.py FCM, its test size
     'nurbs_plate_p2': lambda: nurbs_plate_case('nurbs_plate_p2', nrefine=2, degree=2),                               # examples/platewithhole.py NURBS
     'nurbs_plate_p4': lambda: nurbs_plate_case('nurbs_plate_p4', nrefine=2, degree=4),                               # config 4 at toy size
+    'bnd2d_top_p1_std': lambda: boundary_case('bnd2d_top_p1_std', (8, 6), 1, 'top', btype='std'),                   # examples/laplace.py Neumann side
+    'bnd2d_left_p2_warp': lambda: boundary_case('bnd2d_left_p2_warp', (5, 7), 2, 'left', warp=.3, seed=8),
+    'bnd3d_right_p2_warp': lambda: boundary_case('bnd3d_right_p2_warp', (4, 3, 5), 2, 'right', warp=.3, seed=9),
+    'bnd3d_front_p3': lambda: boundary_case('bnd3d_front_p3', (3, 4, 2), 3, 'front', warp=.2, seed=10),
+    'bnd1d_right_p2': lambda: boundary_case('bnd1d_right_p2', (6,), 2, 'right'),
+    'varcoef3d_p2': lambda: varcoef_case('varcoef3d_p2', (4, 3, 3), 2, seed=11),
+    'varcoef2d_p3': lambda: varcoef_case('varcoef2d_p3', (5, 4), 3, seed=12),
     'elast3d_p2_warp': lambda: elasticity_case('elast3d_p2_warp', (3, 3, 2), 2, warp=.3, seed=7),  # config 3 at toy size
 }
 

@@ -34,9 +34,12 @@ def _plan(ctx, prob):
         g = prob.geom_spline
         gb = [bspline.Basis1D(g['degree'][d], prob.nelems[d], g['coeffs'][d], g['setidx'][d], g['start'][d], g['ndofs_d'][d]) for d in range(prob.ndims)]
         gs = gb, g['ctrl'], g['weights']
-    return engine.ElemSetPlan(ctx, _bases(prob), nodes=None if gs else prob.nodes, ncomp=prob.ncomp, rules=list(zip(prob.qpts, prob.qwts)),
+    plan = engine.ElemSetPlan(ctx, _bases(prob), nodes=None if gs else prob.nodes, ncomp=prob.ncomp, rules=list(zip(prob.qpts, prob.qwts)),
                               elem_ids=prob.elem_ids, qoff=prob.qoff, qcoords=prob.qcoords, qweights=prob.qweights,
                               renumber=prob.renumber, nbasis_new=prob.nbasis_new, scale=prob.scale, rational=prob.rational, geom_spline=gs)
+    if prob.face_dim is not None:
+        plan.set_faces(prob.face_dim)
+    return plan
 
 
 @pytest.fixture(params=[1, 0], ids=['mma', 'fma'])
@@ -58,11 +61,20 @@ def test_golden(ctx, name, mma):
     assert numpy.array_equal(colidx, g['colidx'])
     assert plan.ndofs == int(g['ndofs']) and plan.nnz == len(g['colidx'])
     Ds, Cs, expect, F = util.elemset_forms(g, prob.ndims)
+    mc, vc = util.elemset_coefs(g, len(Ds), len(Cs))
+    for k in range(len(Ds)):
+        plan.set_coefficient('matrix', k, None if mc is None else mc[k])
+    for k in range(len(Cs)):
+        plan.set_coefficient('vector', k, None if vc is None else vc[k])
     vals, rhs = plan.assemble_host(Ds, Cs)
     for v, ref in zip(vals, expect):
         assert util.relerr(v, ref) <= TOL
         assert util.rowsum_relerr(v, ref, rowptr) <= TOL
     assert util.relerr(rhs[0], F) <= TOL
+    if 'area' in g and mc is not None:
+        # without the coefficient the boundary mass matrix sums to the area of the face (partition of unity on the boundary)
+        plan.set_coefficient('matrix', 0, None)
+        assert abs(plan.assemble_host(Ds, [])[0][0].sum() - float(g['area'])) <= 1e-12 * abs(float(g['area']))
     if 'volume' in g:
         assert abs(vals[1].sum() - float(g['volume'])) <= 1e-12 * abs(float(g['volume']))
     for k in range(plan.ndofs + 1):

@@ -55,7 +55,8 @@ def test_numpy_oracle_elemset(name):
     g = util.load_golden(name)
     prob = util.elemset_problem_from_golden(g)
     Ds, Cs, expect, F = util.elemset_forms(g, prob.ndims)
-    mats, vecs = fem_oracle.assemble(prob, [('generic', D) for D in Ds], [('generic', C) for C in Cs])
+    mc, vc = util.elemset_coefs(g, len(Ds), len(Cs))
+    mats, vecs = fem_oracle.assemble(prob, [('generic', D) for D in Ds], [('generic', C) for C in Cs], matrix_coefs=mc, vector_coefs=vc)
     for (v, rp, ci), ref in zip(mats, expect):
         assert rp.dtype == numpy.int64 and ci.dtype == numpy.int64
         assert numpy.array_equal(rp, g['rowptr'])

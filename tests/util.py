@@ -62,7 +62,7 @@ def elemset_problem_from_golden(g):
     b1 = bases_1d(nelems, degree, str(g['btype']))
     rules = points.tensor_gauss(ndims, int(g['qdegree']))
     kw = dict(ncomp=int(g['ncomp']))
-    for key in 'elem_ids', 'qoff', 'qcoords', 'qweights', 'renumber', 'scale':
+    for key in 'elem_ids', 'qoff', 'qcoords', 'qweights', 'renumber', 'scale', 'face_dim':
         if key in g:
             kw[key] = g[key]
     if 'renumber' in g:
@@ -85,9 +85,20 @@ def elemset_forms(g, ndims):
     from nutils_b200 import engine
     if str(g['kind']) == 'elemset_scalar':
         return [engine.form_stiffness(ndims), engine.form_mass(ndims)], [engine.form_load(ndims)], [g['K_values'], g['M_values']], g['F']
+    if str(g['kind']) == 'elemset_boundary':   # int_G g N_i N_j dS, int_G g N_i dS
+        return [engine.form_mass(ndims)], [engine.form_load(ndims)], [g['M_values']], g['F']
+    if str(g['kind']) == 'elemset_varcoef':    # int g grad N_i . grad N_j dV, int g N_i dV
+        return [engine.form_stiffness(ndims)], [engine.form_load(ndims)], [g['K_values']], g['F']
     C = numpy.zeros((ndims, ndims + 1))
     C[:, 0] = -numpy.asarray(g['load'])
     return [engine.form_elasticity(ndims, float(g['lmbda']), float(g['mu']))], [C], [g['K_values']], g['F']
+
+
+def elemset_coefs(g, nmat, nvec):
+    'pointwise coefficients per matrix / vector form of an element-set golden (None: constant coefficient tensors only)'
+    if 'coef' not in g:
+        return None, None
+    return [g['coef']] * nmat, [g['coef']] * nvec
 
 
 def relerr(a, b):
