@@ -36,6 +36,75 @@ class Geometry:
     def __repr__(self):
         return 'Geometry<{}>'.format('x'.join(str(n - 1) for n in self.nodes.shape[1:]))
 
+    def __getitem__(self, i):
+        'coordinate function x_i: a PointFunction usable as a coefficient, e.g. ``numpy.cosh(geom[0]) * basis * J(geom)``'
+        i = int(i)
+        if not -self.ndims <= i < self.ndims:
+            raise IndexError(i)
+        return PointFunction(self, lambda x, i=i: x[..., i])
+
+    def __iter__(self):
+        return (self[i] for i in range(self.ndims))
+
+    def __len__(self):
+        return self.ndims
+
+
+class PointFunction:
+    '''Scalar function of the physical coordinates, evaluated on the host at the quadrature points and handed to the
+    kernels as a per-point coefficient (b2_elemset_set_coefficient).  Built from ``geom[i]`` with arithmetic and numpy
+    ufuncs -- the spelling of the reference's examples (``numpy.cosh(x[0])``, examples/laplace.py:60-70).'''
+
+    __array_priority__ = 90.
+
+    def __init__(self, geom, f):
+        self.geom = geom
+        self.f = f
+
+    def __call__(self, x):
+        return numpy.broadcast_to(self.f(x), x.shape[:-1])
+
+    def _lift(self, other):
+        if isinstance(other, PointFunction):
+            if other.geom is not self.geom:
+                raise NotImplementedError('functions of different geometries')
+            return other.f
+        if isinstance(other, (Array, Geometry, _Jacobian)) or hasattr(other, '_array'):
+            return None
+        c = float(other)
+        return lambda x: c
+
+    def _binary(self, other, op, swap=False):
+        g = self._lift(other)
+        if g is None:
+            return NotImplemented
+        f = self.f
+        return PointFunction(self.geom, (lambda x: op(g(x), f(x))) if swap else (lambda x: op(f(x), g(x))))
+
+    def __add__(self, o): return self._binary(o, numpy.add)
+    def __radd__(self, o): return self._binary(o, numpy.add, True)
+    def __sub__(self, o): return self._binary(o, numpy.subtract)
+    def __rsub__(self, o): return self._binary(o, numpy.subtract, True)
+    def __truediv__(self, o): return self._binary(o, numpy.divide)
+    def __rtruediv__(self, o): return self._binary(o, numpy.divide, True)
+    def __pow__(self, o): return self._binary(o, numpy.power)
+    def __neg__(self): return PointFunction(self.geom, lambda x, f=self.f: -f(x))
+
+    def __mul__(self, o):
+        if isinstance(o, (Array, _Jacobian)) or hasattr(o, '_array'):
+            return Array.cast(o) * self if not isinstance(o, _Jacobian) else NotImplemented
+        return self._binary(o, numpy.multiply)
+
+    __rmul__ = __mul__
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != '__call__' or kwargs:
+            return NotImplemented
+        fs = [self._lift(a) for a in inputs]
+        if any(f is None for f in fs):
+            return NotImplemented
+        return PointFunction(self.geom, lambda x: ufunc(*[f(x) for f in fs]))
+
 
 class Array:
     '''Closed-form integrand: see the module docstring.
@@ -49,12 +118,13 @@ class Array:
 
     __array_priority__ = 100.  # numpy defers to our __rmul__ etc.
 
-    def __init__(self, shape, dofaxes, space, C, jac=None):
+    def __init__(self, shape, dofaxes, space, C, jac=None, coef=None):
         self.shape = tuple(int(n) for n in shape)
         self.dofaxes = tuple(dofaxes)
         self.space = space
         self.C = numpy.asarray(C, dtype=float)
         self.jac = jac
+        self.coef = coef  # PointFunction multiplying the whole array, or None
         assert self.C.ndim == len(self.shape) + 2 * len(self.dofaxes)
 
     ndim = property(lambda self: len(self.shape))
@@ -84,7 +154,7 @@ class Array:
         return Array(a.shape, (), None, a)
 
     def _with(self, **kw):
-        d = dict(shape=self.shape, dofaxes=self.dofaxes, space=self.space, C=self.C, jac=self.jac)
+        d = dict(shape=self.shape, dofaxes=self.dofaxes, space=self.space, C=self.C, jac=self.jac, coef=self.coef)
         d.update(kw)
         return Array(**d)
 
@@ -119,7 +189,7 @@ class Array:
                 cidx.append(int(it))
             ax += 1
         C = self.C[tuple(cidx) + (Ellipsis,)]
-        return Array(shape, dofaxes, self.space, C, self.jac)
+        return Array(shape, dofaxes, self.space, C, self.jac, self.coef)
 
     def sum(self, axis=None):
         axes = range(self.ndim) if axis is None else ([axis] if numpy.ndim(axis) == 0 else list(axis))
@@ -133,7 +203,7 @@ class Array:
             C = out.C
             if C.shape[a] == 1 and out.shape[a] != 1:
                 C = C * out.shape[a]
-            out = Array(shape, dofaxes, out.space, C.sum(a), out.jac)
+            out = Array(shape, dofaxes, out.space, C.sum(a), out.jac, out.coef)
         return out
 
     def swapaxes(self, a, b):
@@ -152,7 +222,7 @@ class Array:
         if len(newdof) == 2 and newdof[0] > newdof[1]:
             C = C.transpose(list(range(self.ndim)) + [self.ndim + 2, self.ndim + 3, self.ndim, self.ndim + 1])
             newdof = newdof[::-1]
-        return Array(shape, newdof, self.space, C, self.jac)
+        return Array(shape, newdof, self.space, C, self.jac, self.coef)
 
     T = property(lambda self: self.transpose())
 
@@ -184,7 +254,7 @@ class Array:
         C = numpy.zeros(self.C.shape[:self.ndim] + (nd,) + self.C.shape[self.ndim:])
         for k in range(nd):
             C[(slice(None),) * self.ndim + (k, slice(None), 1 + k)] = self.C[..., 0]
-        return Array(self.shape + (nd,), self.dofaxes, self.space, C, self.jac)
+        return Array(self.shape + (nd,), self.dofaxes, self.space, C, self.jac, self.coef)
 
     def div(self, geom):
         return self.grad(geom).trace(-2, -1)
@@ -197,12 +267,14 @@ class Array:
 
     def _binary_linear(self, other, sign):
         other = Array.cast(other)
+        if other.coef is not self.coef:
+            raise NotImplementedError('sum of arrays with different coefficient functions (integrate them separately)')
         if other.dofaxes != self.dofaxes or other.shape != self.shape or (self.dofaxes and other.space is not self.space) or other.jac is not self.jac:
             a, b = _broadcast_plain(self, other)
             if a.dofaxes != b.dofaxes or (a.dofaxes and a.space is not b.space) or a.jac is not b.jac:
                 raise NotImplementedError('sum of arrays with different dof structure')
             shape = tuple(max(m, n) for m, n in zip(a.shape, b.shape))
-            return Array(shape, a.dofaxes, a.space, a.C + sign * b.C, a.jac)
+            return Array(shape, a.dofaxes, a.space, a.C + sign * b.C, a.jac, a.coef)
         return self._with(C=self.C + sign * other.C)
 
     def __add__(self, other):
@@ -229,8 +301,11 @@ class Array:
             if self.jac is not None:
                 raise NotImplementedError('product of two jacobians')
             return self._with(jac=other.geom)
+        if isinstance(other, PointFunction):
+            return self._with(coef=other if self.coef is None else self.coef * other)
         other = Array.cast(other)
         a, b = _broadcast_plain(self, other)
+        coef = a.coef if b.coef is None else b.coef if a.coef is None else a.coef * b.coef
         if a.jac is not None and b.jac is not None:
             raise NotImplementedError('product of two jacobians')
         jac = a.jac if a.jac is not None else b.jac
@@ -247,13 +322,13 @@ class Array:
             if da > db:  # slot groups follow the order of the dof axes
                 C = C.transpose(list(range(nd)) + [nd + 2, nd + 3, nd, nd + 1])
             shape = tuple(max(m, n) for m, n in zip(a.shape, b.shape))
-            return Array(shape, sorted((da, db)), a.space, C, jac)
+            return Array(shape, sorted((da, db)), a.space, C, jac, coef)
         if b.dofaxes:
             a, b = b, a
         nslot = 2 * len(a.dofaxes)
         C = a.C * b.C[(Ellipsis,) + (None,) * nslot]
         shape = tuple(max(m, n) for m, n in zip(a.shape, b.shape))
-        return Array(shape, a.dofaxes, a.space, C, jac)
+        return Array(shape, a.dofaxes, a.space, C, jac, coef)
 
     __rmul__ = __mul__
 
@@ -281,7 +356,7 @@ def _broadcast_plain(a, b):
         k = nd - x.ndim
         if not k:
             return x
-        return Array((1,) * k + x.shape, tuple(d + k for d in x.dofaxes), x.space, x.C[(None,) * k], x.jac)
+        return Array((1,) * k + x.shape, tuple(d + k for d in x.dofaxes), x.space, x.C[(None,) * k], x.jac, x.coef)
     a, b = pad(a), pad(b)
     for m, n, i in zip(a.shape, b.shape, range(nd)):
         if m != n and m != 1 and n != 1:
@@ -296,6 +371,8 @@ class _Jacobian:
         self.geom = geom
 
     def __mul__(self, other):
+        if isinstance(other, PointFunction):
+            return Array((), (), None, numpy.ones(()), self.geom, other)
         return Array.cast(other) * self
 
     __rmul__ = __mul__

@@ -10,14 +10,16 @@ from . import function, engine
 
 
 class Sample:
-    def __init__(self, topo, rules, device=0):
+    def __init__(self, topo, rules, device=0, faces=None):
         self.topo = topo
         self.rules = rules
         self.ndims = topo.ndims
+        self.faces = faces  # None: volume sample; tuple of (direction, side): boundary sample on those sides
         self.nelems = len(topo)
         self.npoints = self.nelems * int(numpy.prod([len(r[0]) for r in rules]))
         self.device = device
         self._plans = {}
+        self._esplans = {}
 
     # -- reference API -------------------------------------------------------------------------------
 
@@ -80,10 +82,100 @@ class Sample:
             entry = self._plans[key] = plan, geom.nodes
         return entry[0]
 
+    # -- element-set route: boundary samples and integrands with coefficient functions ---------------
+
+    def _face_tables(self, dim, side):
+        'adjacent volume elements of one side and the face Gauss points in their local coordinates'
+        shape = self.topo.shape
+        nd = self.ndims
+        grids = [numpy.arange(n) for n in shape]
+        grids[dim] = numpy.array([shape[dim] - 1 if side else 0])
+        idx = numpy.stack(numpy.meshgrid(*grids, indexing='ij'), -1).reshape(-1, nd)
+        elem_ids = numpy.sort(numpy.ravel_multi_index(idx.T, shape))
+        tang = [d for d in range(nd) if d != dim]
+        xi = numpy.zeros((1, nd))
+        w = numpy.ones(1)
+        xi[:, dim] = float(side)
+        for d in tang:  # tensor product of the 1-D rules of the tangential directions
+            x1, w1 = self.rules[d]
+            xi = numpy.repeat(xi, len(x1), axis=0)
+            xi[:, d] = numpy.tile(x1, len(w))
+            w = numpy.repeat(w, len(x1)) * numpy.tile(w1, len(w))
+        return elem_ids, xi, w
+
+    def _physical_points(self, nodes, elem_ids, xi):
+        'x[nsel, nq, ndims] of the multilinear geometry at local points xi[nq, ndims] of the elements elem_ids'
+        nd = self.ndims
+        idx = numpy.unravel_index(elem_ids, self.topo.shape)
+        x = numpy.zeros((len(elem_ids), len(xi), nd))
+        for corner in range(1 << nd):
+            bits = [(corner >> (nd - 1 - d)) & 1 for d in range(nd)]
+            phi = numpy.ones(len(xi))
+            for d, b in enumerate(bits):
+                phi = phi * (xi[:, d] if b else 1. - xi[:, d])
+            X = nodes[(slice(None),) + tuple(i + b for i, b in zip(idx, bits))]  # (ndims, nsel)
+            x += phi[None, :, None] * X.T[:, None, :]
+        return x
+
+    def _evaluate_elemset(self, integrals):
+        'boundary integrals and integrands with coefficient functions: engine.ElemSetPlan, one plan per side'
+        from . import matrix as _matrix
+        geom = integrals[0].func.jac
+        space = integrals[0].func.space
+        if any(i.func.jac is not geom for i in integrals):
+            raise NotImplementedError('integrals over different geometries in one evaluation')
+        faces = self.faces if self.faces is not None else (None,)
+        mats = [k for k, i in enumerate(integrals) if i.kind == 'matrix']
+        vecs = [k for k, i in enumerate(integrals) if i.kind == 'vector']
+        if len(faces) > 1 and mats:
+            raise NotImplementedError('matrix-valued integrals over several sides at once (integrate the sides separately)')
+        if len(mats) > 4 or len(vecs) > 4:
+            raise NotImplementedError('more than four matrices or vectors per evaluation')
+        out = [None] * len(integrals)
+        ctx = engine.Context.get(self.device)
+        for face in faces:
+            key = id(space), id(geom), face
+            entry = self._esplans.get(key)
+            if entry is None or entry[1] is not geom.nodes:
+                if face is None:
+                    nq = int(numpy.prod([len(r[0]) for r in self.rules]))
+                    xi = numpy.stack([g.ravel() for g in numpy.meshgrid(*[r[0] for r in self.rules], indexing='ij')], -1)
+                    elem_ids = numpy.arange(self.nelems)
+                    plan = engine.ElemSetPlan(ctx, space.bases1d, nodes=geom.nodes, ncomp=space.ncomp, rules=self.rules)
+                else:
+                    elem_ids, xi, w = self._face_tables(*face)
+                    nq = len(w)
+                    qoff = numpy.arange(len(elem_ids) + 1, dtype=numpy.int64) * nq
+                    plan = engine.ElemSetPlan(ctx, space.bases1d, nodes=geom.nodes, ncomp=space.ncomp, elem_ids=elem_ids, qoff=qoff,
+                                              qcoords=numpy.tile(xi, (len(elem_ids), 1)), qweights=numpy.tile(w, len(elem_ids)))
+                    plan.set_faces(numpy.full(len(elem_ids), face[0], dtype=numpy.int8))
+                entry = self._esplans[key] = plan, geom.nodes, elem_ids, xi
+            plan, _, elem_ids, xi = entry
+            xq = None
+            for slot, ks in (('matrix', mats), ('vector', vecs)):
+                for j, k in enumerate(ks):
+                    coef = integrals[k].func.coef
+                    if coef is None:
+                        plan.set_coefficient(slot, j, None)
+                    else:
+                        if xq is None:
+                            xq = self._physical_points(geom.nodes, elem_ids, xi)
+                        plan.set_coefficient(slot, j, numpy.ascontiguousarray(coef(xq), dtype=float))
+            values, rhs = plan.assemble_host([integrals[k].tensor for k in mats], [integrals[k].tensor for k in vecs])
+            if mats:
+                rowptr, colidx = plan.csr_pattern()
+            for k, v in zip(mats, values):
+                out[k] = v, rowptr, colidx
+            for k, r in zip(vecs, rhs):
+                out[k] = r if out[k] is None else out[k] + r
+        return out
+
     def _evaluate(self, integrals):
         '''Assemble a list of Integrals that share this sample and one basis with ONE launch per geometry.
 
         Returns per integral: the rhs vector, or (values, rowptr, colidx).'''
+        if self.faces is not None or any(i.func.coef is not None for i in integrals):
+            return self._evaluate_elemset(integrals)
         out = [None] * len(integrals)
         bygeom = {}
         for k, integral in enumerate(integrals):

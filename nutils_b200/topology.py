@@ -78,6 +78,55 @@ class Basis:
         return self.topo._vector_basis(self, ncomp)
 
 
+BOUNDARY_NAMES = {1: ('left', 'right'), 2: ('left', 'right', 'bottom', 'top'), 3: ('left', 'right', 'bottom', 'top', 'front', 'back')}
+
+
+class _Boundary:
+    "``topo.boundary['left']``, ``topo.boundary['left,top']`` (topology.py:2049-2057, names of StructuredTopology.boundary)"
+
+    def __init__(self, topo):
+        self.topo = topo
+
+    def __getitem__(self, names):
+        faces = []
+        for name in names.split(','):
+            try:
+                k = BOUNDARY_NAMES[self.topo.ndims].index(name.strip())
+            except ValueError:
+                raise KeyError(name)
+            faces.append((k // 2, k % 2))
+        return BoundaryTopology(self.topo, tuple(faces))
+
+
+class BoundaryTopology:
+    '''One or more sides of a structured topology: integrals over it are boundary integrals (Neumann terms, the boundary
+    projections of solve_constraints).  The points are the face Gauss points of the adjacent volume elements; the basis
+    and its dof numbering are the volume ones.'''
+
+    def __init__(self, parent, faces):
+        self.parent = parent
+        self.faces = faces
+        self.ndims = parent.ndims - 1
+        self._samples = {}
+
+    def sample(self, ischeme, degree):
+        if ischeme != 'gauss':
+            raise NotImplementedError('only gauss samples are on the accelerated path')
+        key = tuple(numpy.ravel(degree).tolist())
+        s = self._samples.get(key)
+        if s is None:
+            s = self._samples[key] = _sample.Sample(self.parent, points.tensor_gauss(self.parent.ndims, degree), faces=self.faces)
+        return s
+
+    def integrate(self, funcs, ischeme='gauss', degree=None, *, arguments=None):
+        ischeme, degree = StructuredTopology._parse(ischeme, degree)
+        return self.sample(ischeme, degree).integrate(funcs, arguments=arguments or {})
+
+    def integral(self, func, ischeme='gauss', degree=None):
+        ischeme, degree = StructuredTopology._parse(ischeme, degree)
+        return self.sample(ischeme, degree).integral(func)
+
+
 class StructuredTopology:
     'structured grid of shape `shape` (number of elements per dimension)'
 
@@ -90,6 +139,10 @@ class StructuredTopology:
 
     def __len__(self):
         return int(numpy.prod(self.shape))
+
+    @property
+    def boundary(self):
+        return _Boundary(self)
 
     # -- bases ---------------------------------------------------------------------------------------
 
