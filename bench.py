@@ -95,7 +95,7 @@ def run_reference(args):
     value = ndofs / t
     sample = '{}^3 elements ({} dofs) of the workload, general geometry; C port of the reference algorithm: threaded element loop + serial stable sort/unique/accumulate'.format(n, ndofs)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'impl': 'reference', 'metric': (METRIC_ELAST if args.workload == 'elasticity' else METRIC).replace('p=2', 'p={}'.format(args.degree)), 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload_name(args.n, args.degree, args.gpus), 'timed_sample': sample},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
@@ -334,7 +334,7 @@ def run_b200(args):
 
     if rank == 0:
         line = {
-            'metric': METRIC_ELAST if elast else METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
+            'metric': (METRIC_ELAST if elast else METRIC).replace('p=2', 'p={}'.format(p)), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': workload_name(n, p, world, elast), 'ndofs': ndofs_global, 'nnz_per_matrix': plan.nnz, 'nelems': plan.ntotal,
                        'step': ('one owner-computes assembly launch (every value written once; no zero-fill, no exchange)' if rows_path else
