@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) k_spmv(const BasisView B, const long long
 // values base += w, first column += 1 -- so per row a lane issues 4 streamed value loads + 4 gathers of x (L1) + 4 DFMA,
 // and the eight row sums are reduced TOGETHER by a transposing butterfly (9 shuffles for 8 rows instead of 40).  Runs that
 // touch the boundary of the box structure take the plain per-row code.
-template <int DIM>
+template <int DIM, int NCH>
 __global__ void __launch_bounds__(256, 3) k_spmv_run(const BasisView B, const int nbasis, const double* __restrict__ values, const double* __restrict__ x,
                                                       double* __restrict__ y, const unsigned char* __restrict__ mask, double* dot) {
   constexpr int LD = DIM - 1, R = 8;
@@ -156,7 +156,9 @@ __global__ void __launch_bounds__(256, 3) k_spmv_run(const BasisView B, const in
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nd1 = DIM > 1 ? B.ndofs[1] : 1, nd2 = DIM > 2 ? B.ndofs[2] : 1, ndl = B.ndofs[LD];
   double local = 0.;
-  int sig = -1, coff[4] = {0, 0, 0, 0};
+  int sig = -1, coff[NCH];
+#pragma unroll
+  for (int t = 0; t < NCH; t++) coff[t] = 0;
   for (long long g = blockIdx.x; g * (8 * R) < nbasis; g += gridDim.x) {
     const int I0 = (int)(g * (8 * R)) + warp * R;
     if (I0 >= nbasis) continue;
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(256, 3) k_spmv_run(const BasisView B, const in
     if (nsig != sig) {
       sig = nsig;
 #pragma unroll
-      for (int t = 0; t < 4; t++) {
+      for (int t = 0; t < NCH; t++) {
         const int k = min(t * 32 + lane, max(w - 1, 0));
         const int j2 = k % wid[2], q = k / wid[2], j1 = q % wid[1], j0 = q / wid[1];
         coff[t] = (j0 * nd1 + j1) * nd2 + j2;
@@ -203,34 +205,55 @@ __global__ void __launch_bounds__(256, 3) k_spmv_run(const BasisView B, const in
     }
     const long long base = row_start_basis<DIM>(B, i);
     const long long c0 = ((long long)lo[0] * nd1 + lo[1]) * nd2 + lo[2];
-    bool ok[4];
-    const double* pv[4];
-    const double* px[4];
+    bool ok[NCH];
+    const double* pv[NCH];
+    const double* px[NCH];
 #pragma unroll
-    for (int t = 0; t < 4; t++) {
+    for (int t = 0; t < NCH; t++) {
       ok[t] = t * 32 + lane < w;
       pv[t] = values + base + (ok[t] ? t * 32 + lane : w - 1);  // clamped into the row: loads need no predicate
       px[t] = x + c0 + coff[t];
     }
     double s[R];
+    if (NCH == 4) {
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-      double a0, a1, a2, a3, b0, b1, b2, b3;
-      asm volatile(
-          "ld.global.cs.f64 %0, [%8];\n\t"
-          "ld.global.cs.f64 %1, [%9];\n\t"
-          "ld.global.cs.f64 %2, [%10];\n\t"
-          "ld.global.cs.f64 %3, [%11];\n\t"
-          "ld.global.nc.f64 %4, [%12];\n\t"
-          "ld.global.nc.f64 %5, [%13];\n\t"
-          "ld.global.nc.f64 %6, [%14];\n\t"
-          "ld.global.nc.f64 %7, [%15];"
-          : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3), "=d"(b0), "=d"(b1), "=d"(b2), "=d"(b3)
-          : "l"(pv[0] + r * w), "l"(pv[1] + r * w), "l"(pv[2] + r * w), "l"(pv[3] + r * w), "l"(px[0] + r), "l"(px[1] + r), "l"(px[2] + r), "l"(px[3] + r));
-      double t = (ok[0] ? a0 : 0.) * b0;
-      t = fma(ok[1] ? a1 : 0., b1, t);
-      t = fma(ok[2] ? a2 : 0., b2, t);
-      s[r] = fma(ok[3] ? a3 : 0., b3, t);
+      for (int r = 0; r < R; r++) {
+        // the eight loads of a row in ONE asm block: issued back to back, all in flight before the first product waits
+        double a0, a1, a2, a3, b0, b1, b2, b3;
+        asm volatile(
+            "ld.global.cs.f64 %0, [%8];\n\t"
+            "ld.global.cs.f64 %1, [%9];\n\t"
+            "ld.global.cs.f64 %2, [%10];\n\t"
+            "ld.global.cs.f64 %3, [%11];\n\t"
+            "ld.global.nc.f64 %4, [%12];\n\t"
+            "ld.global.nc.f64 %5, [%13];\n\t"
+            "ld.global.nc.f64 %6, [%14];\n\t"
+            "ld.global.nc.f64 %7, [%15];"
+            : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3), "=d"(b0), "=d"(b1), "=d"(b2), "=d"(b3)
+            : "l"(pv[0] + r * w), "l"(pv[1 % NCH] + r * w), "l"(pv[2 % NCH] + r * w), "l"(pv[3 % NCH] + r * w), "l"(px[0] + r), "l"(px[1 % NCH] + r), "l"(px[2 % NCH] + r),
+              "l"(px[3 % NCH] + r));
+        double t = (ok[0] ? a0 : 0.) * b0;
+        t = fma(ok[1 % NCH] ? a1 : 0., b1, t);
+        t = fma(ok[2 % NCH] ? a2 : 0., b2, t);
+        s[r] = fma(ok[3 % NCH] ? a3 : 0., b3, t);
+      }
+    } else {
+      // short rows (degree 1: 27 entries): the loads of all eight rows first, then the products
+      double a[R][NCH], b[R][NCH];
+#pragma unroll
+      for (int r = 0; r < R; r++)
+#pragma unroll
+        for (int t = 0; t < NCH; t++) {
+          a[r][t] = __ldcs(pv[t] + r * w);
+          b[r][t] = __ldg(px[t] + r);
+        }
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        double acc = 0.;
+#pragma unroll
+        for (int t = 0; t < NCH; t++) acc = fma(ok[t] ? a[r][t] : 0., b[r][t], acc);
+        s[r] = acc;
+      }
     }
     // transposing butterfly: after the xor-16/8/4 steps a lane holds ONE row (row = lane >> 2), then two plain steps
     double t4[4], t2[2], v;
@@ -521,10 +544,16 @@ int spmv_launch(b2_ctx* ctx, const b2_pattern* p, const double* values, const do
       const bool plain = ctx->opts.count("spmv_plain") && ctx->opts["spmv_plain"];
       if (nc == 1 && maxrow <= 128 && !plain) {
         const int rblocks = grid_for(ctx, nbasis, 64);
+        const bool one = maxrow <= 32;  // one 32-entry chunk per row (degree 1)
         switch (basis->ndims) {
-          case 1: k_spmv_run<1><<<rblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, values, x, y, mask, dot); break;
-          case 2: k_spmv_run<2><<<rblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, values, x, y, mask, dot); break;
-          default: k_spmv_run<3><<<rblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, values, x, y, mask, dot); break;
+          case 1: k_spmv_run<1, 1><<<rblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, values, x, y, mask, dot); break;
+          case 2:
+            if (one) k_spmv_run<2, 1><<<rblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, values, x, y, mask, dot);
+            else k_spmv_run<2, 4><<<rblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, values, x, y, mask, dot);
+            break;
+          default:
+            if (one) k_spmv_run<3, 1><<<rblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, values, x, y, mask, dot);
+            else k_spmv_run<3, 4><<<rblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, values, x, y, mask, dot);
         }
       } else if (maxrow <= 384 && !plain) {
         const int rpw = 16, fblocks = grid_for(ctx, nbasis, 8 * rpw);

@@ -8,14 +8,15 @@ from bench import make_nodes
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 p = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+nc = int(sys.argv[3]) if len(sys.argv) > 3 else 1   # 3: elasticity matrix (vector-valued space)
 ctx = engine.Context.get(0)
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 b1 = [bspline.spline_basis_1d(n, p) for _ in range(3)]
-plan = engine.Plan(ctx, b1, points.tensor_gauss(3, 2 * p), make_nodes((n,) * 3))
+plan = engine.Plan(ctx, b1, points.tensor_gauss(3, 2 * p), make_nodes((n,) * 3), ncomp=nc)
 dev = torch.device('cuda', 0)
 K = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
 f = torch.empty(plan.ndofs, dtype=torch.float64, device=dev)
-plan.assemble_rows_device([engine.form_stiffness(3)], [engine.form_load(3)], [K], [f])
+plan.assemble_rows_device([engine.form_stiffness(3) if nc == 1 else engine.form_elasticity(3, 1., .5 / .3 - 1.)], [engine.form_load(3, nc)], [K], [f])
 x = torch.rand(plan.ndofs, dtype=torch.float64, device=dev)
 y = torch.empty_like(x)
 for _ in range(3):
@@ -29,7 +30,9 @@ for _ in range(reps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
-print(json.dumps({'kernel': 'k_spmv', 'n': n, 'p': p, 'ndofs': plan.ndofs, 'nnz': plan.nnz, 'ms': ms, 'algorithmic_GBps': (8 * plan.nnz + 16 * plan.ndofs) / ms * 1e-6}))
+print(json.dumps({'kernel': 'k_spmv', 'n': n, 'p': p, 'ncomp': nc, 'ndofs': plan.ndofs, 'nnz': plan.nnz, 'ms': ms, 'algorithmic_GBps': (8 * plan.nnz + 16 * plan.ndofs) / ms * 1e-6}))
+if nc != 1:
+    sys.exit(0)
 # Dirichlet on the first and last dof plane along x, CG to 1e-10
 nd = n + p
 mask = torch.zeros((nd, nd, nd), dtype=torch.uint8, device=dev)
