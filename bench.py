@@ -360,7 +360,7 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--n', type=int, default=128, help='elements per direction and GPU')
+    ap.add_argument('--n', '--nelems', dest='n', type=int, default=128, help='elements per direction and GPU (under torchrun spell it --nelems: the launcher claims the abbreviation --n)')
     ap.add_argument('--degree', type=int, default=2)
     ap.add_argument('--cpu-n', type=int, default=40, help='elements per direction of the bounded CPU sample')
     ap.add_argument('--e2e-steps', type=int, default=5)
