@@ -723,6 +723,12 @@ static int assemble_impl(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis*
     for (int m = 0; m < nmat; m++) B2_CUDA(ctx, cudaMemsetAsync(values_dev[m] + s0, 0, sizeof(double) * (size_t)(s1 - s0), ctx->stream));
     for (int v = 0; v < nvec; v++) B2_CUDA(ctx, cudaMemsetAsync(rhs_dev[v] + plane_begin * nb_plane, 0, sizeof(double) * (size_t)((plane_end - plane_begin) * nb_plane), ctx->stream));
     if (elem_begin == elem_end) return B2_OK;
+    if (plane_begin == 0 && plane_end == basis->ndofs_d[0] && kernel_opt != 1) {
+      // all planes (no row filter needed): the specialised element-scatter kernel where it applies -- e.g. C0 ('std')
+      // bases of degree 1 and 2, which the owner-computes kernel (maximal smoothness) does not cover
+      rc = launch_assemble_fast(ctx, B, Q, G, F, D_host, C_host, elem_begin, elem_end);
+      if (rc != B2_EUNSUPPORTED) return rc;
+    }
     return launch_assemble_generic(ctx, B, Q, G, F, elem_begin, elem_end, (int)plane_begin, (int)plane_end);
   }
   if (kernel_opt != 1) {

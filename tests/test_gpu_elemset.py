@@ -181,3 +181,28 @@ def test_invalid_arguments(ctx):
     with pytest.raises(_lib.B200Error):   # rational mode 2 without a rational geometry
         plan = engine.ElemSetPlan(ctx, b1, nodes=nodes, rules=rules, scale=numpy.ones(25), rational=2)
         plan.assemble_host([engine.form_mass(2)], [])
+
+
+@pytest.mark.parametrize('n,degree,depth', [(20, 2, 2), (12, 3, 1), (10, 4, 1)])
+def test_finite_cell_ball_properties(ctx, n, degree, depth):
+    # size-independent properties on a synthetic finite-cell workload (octree quadrature of scripts/time_elemset.py):
+    # partition of unity survives trimming and pruning: sum(M) = sum(f) = quadrature volume, K has zero row sums and is symmetric
+    import sys, os
+    sys.path.insert(0, os.path.join(util.ROOT, 'scripts'))
+    import time_elemset
+    elem_ids, qoff, qc, qw, ren, nbn = time_elemset.octree_ball(n, degree, depth)
+    b1 = util.bases_1d((n,) * 3, degree, 'spline')
+    v = numpy.linspace(-1, 1, n + 1)
+    nodes = numpy.stack(numpy.meshgrid(v, v, v, indexing='ij'))
+    plan = engine.ElemSetPlan(ctx, b1, nodes=nodes, elem_ids=elem_ids, qoff=qoff, qcoords=qc, qweights=qw, renumber=ren, nbasis_new=nbn)
+    (K, M), (f,) = plan.assemble_host([engine.form_stiffness(3), engine.form_mass(3)], [engine.form_load(3)])
+    vol = qw.sum() * (2. / n) ** 3
+    assert abs(M.sum() - vol) <= 1e-12 * vol and abs(f.sum() - vol) <= 1e-12 * vol
+    assert abs(vol - 4 / 3 * numpy.pi * .8 ** 3) < .02 * vol
+    rowptr, colidx = plan.csr_pattern()
+    import scipy.sparse
+    A = scipy.sparse.csr_matrix((K, colidx, rowptr), shape=(plan.ndofs,) * 2)
+    assert abs(A @ numpy.ones(plan.ndofs)).max() <= 1e-11 * abs(K).max()
+    assert abs(A - A.T).max() <= 1e-12 * abs(K).max()
+    # every kept function has support on a kept element: no empty rows
+    assert (numpy.diff(rowptr) > 0).all()
