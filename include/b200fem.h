@@ -233,6 +233,16 @@ int b2_assemble_elemset_host(b2_ctx* ctx, const b2_pattern* pattern, const b2_el
                              int nmat, const double* const* D_host, double* const* values_host,
                              int nvec, const double* const* C_host, double* const* rhs_host);
 
+/* Sample.eval / Sample.bind (src/nutils/sample.py:192-237, 959-975): evaluate at every point of the element set, in point
+ * order (elements in selection order, points in their stored / C-order tensor order): the physical coordinates x
+ * (float64[npoints][ndims]), the integration weight w |det J| -- surface measure on faces -- (float64[npoints]), and for
+ * `nfields` coefficient vectors coef_dev (float64[nfields][ndofs]) the discrete fields u = sum_i coef[i] N_i
+ * (values float64[npoints][nfields * ncomp]) and their physical gradients (float64[npoints][nfields * ncomp][ndims]).
+ * Any output pointer may be NULL.  This is what error norms, plots and pointwise post-processing of the reference's
+ * examples consume; with it an integral of ANY pointwise function of the solution is a dot product on the host. */
+int b2_evaluate_elemset_device(b2_ctx* ctx, const b2_elemset* elemset, const b2_quad* quad, const b2_geom* geom, int nfields, const double* coef_dev,
+                               double* x_dev, double* wdet_dev, double* values_dev, double* grads_dev);
+
 /* ---- device-resident matrix operations -------------------------------------------------------------
  * The assembled values stay in HBM (a 128^3 p=2 matrix is 2.1 GB: copying it to the host costs 10x the assembly);
  * these entry points are what nutils.matrix.Matrix offers on the result (src/nutils/matrix/_base.py), for BOTH kinds

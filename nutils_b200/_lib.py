@@ -92,6 +92,7 @@ SIGNATURES = {
     'b2_pattern_create_elemset': (ctypes.c_int, [c_vp, c_vp, p_vp]),
     'b2_assemble_elemset_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
     'b2_assemble_elemset_host': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
+    'b2_evaluate_elemset_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b2_spmv_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b2_diagonal_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     'b2_cg_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)]),

@@ -212,29 +212,23 @@ extern "C" int b2_pattern_create_elemset(b2_ctx* ctx, const b2_elemset* es, b2_p
   return B2_OK;
 }
 
-extern "C" int b2_assemble_elemset_device(b2_ctx* ctx, const b2_pattern* pattern, const b2_elemset* es, const b2_quad* quad, const b2_geom* geom,
-                                          int64_t sel_begin, int64_t sel_end, int nmat, const double* const* D_host, double* const* values_dev,
-                                          int nvec, const double* const* C_host, double* const* rhs_dev) {
-  if (!ctx || !pattern || !es || !geom) return b2_fail(ctx, B2_EINVAL, "null argument");
-  if (nmat < 0 || nmat > B2_MAX_FORMS || nvec < 0 || nvec > B2_MAX_FORMS) return b2_fail(ctx, B2_EINVAL, "0..4 matrix and vector forms per call");
-  if ((nmat && (!D_host || !values_dev)) || (nvec && (!C_host || !rhs_dev))) return b2_fail(ctx, B2_EINVAL, "null form argument");
-  if (pattern->elemset != es) return b2_fail(ctx, B2_EINVAL, "pattern was built for a different element set");
+// device views of an element set with its rule and geometry (shared by the assembly and the evaluation entry points)
+struct ESViews {
+  BasisView B;
+  QuadView Q;
+  GeomView G;
+  SplineGeomView SG;
+  ElemSetView E;
+};
+
+static int build_views(b2_ctx* ctx, const b2_pattern* pattern, const b2_elemset* es, const b2_quad* quad, const b2_geom* geom, ESViews* out) {
   const b2_basis* basis = es->basis;
-  const int nd = basis->ndims, nc = basis->ncomp;
+  const int nd = basis->ndims;
   if (!es->d_qoff && !quad) return b2_fail(ctx, B2_EINVAL, "the element set carries no points and no quadrature rule was given");
   if ((quad && quad->ndims != nd) || geom->ndims != nd) return b2_fail(ctx, B2_EINVAL, "dimension mismatch");
   for (int d = 0; d < nd; d++)
     if (geom->nel[d] != basis->nel[d]) return b2_fail(ctx, B2_EINVAL, "geometry and basis live on different topologies");
   if (es->rational == 2 && !(geom->gbasis && geom->d_wts)) return b2_fail(ctx, B2_EINVAL, "rational mode 2 needs a rational spline geometry");
-  if (sel_end < 0) sel_end = es->nsel;
-  if (sel_begin < 0 || sel_begin > sel_end || sel_end > es->nsel) return b2_fail(ctx, B2_EINVAL, "invalid element range");
-  for (int m = 0; m < nmat; m++)
-    if (!D_host[m] || !values_dev[m]) return b2_fail(ctx, B2_EINVAL, "null matrix form");
-  for (int v = 0; v < nvec; v++)
-    if (!C_host[v] || !rhs_dev[v]) return b2_fail(ctx, B2_EINVAL, "null vector form");
-  if (sel_begin == sel_end || (nmat == 0 && nvec == 0)) return B2_OK;
-  B2_CUDA(ctx, cudaSetDevice(ctx->device));
-
   BasisView B = basis->view();
   QuadView Q;
   memset(&Q, 0, sizeof(Q));
@@ -284,8 +278,50 @@ extern "C" int b2_assemble_elemset_device(b2_ctx* ctx, const b2_pattern* pattern
   }
   E.nbasis_new = es->nbasis_new;
   for (int d = 0; d < nd; d++) E.coeffs[d] = es->d_coeffs[d];
-  E.rowptr_b = pattern->d_rowptr_b;
-  E.colidx_b = pattern->d_colidx_b;
+  E.rowptr_b = pattern ? pattern->d_rowptr_b : nullptr;
+  E.colidx_b = pattern ? pattern->d_colidx_b : nullptr;
+
+  out->B = B;
+  out->Q = Q;
+  out->G = G;
+  out->SG = SG;
+  out->E = E;
+  return B2_OK;
+}
+
+extern "C" int b2_assemble_elemset_device(b2_ctx* ctx, const b2_pattern* pattern, const b2_elemset* es, const b2_quad* quad, const b2_geom* geom,
+                                          int64_t sel_begin, int64_t sel_end, int nmat, const double* const* D_host, double* const* values_dev,
+                                          int nvec, const double* const* C_host, double* const* rhs_dev) {
+  if (!ctx || !pattern || !es || !geom) return b2_fail(ctx, B2_EINVAL, "null argument");
+  if (nmat < 0 || nmat > B2_MAX_FORMS || nvec < 0 || nvec > B2_MAX_FORMS) return b2_fail(ctx, B2_EINVAL, "0..4 matrix and vector forms per call");
+  if ((nmat && (!D_host || !values_dev)) || (nvec && (!C_host || !rhs_dev))) return b2_fail(ctx, B2_EINVAL, "null form argument");
+  if (pattern->elemset != es) return b2_fail(ctx, B2_EINVAL, "pattern was built for a different element set");
+  const b2_basis* basis = es->basis;
+  const int nd = basis->ndims, nc = basis->ncomp;
+  if (!es->d_qoff && !quad) return b2_fail(ctx, B2_EINVAL, "the element set carries no points and no quadrature rule was given");
+  if ((quad && quad->ndims != nd) || geom->ndims != nd) return b2_fail(ctx, B2_EINVAL, "dimension mismatch");
+  for (int d = 0; d < nd; d++)
+    if (geom->nel[d] != basis->nel[d]) return b2_fail(ctx, B2_EINVAL, "geometry and basis live on different topologies");
+  if (es->rational == 2 && !(geom->gbasis && geom->d_wts)) return b2_fail(ctx, B2_EINVAL, "rational mode 2 needs a rational spline geometry");
+  if (sel_end < 0) sel_end = es->nsel;
+  if (sel_begin < 0 || sel_begin > sel_end || sel_end > es->nsel) return b2_fail(ctx, B2_EINVAL, "invalid element range");
+  for (int m = 0; m < nmat; m++)
+    if (!D_host[m] || !values_dev[m]) return b2_fail(ctx, B2_EINVAL, "null matrix form");
+  for (int v = 0; v < nvec; v++)
+    if (!C_host[v] || !rhs_dev[v]) return b2_fail(ctx, B2_EINVAL, "null vector form");
+  if (sel_begin == sel_end || (nmat == 0 && nvec == 0)) return B2_OK;
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  ESViews V;
+  {
+    int rcv = build_views(ctx, pattern, es, quad, geom, &V);
+    if (rcv != B2_OK) return rcv;
+  }
+  const BasisView& B = V.B;
+  const QuadView& Q = V.Q;
+  const GeomView& G = V.G;
+  const SplineGeomView& SG = V.SG;
+  const ElemSetView& E = V.E;
 
   FormView F;
   int rc = b2_upload_forms(ctx, nd, nc, nmat, D_host, values_dev, nvec, C_host, rhs_dev, &F);
@@ -325,4 +361,17 @@ extern "C" int b2_assemble_elemset_host(b2_ctx* ctx, const b2_pattern* pattern, 
   for (int v = 0; v < nvec; v++) B2_CUDA(ctx, cudaMemcpyAsync(rhs_host[v], rhs[v], bv, cudaMemcpyDeviceToHost, ctx->stream));
   B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return B2_OK;
+}
+
+extern "C" int b2_evaluate_elemset_device(b2_ctx* ctx, const b2_elemset* es, const b2_quad* quad, const b2_geom* geom, int nfields, const double* coef_dev,
+                                          double* x_dev, double* wdet_dev, double* values_dev, double* grads_dev) {
+  if (!ctx || !es || !geom) return b2_fail(ctx, B2_EINVAL, "null argument");
+  if (nfields < 0 || (nfields && !coef_dev) || ((values_dev || grads_dev) && !nfields)) return b2_fail(ctx, B2_EINVAL, "fields without coefficients");
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
+  ESViews V;
+  int rc = build_views(ctx, nullptr, es, quad, geom, &V);
+  if (rc != B2_OK) return rc;
+  if (es->nsel == 0) return B2_OK;
+  return launch_evaluate_elemset(ctx, V.B, V.Q, V.G, V.SG, V.E, es->d_qoff ? es->max_nq : V.Q.nqt, nfields, coef_dev, es->nbasis_new * es->basis->ncomp, x_dev, wdet_dev,
+                                 values_dev, grads_dev);
 }

@@ -29,6 +29,7 @@
 // thousands of points per element).  Context option "elemset_mma" = 0 selects the scalar FMA loop (kept for A/B parity).
 
 #include <algorithm>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -36,7 +37,21 @@ namespace {
 
 constexpr int EPT = 8;  // block entries per thread and pass
 
+// evaluation mode (b2_evaluate_elemset_device): instead of integrating, write per point the physical coordinates, the
+// weight w |det J| (surface measure on faces), and the values / physical gradients of discrete fields sum_i coef[i] N_i
+struct EvalView {
+  int nfields;            // 0: integration mode
+  const double* coef;     // [nfields][ndofs]
+  double* x;              // [npoints][DIM] or null
+  double* wdet;           // [npoints] or null
+  double* values;         // [npoints][nfields ncomp] or null
+  double* grads;          // [npoints][nfields ncomp][DIM] or null
+  long long ndofs;
+  int enabled;
+};
+
 struct ESParams {
+  EvalView ev;
   BasisView B;
   QuadView Q;
   GeomView G;
@@ -206,8 +221,8 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512, TCMAX == 4 ? 4 : 1) k_
       if (In < 0 || In >= E.nbasis_new) In = -1;
       sDof[a] = In;
       sS[a] = E.scale ? E.scale[I] : 1.;
-      sRow[a] = In >= 0 ? E.rowptr_b[In] : 0;
-      sLen[a] = In >= 0 ? (int)(E.rowptr_b[In + 1] - E.rowptr_b[In]) : 0;
+      sRow[a] = (In >= 0 && E.rowptr_b) ? E.rowptr_b[In] : 0;
+      sLen[a] = (In >= 0 && E.rowptr_b) ? (int)(E.rowptr_b[In + 1] - E.rowptr_b[In]) : 0;
     }
     for (int t = tid; t < P.F.nvec * ne; t += T) sV[t] = 0.;
     __syncthreads();
@@ -406,6 +421,62 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512, TCMAX == 4 ? 4 : 1) k_
           }
         }
         __syncthreads();
+        if (!MMA && P.ev.enabled) {
+          // evaluation mode: outputs of the chunk, no integration
+          const long long g0 = qbeg + q0;  // global index of the first point of the chunk
+          for (int ql = tid; ql < nqc; ql += T) {
+            if (P.ev.wdet) P.ev.wdet[g0 + ql] = sJ[ql * JS + DIM * DIM];
+            if (P.ev.x) {
+              const double* pt = sPt + ql * NA;
+              double xq[DIM];
+#pragma unroll
+              for (int i = 0; i < DIM; i++) xq[i] = 0.;
+              if (spline) {
+                double W = 0.;
+                for (int a = 0; a < nbg; a++) {
+                  double N, dxi[DIM];
+                  tensor_eval<DIM>(sAg + ql * DIM * pgm1 * 2, pgm1, sMg[a], N, dxi);
+                  W = fma(N, sX[DIM * nbg + a], W);
+#pragma unroll
+                  for (int i = 0; i < DIM; i++) xq[i] = fma(N, sX[i * nbg + a], xq[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < DIM; i++) xq[i] /= W;
+              } else {
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                  double f = 1.;
+#pragma unroll
+                  for (int d = 0; d < DIM; d++) f *= ((v >> (DIM - 1 - d)) & 1) ? pt[d] : 1. - pt[d];
+#pragma unroll
+                  for (int i = 0; i < DIM; i++) xq[i] = fma(sX[i * NV + v], f, xq[i]);
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < DIM; i++) P.ev.x[(g0 + ql) * DIM + i] = xq[i];
+            }
+          }
+          const int nfc = P.ev.nfields * nc;
+          for (int t = tid; t < nqc * nfc; t += T) {
+            const int ql = t / nfc, fc = t - ql * nfc, f = fc / nc, c = fc - f * nc;
+            double u[NA];
+#pragma unroll
+            for (int x = 0; x < NA; x++) u[x] = 0.;
+            for (int a = 0; a < nb; a++) {
+              if (sDof[a] < 0) continue;
+              const double ca = P.ev.coef[f * P.ev.ndofs + (long long)sDof[a] * nc + c];
+              const double* Ba = sB + (ql * nb + a) * NA;
+#pragma unroll
+              for (int x = 0; x < NA; x++) u[x] = fma(ca, Ba[x], u[x]);
+            }
+            if (P.ev.values) P.ev.values[(g0 + ql) * nfc + fc] = u[0];
+            if (P.ev.grads)
+#pragma unroll
+              for (int k = 0; k < DIM; k++) P.ev.grads[((g0 + ql) * nfc + fc) * DIM + k] = u[1 + k];
+          }
+          __syncthreads();
+          continue;
+        }
         // P4: block entries
         if constexpr (MMA) {
           const int warp = tid >> 5, lane = tid & 31;
@@ -529,6 +600,7 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512, TCMAX == 4 ? 4 : 1) k_
         }
         __syncthreads();
       }
+      if (!MMA && P.ev.enabled) break;  // evaluation mode: one sweep over the points, nothing to scatter
       // scatter: bisection of the column in the row's sorted list
       if constexpr (MMA) {
         const int warp = tid >> 5, lane = tid & 31;
@@ -650,9 +722,48 @@ int launch_dim(b2_ctx* ctx, ESParams& P, int max_nq) {
 
 }  // namespace
 
+int launch_evaluate_elemset(b2_ctx* ctx, const BasisView& B, const QuadView& Q, const GeomView& G, const SplineGeomView& SG, const ElemSetView& E, int max_nq,
+                            int nfields, const double* coef, long long ndofs, double* x, double* wdet, double* values, double* grads) {
+  ESParams P;
+  memset(&P, 0, sizeof(P));
+  P.ev.enabled = 1;
+  P.ev.nfields = nfields;
+  P.ev.coef = coef;
+  P.ev.ndofs = ndofs;
+  P.ev.x = x;
+  P.ev.wdet = wdet;
+  P.ev.values = values;
+  P.ev.grads = grads;
+  P.B = B;
+  P.Q = Q;
+  P.G = G;
+  P.SG = SG;
+  P.E = E;
+  P.sel_begin = 0;
+  P.sel_end = E.nsel;
+  P.pm1 = 1;
+  P.pgm1 = 1;
+  P.nbg = 1;
+  for (int d = 0; d < B.ndims; d++) {
+    P.pm1 = std::max(P.pm1, B.p[d] + 1);
+    if (SG.enabled) {
+      P.pgm1 = std::max(P.pgm1, SG.GB.p[d] + 1);
+      P.nbg *= SG.GB.p[d] + 1;
+    }
+  }
+  P.ne = B.nb * B.ncomp;
+  P.qchunk = 1;
+  switch (B.ndims) {
+    case 1: return launch_cfg<1, 0, 1>(ctx, P, max_nq);
+    case 2: return launch_cfg<2, 0, 1>(ctx, P, max_nq);
+    default: return launch_cfg<3, 0, 1>(ctx, P, max_nq);
+  }
+}
+
 int launch_assemble_elemset(b2_ctx* ctx, const BasisView& B, const QuadView& Q, const GeomView& G, const SplineGeomView& SG, const ElemSetView& E, const FormView& F,
                             long long sel_begin, long long sel_end, int max_nq) {
   ESParams P;
+  memset(&P.ev, 0, sizeof(P.ev));
   P.B = B;
   P.Q = Q;
   P.G = G;

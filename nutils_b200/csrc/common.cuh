@@ -239,6 +239,8 @@ int launch_assemble_fast(b2_ctx* ctx, const BasisView& B, const QuadView& Q, con
 // element-set path (assemble_elemset.cu, pattern_elemset.cu)
 int launch_assemble_elemset(b2_ctx* ctx, const BasisView& B, const QuadView& Q, const GeomView& G, const SplineGeomView& SG, const ElemSetView& E, const FormView& F,
                             long long sel_begin, long long sel_end, int max_nq);
+int launch_evaluate_elemset(b2_ctx* ctx, const BasisView& B, const QuadView& Q, const GeomView& G, const SplineGeomView& SG, const ElemSetView& E, int max_nq,
+                            int nfields, const double* coef, long long ndofs, double* x, double* wdet, double* values, double* grads);
 // counts[new basis row] = number of coupled columns (pass 0) / fills colidx_b (pass 1)
 int launch_pattern_elemset_impl(b2_ctx* ctx, const BasisView& B, const int* const* efirst, const int* const* elast, const long long* dofmap, const int* renumber,
                                 const unsigned char* selmask, long long nbasis_new, int pass, long long* counts_or_rowptr, int* colidx_b);

@@ -307,6 +307,7 @@ class ElemSetPlan:
             if rules is None:
                 raise ValueError('either ragged points (qoff, qcoords, qweights) or tensor rules are needed')
             rules = [(as_f64(x), as_f64(w)) for x, w in rules]
+            self.rules = rules
             nq = numpy.array([len(x) for x, w in rules], dtype=numpy.int32)
             h = c_vp()
             ctx.check(lib.b2_quad_create_tensor(ctx.handle, nd, nq.ctypes.data_as(_lib.p_i32), _lib.ptr_array([x for x, w in rules], _lib.p_f64),
@@ -380,6 +381,34 @@ class ElemSetPlan:
             return
         coef = as_f64(coef).ravel()
         self.ctx.check(self.ctx.lib.b2_elemset_set_coefficient(self.elemset, which, coef.ctypes.data_as(c_vp), len(coef)))
+
+    def evaluate(self, fields=(), x=True, weights=True, values=True, grads=False):
+        '''Sample.eval on the device (b2_evaluate_elemset_device): returns a dict with the requested arrays in point order:
+        'x' [npoints, ndims], 'weights' [npoints] (w |det J|), 'values' [npoints, nfields, ncomp] and 'grads'
+        [npoints, nfields, ncomp, ndims] of the discrete fields with coefficient vectors `fields` (each of length ndofs).'''
+        fields = [as_f64(f).ravel() for f in fields]
+        if any(len(f) != self.ndofs for f in fields):
+            raise ValueError('coefficient vectors must have length ndofs')
+        nf, nc, nd = len(fields), self.ncomp, self.ndims
+        npts = self.npoints if self.quad is None else self.nsel * int(numpy.prod([len(r[0]) for r in self.rules]))
+        ctx = self.ctx
+        bufs, out = {}, {}
+        coef = None
+        if nf:
+            coef = ctx.device_alloc(8 * nf * self.ndofs)
+            coef.from_host(numpy.concatenate(fields))
+        shapes = {'x': (npts, nd), 'weights': (npts,), 'values': (npts, nf, nc), 'grads': (npts, nf, nc, nd)}
+        want = {'x': x, 'weights': weights, 'values': values and nf, 'grads': grads and nf}
+        for key, shp in shapes.items():
+            if want[key]:
+                bufs[key] = ctx.device_alloc(8 * max(int(numpy.prod(shp)), 1))
+        ptr = lambda key: bufs[key].ptr if key in bufs else None
+        ctx.check(ctx.lib.b2_evaluate_elemset_device(ctx.handle, self.elemset, self.quad, self.geom, nf, None if coef is None else coef.ptr,
+                                                     ptr('x'), ptr('weights'), ptr('values'), ptr('grads')))
+        for key, buf in bufs.items():
+            n = int(numpy.prod(shapes[key]))
+            out[key] = buf.to_host()[:n].reshape(shapes[key]) if n else numpy.zeros(shapes[key])
+        return out
 
     def _make_basis(self, bases, ncomp):
         ctx, lib, nd = self.ctx, self.ctx.lib, len(bases)

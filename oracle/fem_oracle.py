@@ -150,9 +150,10 @@ def _basis_at(coeffs, setidx, start, degree, ndofs_d, idx, xi):
     return N, dN, dofs
 
 
-def element_data(prob, isel):
+def element_data(prob, isel, return_x=False):
     '''Everything the generated loop computes for one (selected) element before the integrand:
-    dofs[n_e] (-1: dropped by the pruned numbering), N[nq,n_e], grad[nq,n_e,ndims] (physical), wdet[nq].'''
+    dofs[n_e] (-1: dropped by the pruned numbering), N[nq,n_e], grad[nq,n_e,ndims] (physical), wdet[nq]
+    (and the physical coordinates x[nq,ndims] with return_x).'''
     nd = prob.ndims
     ielem = isel if prob.elem_ids is None else int(prob.elem_ids[isel])
     idx = numpy.unravel_index(ielem, prob.nelems)
@@ -172,12 +173,14 @@ def element_data(prob, isel):
         lin_d = [numpy.stack([-numpy.ones(len(xi)), numpy.ones(len(xi))]) for d in range(nd)]
         X = prob.nodes[(slice(None),) + tuple(slice(i, i + 2) for i in idx)].reshape(nd, -1)  # [ndims, 2^nd] C-order vertices
         J = numpy.stack([_tensor_points([lin_d[k] if k == d else lin_v[k] for k in range(nd)], len(xi)) @ X.T for d in range(nd)], axis=-1)  # [nq, i, k] = dx_i/dxi_k
+        xphys = _tensor_points(lin_v, len(xi)) @ X.T
     else:
         g = prob.geom_spline
         Ng, dNg, gdofs = _basis_at(g['coeffs'], g['setidx'], g['start'], g['degree'], g['ndofs_d'], idx, xi)
         ctrl = numpy.asarray(g['ctrl'], dtype=float)[:, gdofs]  # [ndims, n_g]
         if g.get('weights') is None:
             J = numpy.einsum('qak,ia->qik', dNg, ctrl)
+            xphys = Ng @ ctrl.T
         else:
             wts = numpy.asarray(g['weights'], dtype=float)[gdofs]
             Wg = Ng @ wts
@@ -186,6 +189,7 @@ def element_data(prob, isel):
             dXh = numpy.einsum('qak,ia->qik', dNg, ctrl * wts)
             x = Xh / Wg[:, None]
             J = (dXh - x[:, :, None] * dWg[:, None, :]) / Wg[:, None, None]
+            xphys = x
     if prob.scale is not None:
         c = prob.scale[dofs]
         N = N * c
@@ -206,6 +210,8 @@ def element_data(prob, isel):
     if prob.renumber is not None:
         dofs = prob.renumber[dofs]
         dofs = numpy.where((dofs >= 0) & (dofs < prob.nbasis_new), dofs, -1)
+    if return_x:
+        return dofs, N, grad, w * meas, xphys
     return dofs, N, grad, w * meas
 
 
@@ -258,6 +264,23 @@ def element_vector(form, N, grad, wdet, ncomp=1):
         B = numpy.concatenate([N[:, :, None], grad], axis=-1)
         return numpy.einsum('qax,cx,q->ac', B, c, wdet).ravel()
     raise ValueError(kind)
+
+
+def evaluate(prob, fields=()):
+    '''Sample.eval (sample.py:192-215, 959-975) in point order: x[npoints, ndims], weights w |det J| [npoints], and for every
+    coefficient vector in `fields` the discrete field values [npoints, nfields, ncomp] and physical gradients
+    [npoints, nfields, ncomp, ndims].'''
+    nc = prob.ncomp
+    xs, ws, vals, grads = [], [], [], []
+    for isel in range(prob.nsel):
+        dofs, N, grad, wdet, x = element_data(prob, isel, return_x=True)
+        xs.append(x)
+        ws.append(wdet)
+        vdofs = (dofs[:, None] * nc + numpy.arange(nc)[None, :])            # [n_e, ncomp]
+        C = numpy.stack([numpy.asarray(f, dtype=float)[vdofs] for f in fields]) if len(fields) else numpy.zeros((0,) + vdofs.shape)
+        vals.append(numpy.einsum('qa,fac->qfc', N, C))
+        grads.append(numpy.einsum('qak,fac->qfck', grad, C))
+    return numpy.concatenate(xs), numpy.concatenate(ws), numpy.concatenate(vals), numpy.concatenate(grads)
 
 
 def coo_to_csr(values, rows, cols, nrows, ncols):

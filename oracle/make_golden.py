@@ -339,6 +339,26 @@ def varcoef_case(name, n, degree, warp=.25, seed=0):
                 coef=_coef_g(xq), K_values=kv, rowptr=rp, colidx=ci, F=f)
 
 
+def eval_case(name, n, degree, ncomp=1, warp=.25, seed=0):
+    'Sample.eval of the reference (sample.py:192-215): coordinates, w |det J|, a discrete field and its gradient at the Gauss points'
+    ndims = len(n)
+    verts = _verts(n, 'graded', seed)
+    X = _nodes(verts, warp, seed)
+    topo, geom0 = mesh.rectilinear(verts)
+    geom = _geom(topo, X) if warp else geom0
+    basis = topo.basis('spline', degree=degree)
+    rng = numpy.random.RandomState(seed + 100)
+    coefs = rng.rand(len(basis), ncomp) - .5
+    u = (basis[:, None] * coefs).sum(0)                        # [ncomp]
+    qd = 2 * degree
+    smp = topo.sample('gauss', qd)
+    x, w, val, grad = smp.eval([geom, function.J(geom), u, function.grad(u, geom)])
+    # the reference multiplies J by the point weights only inside integrals: do it here
+    weights = numpy.concatenate([numpy.asarray(smp.points.get(i).weights) for i in range(len(topo))])
+    return dict(kind='elemset_eval', name=name, ndims=ndims, nelems=numpy.array(n), degree=degree, btype='spline', qdegree=qd, nodes=X, ndofs=len(basis) * ncomp, ncomp=ncomp,
+                coefs=coefs.ravel(), x=x, wdet=w * weights, values=val, grads=grad)
+
+
 def known_answer_mass_1d():
     # tests/test_function.py:1574-1585 (known-answer COO of a 1-D p=1 mass matrix)
     topo, geom = mesh.line([0, 1, 2], bnames=['a', 'b'], space='X')
@@ -381,6 +401,8 @@ CASES = {
     'bnd1d_right_p2': lambda: boundary_case('bnd1d_right_p2', (6,), 2, 'right'),
     'varcoef3d_p2': lambda: varcoef_case('varcoef3d_p2', (4, 3, 3), 2, seed=11),
     'varcoef2d_p3': lambda: varcoef_case('varcoef2d_p3', (5, 4), 3, seed=12),
+    'eval3d_p2': lambda: eval_case('eval3d_p2', (3, 4, 2), 2, seed=13),
+    'eval2d_p3_vec': lambda: eval_case('eval2d_p3_vec', (4, 3), 3, ncomp=2, seed=14),
     'elast3d_p2_warp': lambda: elasticity_case('elast3d_p2_warp', (3, 3, 2), 2, warp=.3, seed=7),  # config 3 at toy size
 }
 
@@ -396,7 +418,7 @@ def main():
         d = f()
         path = os.path.join(OUT, name + '.npz')
         numpy.savez_compressed(path, **d)
-        print('{:20s} ndofs={:6d} nnz={:8d} {:8.1f} kB'.format(name, int(d['ndofs']), len(d['colidx']), os.path.getsize(path) / 1e3))
+        print('{:20s} ndofs={:6d} nnz={:8d} {:8.1f} kB'.format(name, int(d['ndofs']), len(d['colidx']) if 'colidx' in d else 0, os.path.getsize(path) / 1e3))
 
 
 if __name__ == '__main__':

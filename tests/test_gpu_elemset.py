@@ -206,3 +206,36 @@ def test_finite_cell_ball_properties(ctx, n, degree, depth):
     assert abs(A - A.T).max() <= 1e-12 * abs(K).max()
     # every kept function has support on a kept element: no empty rows
     assert (numpy.diff(rowptr) > 0).all()
+
+
+@pytest.mark.parametrize('name', util.eval_golden_names())
+def test_evaluate_golden(ctx, name):
+    # b2_evaluate_elemset_device against Sample.eval of the reference
+    g = util.load_golden(name)
+    prob = util.elemset_problem_from_golden(g)
+    plan = _plan(ctx, prob)
+    out = plan.evaluate([g['coefs']], grads=True)
+    assert util.relerr(out['x'], g['x']) <= TOL and util.relerr(out['weights'], g['wdet']) <= TOL
+    assert util.relerr(out['values'][:, 0].reshape(g['values'].shape), g['values']) <= TOL
+    assert util.relerr(out['grads'][:, 0].reshape(g['grads'].shape), g['grads']) <= TOL
+
+
+@pytest.mark.parametrize('name', ['fcm3d_ball_p2', 'nurbs_plate_p4', 'bnd3d_right_p2_warp', 'fcm2d_plate_p2', 'bnd1d_right_p2'])
+def test_evaluate_against_oracle(ctx, name):
+    # ragged cut-cell points, rational functions on a NURBS geometry, boundary faces (weights = surface measure), two fields
+    g = util.load_golden(name)
+    prob = util.elemset_problem_from_golden(g)
+    plan = _plan(ctx, prob)
+    rng = numpy.random.RandomState(3)
+    fields = [rng.rand(plan.ndofs) - .5, numpy.ones(plan.ndofs)]
+    x, w, v, gr = fem_oracle.evaluate(prob, fields)
+    out = plan.evaluate(fields, grads=True)
+    assert util.relerr(out['x'], x) <= TOL and util.relerr(out['weights'], w) <= TOL
+    assert util.relerr(out['values'], v) <= TOL
+    assert abs(out['grads'] - gr).max() <= 1e-10 * max(abs(gr).max(), 1.)
+    if not prob.rational or True:
+        # partition of unity: the all-ones field evaluates to 1 with zero gradient (NURBS included)
+        assert abs(out['values'][:, 1] - 1.).max() <= 1e-12
+        assert abs(out['grads'][:, 1]).max() <= 1e-9
+    # weights only (no fields): the measure of the sample
+    assert abs(plan.evaluate(x=False)['weights'].sum() - w.sum()) <= 1e-12 * abs(w.sum())

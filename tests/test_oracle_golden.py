@@ -69,6 +69,17 @@ def test_numpy_oracle_elemset(name):
         assert abs(mats[1][0].sum() - float(g['volume'])) <= 1e-13 * abs(float(g['volume']))
 
 
+@pytest.mark.parametrize('name', util.eval_golden_names())
+def test_numpy_oracle_eval(name):
+    # Sample.eval of the reference: coordinates, w |det J|, a discrete field and its physical gradient at the Gauss points
+    g = util.load_golden(name)
+    prob = util.elemset_problem_from_golden(g)
+    x, w, v, gr = fem_oracle.evaluate(prob, [g['coefs']])
+    assert util.relerr(x, g['x']) <= 1e-13 and util.relerr(w, g['wdet']) <= 1e-13
+    assert util.relerr(v[:, 0].reshape(g['values'].shape), g['values']) <= 1e-13
+    assert util.relerr(gr[:, 0].reshape(g['grads'].shape), g['grads']) <= 1e-13
+
+
 def test_known_answer_mass_1d():
     # tests/test_function.py:1574-1585 of the reference: exact COO of the 1-D p=1 mass matrix
     g = util.load_golden('mass1d_known')

@@ -30,7 +30,12 @@ def golden_names():
 
 def elemset_golden_names():
     'element-set cases: trimmed topologies with ragged points and pruned numbering, NURBS'
-    return [n for n in _all_golden_names() if _kind(n).startswith('elemset')]
+    return [n for n in _all_golden_names() if _kind(n).startswith('elemset') and _kind(n) != 'elemset_eval']
+
+
+def eval_golden_names():
+    'Sample.eval cases: coordinates, weights, field values and gradients at the points'
+    return [n for n in _all_golden_names() if _kind(n) == 'elemset_eval']
 
 
 def load_golden(name):
