@@ -117,6 +117,39 @@ class Sample:
             x += phi[None, :, None] * X.T[:, None, :]
         return x
 
+    def _esplan(self, space, geom, face):
+        'engine.ElemSetPlan of this sample for one side (or the volume: face None), cached; returns (plan, elem_ids, xi)'
+        key = id(space), id(geom), face
+        entry = self._esplans.get(key)
+        if entry is None or entry[1] is not geom.nodes:
+            ctx = engine.Context.get(self.device)
+            if face is None:
+                xi = numpy.stack([g.ravel() for g in numpy.meshgrid(*[r[0] for r in self.rules], indexing='ij')], -1)
+                elem_ids = numpy.arange(self.nelems)
+                plan = engine.ElemSetPlan(ctx, space.bases1d, nodes=geom.nodes, ncomp=space.ncomp, rules=self.rules)
+            else:
+                elem_ids, xi, w = self._face_tables(*face)
+                nq = len(w)
+                qoff = numpy.arange(len(elem_ids) + 1, dtype=numpy.int64) * nq
+                plan = engine.ElemSetPlan(ctx, space.bases1d, nodes=geom.nodes, ncomp=space.ncomp, elem_ids=elem_ids, qoff=qoff,
+                                          qcoords=numpy.tile(xi, (len(elem_ids), 1)), qweights=numpy.tile(w, len(elem_ids)))
+                plan.set_faces(numpy.full(len(elem_ids), face[0], dtype=numpy.int8))
+            entry = self._esplans[key] = plan, geom.nodes, elem_ids, xi
+        return entry[0], entry[2], entry[3]
+
+    def eval_fields(self, space, geom, fields=(), grads=False):
+        '''``Sample.eval`` for discrete fields (sample.py:192-215): a dict with the physical coordinates 'x' [npoints, ndims],
+        the integration weights 'weights' [npoints] (w |det J|; on a boundary sample the surface measure), the 'values'
+        [npoints, nfields, ncomp] of u_f = sum_i fields[f][i] N_i and, on request, their physical 'grads'.  Points are
+        ordered like the reference orders them (elements, then the tensor points in C order).  With these an integral of
+        any pointwise function of the solution is ``(weights * g(x, values)).sum()``.'''
+        faces = self.faces if self.faces is not None else (None,)
+        outs = []
+        for face in faces:
+            plan, _, _ = self._esplan(space, geom, face)
+            outs.append(plan.evaluate(list(fields), grads=grads))
+        return {k: numpy.concatenate([o[k] for o in outs]) for k in outs[0]}
+
     def _evaluate_elemset(self, integrals):
         'boundary integrals and integrands with coefficient functions: engine.ElemSetPlan, one plan per side'
         from . import matrix as _matrix
@@ -134,23 +167,7 @@ class Sample:
         out = [None] * len(integrals)
         ctx = engine.Context.get(self.device)
         for face in faces:
-            key = id(space), id(geom), face
-            entry = self._esplans.get(key)
-            if entry is None or entry[1] is not geom.nodes:
-                if face is None:
-                    nq = int(numpy.prod([len(r[0]) for r in self.rules]))
-                    xi = numpy.stack([g.ravel() for g in numpy.meshgrid(*[r[0] for r in self.rules], indexing='ij')], -1)
-                    elem_ids = numpy.arange(self.nelems)
-                    plan = engine.ElemSetPlan(ctx, space.bases1d, nodes=geom.nodes, ncomp=space.ncomp, rules=self.rules)
-                else:
-                    elem_ids, xi, w = self._face_tables(*face)
-                    nq = len(w)
-                    qoff = numpy.arange(len(elem_ids) + 1, dtype=numpy.int64) * nq
-                    plan = engine.ElemSetPlan(ctx, space.bases1d, nodes=geom.nodes, ncomp=space.ncomp, elem_ids=elem_ids, qoff=qoff,
-                                              qcoords=numpy.tile(xi, (len(elem_ids), 1)), qweights=numpy.tile(w, len(elem_ids)))
-                    plan.set_faces(numpy.full(len(elem_ids), face[0], dtype=numpy.int8))
-                entry = self._esplans[key] = plan, geom.nodes, elem_ids, xi
-            plan, _, elem_ids, xi = entry
+            plan, elem_ids, xi = self._esplan(space, geom, face)
             xq = None
             for slot, ks in (('matrix', mats), ('vector', vecs)):
                 for j, k in enumerate(ks):
