@@ -339,52 +339,70 @@ __global__ void __launch_bounds__(256, 3) k_spmv_fast(const BasisView B, const i
       const long long base = row_start_basis<DIM>(B, i) * nc * nc;
       const long long c0 = (((long long)lo[0] * nd1 + lo[1]) * nd2 + lo[2]) * nc;
       const double* xr = x + c0;
-      for (int c = 0; c < nc; c++) {
-        const long long row = (long long)I * nc + c;
-        if (mask && mask[row]) {
-          if (lane == 0) y[row] = 0.;
-          continue;
-        }
-        const double* v = values + base + (long long)c * rowlen;
-        double s = 0.;
-        if (rowlen > 0) {
-          // Addresses are clamped into the row instead of predicating the loads, and the eight loads of a group of four
-          // chunks sit in ONE asm block: they are issued back to back and are all in flight before the first product waits
-          // (ptxas otherwise serialises load pair -> DFMA -> load pair: four HBM round trips per row instead of one).
+      // The ncomp dof rows (I, c) of a basis function couple with the SAME columns: x is gathered once per group of four
+      // chunks and used for every component.  Addresses are clamped into the row instead of predicating the loads, and the
+      // loads of a group sit in asm blocks issued back to back, so they are all in flight before the first product waits
+      // (ptxas otherwise serialises load pair -> DFMA -> load pair: one HBM round trip per chunk instead of one per group).
+      double s[3] = {0., 0., 0.};
+      if (rowlen > 0) {
 #pragma unroll
-          for (int t0 = 0; t0 < NCH; t0 += 4) {
-            const double* pa[4];
-            const double* pb[4];
-            bool ok[4];
+        for (int t0 = 0; t0 < NCH; t0 += 4) {
+          const double* pb[4];
+          int ka[4];
+          bool ok[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const int k = (t0 + u) * 32 + lane;
-              ok[u] = k < rowlen;
-              pa[u] = v + (ok[u] ? k : rowlen - 1);
-              pb[u] = xr + (ok[u] ? coff[t0 + u] : 0);
+          for (int u = 0; u < 4; u++) {
+            const int k = (t0 + u) * 32 + lane;
+            ok[u] = k < rowlen;
+            ka[u] = ok[u] ? k : rowlen - 1;
+            pb[u] = xr + (ok[u] ? coff[t0 + u] : 0);
+          }
+          double a[3][4], b0, b1, b2, b3;
+          const double* v0 = values + base;
+          asm volatile(
+              "ld.global.cs.f64 %0, [%8];\n\t"
+              "ld.global.cs.f64 %1, [%9];\n\t"
+              "ld.global.cs.f64 %2, [%10];\n\t"
+              "ld.global.cs.f64 %3, [%11];\n\t"
+              "ld.global.nc.f64 %4, [%12];\n\t"
+              "ld.global.nc.f64 %5, [%13];\n\t"
+              "ld.global.nc.f64 %6, [%14];\n\t"
+              "ld.global.nc.f64 %7, [%15];"
+              : "=d"(a[0][0]), "=d"(a[0][1]), "=d"(a[0][2]), "=d"(a[0][3]), "=d"(b0), "=d"(b1), "=d"(b2), "=d"(b3)
+              : "l"(v0 + ka[0]), "l"(v0 + ka[1]), "l"(v0 + ka[2]), "l"(v0 + ka[3]), "l"(pb[0]), "l"(pb[1]), "l"(pb[2]), "l"(pb[3]));
+#pragma unroll
+          for (int c = 1; c < 3; c++) {
+            if (c < nc) {
+              const double* vc = values + base + (long long)c * rowlen;
+              asm volatile(
+                  "ld.global.cs.f64 %0, [%4];\n\t"
+                  "ld.global.cs.f64 %1, [%5];\n\t"
+                  "ld.global.cs.f64 %2, [%6];\n\t"
+                  "ld.global.cs.f64 %3, [%7];"
+                  : "=d"(a[c][0]), "=d"(a[c][1]), "=d"(a[c][2]), "=d"(a[c][3])
+                  : "l"(vc + ka[0]), "l"(vc + ka[1]), "l"(vc + ka[2]), "l"(vc + ka[3]));
             }
-            double a0, a1, a2, a3, b0, b1, b2, b3;
-            asm volatile(
-                "ld.global.cs.f64 %0, [%8];\n\t"
-                "ld.global.cs.f64 %1, [%9];\n\t"
-                "ld.global.cs.f64 %2, [%10];\n\t"
-                "ld.global.cs.f64 %3, [%11];\n\t"
-                "ld.global.nc.f64 %4, [%12];\n\t"
-                "ld.global.nc.f64 %5, [%13];\n\t"
-                "ld.global.nc.f64 %6, [%14];\n\t"
-                "ld.global.nc.f64 %7, [%15];"
-                : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3), "=d"(b0), "=d"(b1), "=d"(b2), "=d"(b3)
-                : "l"(pa[0]), "l"(pa[1]), "l"(pa[2]), "l"(pa[3]), "l"(pb[0]), "l"(pb[1]), "l"(pb[2]), "l"(pb[3]));
-            s = fma(ok[0] ? a0 : 0., b0, s);
-            s = fma(ok[1] ? a1 : 0., b1, s);
-            s = fma(ok[2] ? a2 : 0., b2, s);
-            s = fma(ok[3] ? a3 : 0., b3, s);
+          }
+          const double bb[4] = {ok[0] ? b0 : 0., ok[1] ? b1 : 0., ok[2] ? b2 : 0., ok[3] ? b3 : 0.};
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            if (c < nc) {
+#pragma unroll
+              for (int u = 0; u < 4; u++) s[c] = fma(a[c][u], bb[u], s[c]);
+            }
           }
         }
-        s = warp_sum(s);
-        if (lane == 0) {
-          y[row] = s;
-          if (dot) local = fma(x[row], s, local);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        if (c < nc) {
+          const long long row = (long long)I * nc + c;
+          const double sc = warp_sum(s[c]);
+          if (lane == 0) {
+            const bool fixed = mask && mask[row];
+            y[row] = fixed ? 0. : sc;
+            if (dot && !fixed) local = fma(x[row], sc, local);
+          }
         }
       }
       // next row of this warp: I + 8
