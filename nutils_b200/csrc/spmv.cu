@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256, 3) k_spmv_run(const BasisView B, const in
 // 64-bit divisions), and (b) the column OFFSETS of a lane's entries relative to the first coupled dof depend only on the
 // box widths (wid0, wid1, wid2), which are the same for all interior rows: they are kept in registers and recomputed only
 // when the widths change.  Per entry: one streamed load, one add, one gather, one DFMA.
-template <int DIM, int NCH>
+template <int DIM, int NCH, bool ALL>
 __global__ void __launch_bounds__(256, 3) k_spmv_fast(const BasisView B, const int nbasis, const int rows_per_warp, const double* __restrict__ values,
                                                     const double* __restrict__ x, double* __restrict__ y, const unsigned char* __restrict__ mask, double* dot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -344,7 +344,42 @@ __global__ void __launch_bounds__(256, 3) k_spmv_fast(const BasisView B, const i
       // loads of a group sit in asm blocks issued back to back, so they are all in flight before the first product waits
       // (ptxas otherwise serialises load pair -> DFMA -> load pair: one HBM round trip per chunk instead of one per group).
       double s[3] = {0., 0., 0.};
-      if (rowlen > 0) {
+      if (ALL && rowlen > 0) {
+        // scalar space, long rows (degree 3): the loads of ALL chunks of the row are issued before the first product, one
+        // HBM round trip per row instead of one per group of four chunks
+        double a[NCH], b[NCH];
+        bool ok[NCH];
+#pragma unroll
+        for (int t0 = 0; t0 < NCH; t0 += 4) {
+          const double* pa[4];
+          const double* pb[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int k = (t0 + u) * 32 + lane;
+            ok[t0 + u] = k < rowlen;
+            pa[u] = values + base + (ok[t0 + u] ? k : rowlen - 1);
+            pb[u] = xr + (ok[t0 + u] ? coff[t0 + u] : 0);
+          }
+          asm volatile(
+              "ld.global.cs.f64 %0, [%8];\n\t"
+              "ld.global.cs.f64 %1, [%9];\n\t"
+              "ld.global.cs.f64 %2, [%10];\n\t"
+              "ld.global.cs.f64 %3, [%11];\n\t"
+              "ld.global.nc.f64 %4, [%12];\n\t"
+              "ld.global.nc.f64 %5, [%13];\n\t"
+              "ld.global.nc.f64 %6, [%14];\n\t"
+              "ld.global.nc.f64 %7, [%15];"
+              : "=d"(a[t0]), "=d"(a[t0 + 1]), "=d"(a[t0 + 2]), "=d"(a[t0 + 3]), "=d"(b[t0]), "=d"(b[t0 + 1]), "=d"(b[t0 + 2]), "=d"(b[t0 + 3])
+              : "l"(pa[0]), "l"(pa[1]), "l"(pa[2]), "l"(pa[3]), "l"(pb[0]), "l"(pb[1]), "l"(pb[2]), "l"(pb[3]));
+        }
+        double s0 = 0., s1 = 0.;
+#pragma unroll
+        for (int t = 0; t < NCH; t += 2) {
+          s0 = fma(ok[t] ? a[t] : 0., b[t], s0);
+          s1 = fma(ok[t + 1] ? a[t + 1] : 0., b[t + 1], s1);
+        }
+        s[0] = s0 + s1;
+      } else if (rowlen > 0) {
 #pragma unroll
         for (int t0 = 0; t0 < NCH; t0 += 4) {
           const double* pb[4];
@@ -577,14 +612,16 @@ int spmv_launch(b2_ctx* ctx, const b2_pattern* p, const double* values, const do
         const int rpw = 16, fblocks = grid_for(ctx, nbasis, 8 * rpw);
         const bool small = maxrow <= 128;
         switch (basis->ndims) {
-          case 1: k_spmv_fast<1, 4><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot); break;
+          case 1: k_spmv_fast<1, 4, false><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot); break;
           case 2:
-            if (small) k_spmv_fast<2, 4><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot);
-            else k_spmv_fast<2, 12><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot);
+            if (small) k_spmv_fast<2, 4, false><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot);
+            else if (nc == 1) k_spmv_fast<2, 12, true><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot);
+            else k_spmv_fast<2, 12, false><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot);
             break;
           default:
-            if (small) k_spmv_fast<3, 4><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot);
-            else k_spmv_fast<3, 12><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot);
+            if (small) k_spmv_fast<3, 4, false><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot);
+            else if (nc == 1) k_spmv_fast<3, 12, true><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot);
+            else k_spmv_fast<3, 12, false><<<fblocks, 256, 0, ctx->stream>>>(B, (int)nbasis, rpw, values, x, y, mask, dot);
         }
       } else {
         switch (basis->ndims) {
