@@ -128,6 +128,25 @@ def _devptr(x):
     return c_vp(int(x))
 
 
+def _create_basis(ctx, bases, ncomp):
+    'b2_basis handle of a tensor-product space given as per-dimension bspline.Basis1D tables'
+    if any(b.periodic for b in bases):
+        raise _lib.B200Error('unsupported configuration: periodic bases')
+    nd = len(bases)
+    nelems = numpy.array([b.nelems for b in bases], dtype=numpy.int64)
+    degree = numpy.array([b.degree for b in bases], dtype=numpy.int32)
+    nsets = numpy.array([len(b.coeffs) for b in bases], dtype=numpy.int32)
+    ndofs = numpy.array([b.ndofs for b in bases], dtype=numpy.int64)
+    coeffs = [as_f64(b.coeffs) for b in bases]
+    setidx = [numpy.ascontiguousarray(b.setidx, dtype=numpy.int32) for b in bases]
+    start = [numpy.ascontiguousarray(b.start, dtype=numpy.int64) for b in bases]
+    h = c_vp()
+    ctx.check(ctx.lib.b2_basis_create(ctx.handle, nd, nelems.ctypes.data_as(_lib.p_i64), degree.ctypes.data_as(_lib.p_i32), nsets.ctypes.data_as(_lib.p_i32),
+                                      _lib.ptr_array(coeffs, _lib.p_f64), _lib.ptr_array(setidx, _lib.p_i32), _lib.ptr_array(start, _lib.p_i64),
+                                      ndofs.ctypes.data_as(_lib.p_i64), int(ncomp), ctypes.byref(h)))
+    return h
+
+
 class Plan:
     '''Device-resident description of one structured assembly problem:
     spline space (b2_basis) + tensor quadrature (b2_quad) + nodal geometry (b2_geom)
@@ -152,19 +171,7 @@ class Plan:
             raise ValueError('nodes must have shape (ndims, nelems_0+1, ...), got {}'.format(nodes.shape))
         self.nodes = nodes
         nelems = numpy.array(self.nelems, dtype=numpy.int64)
-        degree = numpy.array([b.degree for b in bases], dtype=numpy.int32)
-        nsets = numpy.array([len(b.coeffs) for b in bases], dtype=numpy.int32)
-        ndofs = numpy.array([b.ndofs for b in bases], dtype=numpy.int64)
-        coeffs = [as_f64(b.coeffs) for b in bases]
-        setidx = [numpy.ascontiguousarray(b.setidx, dtype=numpy.int32) for b in bases]
-        start = [numpy.ascontiguousarray(b.start, dtype=numpy.int64) for b in bases]
-        if any(b.periodic for b in bases):
-            raise _lib.B200Error('unsupported configuration: periodic bases')
-        h = c_vp()
-        ctx.check(lib.b2_basis_create(ctx.handle, nd, nelems.ctypes.data_as(_lib.p_i64), degree.ctypes.data_as(_lib.p_i32), nsets.ctypes.data_as(_lib.p_i32),
-                                      _lib.ptr_array(coeffs, _lib.p_f64), _lib.ptr_array(setidx, _lib.p_i32), _lib.ptr_array(start, _lib.p_i64),
-                                      ndofs.ctypes.data_as(_lib.p_i64), self.ncomp, ctypes.byref(h)))
-        self.basis = h
+        self.basis = h = _create_basis(ctx, bases, self.ncomp)
         self._fin = [weakref.finalize(self, lib.b2_basis_destroy, h)]
         nq = numpy.array([len(x) for x, w in self.rules], dtype=numpy.int32)
         h = c_vp()
@@ -411,21 +418,8 @@ class ElemSetPlan:
         return out
 
     def _make_basis(self, bases, ncomp):
-        ctx, lib, nd = self.ctx, self.ctx.lib, len(bases)
-        if any(b.periodic for b in bases):
-            raise _lib.B200Error('unsupported configuration: periodic bases')
-        nelems = numpy.array([b.nelems for b in bases], dtype=numpy.int64)
-        degree = numpy.array([b.degree for b in bases], dtype=numpy.int32)
-        nsets = numpy.array([len(b.coeffs) for b in bases], dtype=numpy.int32)
-        ndofs = numpy.array([b.ndofs for b in bases], dtype=numpy.int64)
-        coeffs = [as_f64(b.coeffs) for b in bases]
-        setidx = [numpy.ascontiguousarray(b.setidx, dtype=numpy.int32) for b in bases]
-        start = [numpy.ascontiguousarray(b.start, dtype=numpy.int64) for b in bases]
-        h = c_vp()
-        ctx.check(lib.b2_basis_create(ctx.handle, nd, nelems.ctypes.data_as(_lib.p_i64), degree.ctypes.data_as(_lib.p_i32), nsets.ctypes.data_as(_lib.p_i32),
-                                      _lib.ptr_array(coeffs, _lib.p_f64), _lib.ptr_array(setidx, _lib.p_i32), _lib.ptr_array(start, _lib.p_i64),
-                                      ndofs.ctypes.data_as(_lib.p_i64), int(ncomp), ctypes.byref(h)))
-        self._fin.append(weakref.finalize(self, lib.b2_basis_destroy, h))
+        h = _create_basis(self.ctx, bases, ncomp)
+        self._fin.append(weakref.finalize(self, self.ctx.lib.b2_basis_destroy, h))
         return h
 
     csr_pattern = Plan.csr_pattern
