@@ -8,12 +8,18 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 mkdir -p "$HERE/_obj"
 SRCS="api api_elemset pattern pattern_elemset assemble_generic assemble_elemset assemble_fast assemble_rows spmv"
 OBJS=""
+PIDS=""
 for f in $SRCS; do
   src="$HERE/$f.cu"; obj="$HERE/_obj/$f.o"
   if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/common.cuh" -nt "$obj" ] || [ "$HERE/../../include/b200fem.h" -nt "$obj" ]; then
-    "$NVCC" $FLAGS ${B2_PTXAS_V:+-Xptxas -v} ${B2_EXPERIMENT:+-DB2_EXPERIMENT} -c "$src" -o "$obj"
+    # translation units are independent: compile them side by side
+    "$NVCC" $FLAGS ${B2_PTXAS_V:+-Xptxas -v} ${B2_EXPERIMENT:+-DB2_EXPERIMENT} -c "$src" -o "$obj" &
+    PIDS="$PIDS $!"
   fi
   OBJS="$OBJS $obj"
+done
+for pid in $PIDS; do
+  wait "$pid"
 done
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o "$OUT" $OBJS
 echo "built $OUT"

@@ -142,3 +142,8 @@ def assemble_csr(values, rowptr, colidx, ncols):
         if not inc.all():
             raise MatrixError('column indices are not strictly increasing within rows')
     return Matrix(values, rowptr, colidx, ncols)
+
+
+# the backend protocol of the reference: ``nutils.matrix.backend(obj)`` accepts any object with
+# ``.assemble(values, rowptr, colidx, ncols)`` (matrix/__init__.py:20-27) -- this module is such an object
+assemble = assemble_csr
