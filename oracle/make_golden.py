@@ -359,6 +359,28 @@ def eval_case(name, n, degree, ncomp=1, warp=.25, seed=0):
                 coefs=coefs.ravel(), x=x, wdet=w * weights, values=val, grads=grad)
 
 
+def example_elasticity_case(name, nelems, degree, btype='std', poisson=.25):
+    'examples/elasticity.py:43-61 (plane strain plate clamped at the top under gravity): constraints and displacement solution'
+    domain, geom = mesh.unitsquare(nelems, 'square')
+    ns = Namespace()
+    ns.δ = function.eye(domain.ndims)
+    ns.x = geom
+    ns.define_for('x', gradient='∇', normal='n', jacobians=('dV', 'dS'))
+    ns.u = domain.field('u', btype=btype, degree=degree, shape=[2])
+    ns.λ = 1
+    ns.μ = .5 / poisson - 1
+    ns.ε_ij = '.5 (∇_i(u_j) + ∇_j(u_i))'
+    ns.σ_ij = 'λ ε_kk δ_ij + 2 μ ε_ij'
+    ns.E = 'ε_ij σ_ij'
+    ns.q_i = '-δ_i1'
+    sqr = domain.boundary['top'].integral('u_k u_k dS' @ ns, degree=degree * 2)
+    cons = System(sqr, trial='u').solve_constraints(droptol=1e-15)
+    energy = domain.integral('(E - u_i q_i) dV' @ ns, degree=degree * 2)
+    args = System(energy, trial='u').solve(constrain=cons)
+    return dict(kind='example_elasticity', name=name, nelems=nelems, degree=degree, btype=btype, poisson=poisson,
+                cons=numpy.asarray(cons['u']), u=numpy.asarray(args['u']), ndofs=numpy.asarray(args['u']).size)
+
+
 def known_answer_mass_1d():
     # tests/test_function.py:1574-1585 (known-answer COO of a 1-D p=1 mass matrix)
     topo, geom = mesh.line([0, 1, 2], bnames=['a', 'b'], space='X')
@@ -403,6 +425,9 @@ CASES = {
     'varcoef2d_p3': lambda: varcoef_case('varcoef2d_p3', (5, 4), 3, seed=12),
     'eval3d_p2': lambda: eval_case('eval3d_p2', (3, 4, 2), 2, seed=13),
     'eval2d_p3_vec': lambda: eval_case('eval2d_p3_vec', (4, 3), 3, ncomp=2, seed=14),
+    'example_elasticity_p1': lambda: example_elasticity_case('example_elasticity_p1', 4, 1),    # the reference's own test sizes (examples/elasticity.py:96-135)
+    'example_elasticity_p2': lambda: example_elasticity_case('example_elasticity_p2', 4, 2),
+    'example_elasticity_spline': lambda: example_elasticity_case('example_elasticity_spline', 6, 2, btype='spline', poisson=.3),
     'elast3d_p2_warp': lambda: elasticity_case('elast3d_p2_warp', (3, 3, 2), 2, warp=.3, seed=7),  # config 3 at toy size
 }
 

@@ -37,3 +37,16 @@ def test_poisson3d_example():
     assert r['u_min'] >= -1e-9 and 1. <= r['u_max'] < 1.2
     # 1-D analogue u = x + x (1 - x) / 2: mean 2/3 - 1/12 ... = 0.5833; the warped 3-D solution stays close to it
     assert abs(r['u_mean'] - (0.5 + 1. / 12)) < 2e-2
+
+
+@pytest.mark.parametrize('name', ['example_elasticity_p1', 'example_elasticity_p2', 'example_elasticity_spline'])
+def test_elasticity_example(name):
+    # examples/elasticity.py of the reference (plate clamped at the top under gravity; its unit tests use these sizes): the
+    # constraint vector and the displacement solution the unmodified reference returns, reproduced on the GPU path
+    from tests import util
+    from examples import elasticity
+    g = util.load_golden(name)
+    cons, u = elasticity.main(int(g['nelems']), str(g['btype']), int(g['degree']), float(g['poisson']))
+    assert numpy.array_equal(numpy.isnan(cons), numpy.isnan(g['cons']))
+    assert numpy.allclose(cons[~numpy.isnan(cons)], g['cons'][~numpy.isnan(g['cons'])], atol=1e-13)
+    assert abs(u - g['u']).max() <= 1e-9 * abs(g['u']).max()
