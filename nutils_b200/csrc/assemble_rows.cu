@@ -982,7 +982,9 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
   // S1/S2 items (256 threads, 230 registers, no spills) beat more, thinner warps (512 threads cap at 128 registers and spill).
   const int64_t variant = ctx->opts.count("rows_variant") ? ctx->opts["rows_variant"] : 0;
   (void)variant;
-  if (P == 1) return launch_rows_forms<RCfg<1, 8, 8, 2, 256, 0>>(ctx, prm, fk, fm);
+  // degree 1: accumulators are small (2 x 2 per pair and form), so 16 thin warps hide more latency than 8 register-rich ones, and a
+  // 9 x 9 tile still fits (128^3: 1.59 ms with <8,8,256 threads> -> 1.28 ms)
+  if (P == 1) return launch_rows_forms<RCfg<1, 9, 9, 2, 512, 0>>(ctx, prm, fk, fm);
   if (P == 4) {
     // degree 4 (the high-order IGA case): 2 x 3 dof columns per CTA, one point-plane per pipeline step, S1/S2 items split
     // in term groups; K and M in separate launches (25 accumulators per dof pair and form, two dof pairs per thread)
