@@ -1026,6 +1026,9 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
     if (variant == 8) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 2>, true, true>(ctx, prm);
     if (variant == 9) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 1>, true, true>(ctx, prm);
     if (variant == 10) return launch_rows_cfg<RCfg<2, 4, 4, 3, 320, 2>, true, true>(ctx, prm);
+    if (variant == 11) return launch_rows_cfg<RCfg<2, 4, 4, 3, 512, 1>, true, true>(ctx, prm);
+    if (variant == 12) return launch_rows_cfg<RCfg<2, 4, 4, 3, 512, 0>, true, true>(ctx, prm);
+    if (variant == 13) return launch_rows_cfg<RCfg<2, 4, 4, 3, 384, 1>, true, true>(ctx, prm);
   }
 #endif
   return launch_rows_forms<RCfg<2, 4, 4, 3, 256, 0>>(ctx, prm, fk, fm);
