@@ -185,12 +185,10 @@ def test_invalid_arguments(ctx):
 
 @pytest.mark.parametrize('n,degree,depth', [(20, 2, 2), (12, 3, 1), (10, 4, 1)])
 def test_finite_cell_ball_properties(ctx, n, degree, depth):
-    # size-independent properties on a synthetic finite-cell workload (octree quadrature of scripts/time_elemset.py):
+    # size-independent properties on a synthetic finite-cell workload (octree quadrature of nutils_b200.fcm):
     # partition of unity survives trimming and pruning: sum(M) = sum(f) = quadrature volume, K has zero row sums and is symmetric
-    import sys, os
-    sys.path.insert(0, os.path.join(util.ROOT, 'scripts'))
-    import time_elemset
-    elem_ids, qoff, qc, qw, ren, nbn = time_elemset.octree_ball(n, degree, depth)
+    from nutils_b200 import fcm
+    elem_ids, qoff, qc, qw, ren, nbn = fcm.octree_ball(n, degree, depth)
     b1 = util.bases_1d((n,) * 3, degree, 'spline')
     v = numpy.linspace(-1, 1, n + 1)
     nodes = numpy.stack(numpy.meshgrid(v, v, v, indexing='ij'))

@@ -50,3 +50,15 @@ def test_elasticity_example(name):
     assert numpy.array_equal(numpy.isnan(cons), numpy.isnan(g['cons']))
     assert numpy.allclose(cons[~numpy.isnan(cons)], g['cons'][~numpy.isnan(g['cons'])], atol=1e-13)
     assert abs(u - g['u']).max() <= 1e-9 * abs(g['u']).max()
+
+
+def test_finitecell_example():
+    # examples/finitecell.py (BASELINE configs[4] at small size): assembled on the tensor-core kernel with a pointwise load
+    # coefficient, solved by CG on the general pattern, evaluated on the device; the error is the octree quadrature error
+    # and halves (at least) with every extra level
+    from examples import finitecell
+    coarse = finitecell.main(n=10, degree=2, depth=1)
+    fine = finitecell.main(n=10, degree=2, depth=3)
+    assert abs(fine['volume'] - fine['exact_volume']) < abs(coarse['volume'] - coarse['exact_volume'])
+    assert fine['relative_l2_error'] < .5 * coarse['relative_l2_error'] and fine['relative_l2_error'] < 2e-2
+    assert fine['cg_iterations'] > 0
