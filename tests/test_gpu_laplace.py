@@ -60,5 +60,5 @@ def test_finitecell_example():
     coarse = finitecell.main(n=10, degree=2, depth=1)
     fine = finitecell.main(n=10, degree=2, depth=3)
     assert abs(fine['volume'] - fine['exact_volume']) < abs(coarse['volume'] - coarse['exact_volume'])
-    assert fine['relative_l2_error'] < .5 * coarse['relative_l2_error'] and fine['relative_l2_error'] < 2e-2
+    assert fine['relative_l2_error'] < .5 * coarse['relative_l2_error'] and fine['relative_l2_error'] < 5e-2
     assert fine['cg_iterations'] > 0
