@@ -456,6 +456,8 @@ extern "C" int b2_pattern_create(b2_ctx* ctx, const b2_basis* basis, b2_pattern*
 
 extern "C" int b2_pattern_destroy(b2_pattern* p) {
   if (!p) return B2_OK;
+  if (p->aux_pattern) b2_pattern_destroy(p->aux_pattern);
+  if (p->aux_elemset) b2_elemset_destroy(p->aux_elemset);
   if (p->d_rowptr_b || p->d_colidx_b) {
     cudaSetDevice(p->ctx->device);
     if (p->d_rowptr_b) cudaFree(p->d_rowptr_b);
@@ -631,6 +633,32 @@ int b2_upload_forms(b2_ctx* ctx, int nd, int nc, int nmat, const double* const* 
   return B2_OK;
 }
 
+// Coverage configurations in 2-D and 3-D (C0 bases of degree >= 3, over-integration, mixed value/gradient forms, two
+// components, ...) run the element-set kernel with its tensor-core block product on the element set "everything": its
+// materialised pattern has exactly the slots of the analytic one (tests: test_full_selection_equals_structured).  Built
+// once per pattern; if it cannot be built (memory) the scalar generic kernel takes over.
+static int assemble_via_elemset(b2_ctx* ctx, const b2_pattern* cpattern, const b2_basis* basis, const b2_quad* quad, const b2_geom* geom,
+                                int64_t elem_begin, int64_t elem_end, int nmat, const double* const* D_host, double* const* values_dev,
+                                int nvec, const double* const* C_host, double* const* rhs_dev) {
+  b2_pattern* pattern = const_cast<b2_pattern*>(cpattern);
+  if (pattern->aux_failed) return B2_EUNSUPPORTED;
+  if (!pattern->aux_pattern) {
+    int64_t ntot = 1;
+    for (int d = 0; d < basis->ndims; d++) ntot *= basis->nel[d];
+    int rc = b2_elemset_create(ctx, basis, ntot, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, &pattern->aux_elemset);
+    if (rc == B2_OK) rc = b2_pattern_create_elemset(ctx, pattern->aux_elemset, &pattern->aux_pattern);
+    if (rc != B2_OK || pattern->aux_pattern->nnz != pattern->nnz) {
+      if (pattern->aux_pattern) b2_pattern_destroy(pattern->aux_pattern);
+      if (pattern->aux_elemset) b2_elemset_destroy(pattern->aux_elemset);
+      pattern->aux_pattern = nullptr;
+      pattern->aux_elemset = nullptr;
+      pattern->aux_failed = true;
+      return B2_EUNSUPPORTED;
+    }
+  }
+  return b2_assemble_elemset_device(ctx, pattern->aux_pattern, pattern->aux_elemset, quad, geom, elem_begin, elem_end, nmat, D_host, values_dev, nvec, C_host, rhs_dev);
+}
+
 // rows == false: integrate elements [elem_begin, elem_end) and ACCUMULATE into the outputs.
 // rows == true:  elem_begin/elem_end are dof planes of dimension 0; every stored value of those planes is WRITTEN.
 static int assemble_impl(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis* basis, const b2_quad* quad, const b2_geom* geom,
@@ -728,6 +756,10 @@ static int assemble_impl(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis*
       // bases of degree 1 and 2, which the owner-computes kernel (maximal smoothness) does not cover
       rc = launch_assemble_fast(ctx, B, Q, G, F, D_host, C_host, elem_begin, elem_end);
       if (rc != B2_EUNSUPPORTED) return rc;
+      if (kernel_opt == 0 && nd >= 2 && nmat > 0 && B.nb <= 128) {
+        rc = assemble_via_elemset(ctx, pattern, basis, quad, geom, elem_begin, elem_end, nmat, D_host, values_dev, nvec, C_host, rhs_dev);
+        if (rc != B2_EUNSUPPORTED) return rc;
+      }
     }
     return launch_assemble_generic(ctx, B, Q, G, F, elem_begin, elem_end, (int)plane_begin, (int)plane_end);
   }
@@ -735,6 +767,10 @@ static int assemble_impl(b2_ctx* ctx, const b2_pattern* pattern, const b2_basis*
     rc = launch_assemble_fast(ctx, B, Q, G, F, D_host, C_host, elem_begin, elem_end);
     if (rc != B2_EUNSUPPORTED) return rc;
     if (kernel_opt >= 2) return b2_fail(ctx, B2_EUNSUPPORTED, "requested specialised kernel does not cover this configuration");
+    if (kernel_opt == 0 && nd >= 2 && nmat > 0 && B.nb <= 128) {
+      rc = assemble_via_elemset(ctx, pattern, basis, quad, geom, elem_begin, elem_end, nmat, D_host, values_dev, nvec, C_host, rhs_dev);
+      if (rc != B2_EUNSUPPORTED) return rc;
+    }
   }
   return launch_assemble_generic(ctx, B, Q, G, F, elem_begin, elem_end, 0, 0x7fffffff);
 }

@@ -213,6 +213,11 @@ struct b2_pattern {
   long long* d_rowptr_b = nullptr;  // [nbasis_new+1]
   int* d_colidx_b = nullptr;        // [nnz_b]
   std::vector<long long> rowptr_b;  // host copy
+  // analytic patterns: lazily built element set "everything" + its materialised pattern (same slots as the analytic one), so
+  // that the coverage path can run the tensor-core element-set kernel instead of the scalar generic kernel
+  b2_elemset* aux_elemset = nullptr;
+  b2_pattern* aux_pattern = nullptr;
+  bool aux_failed = false;
 };
 
 // ---- error helpers -------------------------------------------------------------------------------
