@@ -1002,6 +1002,8 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
   if (P == 3) {
     // two chunks of two point-planes per layer
     using C3 = RCfg<3, 3, 3, 2, 256, 3>;
+    // K and M together: 512 threads (one dof pair per thread: 2 x 16 accumulators, 128 registers) -- 96^3: 14.5 ms
+    if (fk && fm && !(ctx->opts.count("rows_split_forms") && ctx->opts["rows_split_forms"])) return launch_rows_cfg<RCfg<3, 3, 3, 2, 512, 3>, true, true>(ctx, prm);
     // K and M in one launch (the geometry stage runs once; 2 x 2 x 16 accumulators per thread spill ~0.7 KB to L1, still
     // 10 % faster than two launches: 96^3 17.7 -> 15.9 ms); option "rows_split_forms" = 1 selects the two launches
     if (!(fk && fm) || !(ctx->opts.count("rows_split_forms") && ctx->opts["rows_split_forms"])) return launch_rows_forms<C3>(ctx, prm, fk, fm);
