@@ -1,7 +1,7 @@
 '''Table extraction from evalf/nutils objects: the reference-side half of the drop-in.
 
 Everything the CUDA path consumes is a plain array that the reference already holds inside its own
-objects; this module reads those arrays out (duck-typed -- nutils is NOT imported here) so that a
+objects; this module reads those arrays out (duck-typed: the nutils modules are reached through the objects passed in) so that a
 topology built, refined or TRIMMED by the reference's host code (topology.trim and the cut-cell
 mosaics of element.py stay where they are: host Python, outside the measured path) can be integrated
 through the C ABI:
@@ -84,6 +84,32 @@ def tables_from_reference(topo, basis, degree, vertices=None, nodes=None, ischem
             raise ValueError('basis and topology have different elements')
         t['qoff'], t['qcoords'], t['qweights'] = ragged_points(topo.sample(ischeme, degree), len(topo))
     return t
+
+
+def nurbs_tables_from_reference(topo, weightfunc, geom, degree, geometry_degree=2):
+    '''Tables of a NURBS discretisation built the way examples/platewithhole.py:66-86 builds it: a coarse rational patch
+    (`weightfunc`, `geom` = nurbsbasis @ controlpoints) on a topology that has since been refined.
+
+    Returns (bases, scale, gbases, gctrl, gweights): the analysis space is ``topo.basis('spline', degree)`` scaled by the
+    projected control weights `scale` and divided by the patch's weight function (``rational=2``); the geometry is the patch
+    itself, represented exactly in the B-splines of degree `geometry_degree` of the refined topology (nested spaces) by its
+    weights `gweights` and control points `gctrl` -- the arguments of b2_geom_create_spline.  The projections are the
+    reference's own (``System(...).solve()`` of a least-squares functional, platewithhole.py:79-82); the nutils modules are
+    taken from the objects passed in.'''
+    import importlib
+    nutils = importlib.import_module(type(topo).__module__.partition('.')[0])
+    function = importlib.import_module(nutils.__name__ + '.function')
+    System = importlib.import_module(nutils.__name__ + '.solver').System
+
+    def project(target, pbasis):
+        sqr = topo.integral((function.field('w', pbasis) - target)**2, degree=9)
+        return numpy.asarray(System(sqr, trial='w').solve()['w'])
+    gbasis = topo.basis('spline', degree=geometry_degree)
+    gweights = project(weightfunc, gbasis)
+    gctrl = numpy.stack([project(weightfunc * geom[i], gbasis) for i in range(topo.ndims)]) / gweights
+    abasis = topo.basis('spline', degree=degree)
+    scale = project(weightfunc, abasis)
+    return bases1d_from_structured_basis(abasis), scale, bases1d_from_structured_basis(gbasis), gctrl, gweights
 
 
 def plan_from_reference(ctx, topo, basis, degree, vertices=None, nodes=None, ncomp=1):

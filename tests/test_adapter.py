@@ -57,6 +57,36 @@ def test_tables_reproduce_reference(trimmed):
     assert util.relerr(vecs[0], f) <= 1e-12
 
 
+@pytest.mark.parametrize('degree', [2, 3])
+def test_nurbs_tables_reproduce_reference(degree):
+    # the NURBS construction of examples/platewithhole.py:66-86: tables read out by the adapter, assembled by the oracle,
+    # against the reference's own mass matrix and load of the rational basis on the NURBS geometry
+    _reference()
+    from nutils import mesh, function
+    topo, geom0 = mesh.rectilinear([1, 2])
+    bsplinebasis = topo.basis('spline', degree=2)
+    controlweights = numpy.ones(12)
+    controlweights[1:3] = .5 + .25 * numpy.sqrt(2)
+    weightfunc = bsplinebasis @ controlweights
+    nurbsbasis = bsplinebasis * controlweights / weightfunc
+    A, B, C = (0, 0, 0), ((2**.5 - 1) * .5, .3 * 1.5 / 2, 1), (.5, 1.5 / 2, 1)
+    geom = nurbsbasis @ numpy.array([[A, B, C, C], [C, C, B, A]]).T.reshape(-1, 2)
+    topo = topo.refine(1)
+    bases, scale, gbases, gctrl, gweights = adapter.nurbs_tables_from_reference(topo, weightfunc, geom, degree)
+    abasis = topo.basis('spline', degree=degree)
+    nbasis = abasis * scale / weightfunc
+    J = function.J(geom)
+    (mv, rp, ci), f = function.eval((function.as_csr(topo.integral(nbasis[:, None] * nbasis[None, :] * J, degree=8)), topo.integral(nbasis * J, degree=8)))
+    rules = points.tensor_gauss(2, 8)
+    prob = fem_oracle.Problem(tuple(topo.shape), [b.degree for b in bases], [b.coeffs for b in bases], [b.setidx for b in bases], [b.start for b in bases],
+                              [b.ndofs for b in bases], [r[0] for r in rules], [r[1] for r in rules], numpy.zeros((2, 0, 0)), scale=scale, rational=2,
+                              geom_spline=dict(degree=[b.degree for b in gbases], coeffs=[b.coeffs for b in gbases], setidx=[b.setidx for b in gbases],
+                                               start=[b.start for b in gbases], ndofs_d=[b.ndofs for b in gbases], ctrl=gctrl, weights=gweights))
+    mats, vecs = fem_oracle.assemble(prob, [('mass',)], [('load',)])
+    assert numpy.array_equal(mats[0][1], rp) and numpy.array_equal(mats[0][2], ci)
+    assert util.relerr(mats[0][0], mv) <= 1e-11 and util.relerr(vecs[0], f) <= 1e-11
+
+
 def test_rejects_unstructured_basis():
     _reference()
     from nutils import mesh
