@@ -1,9 +1,13 @@
-'''BASELINE.json configs[0]: examples/laplace.py of the reference, assembled AND solved on the B200 path through the
-Nutils-style API: volume stiffness (owner-computes kernel / coverage path), Neumann load on the right boundary, Dirichlet
-data by L2 projection on the left and top boundaries (boundary mass matrices and loads with coefficient functions:
-element-set kernel with the surface measure), constrained solve with the device-resident matrix.  Known answers: the L2
-errors asserted by the reference's own unit tests (examples/laplace.py:113-137: 1.63e-3 for nelems=4 std p=1, 8.04e-5 for
-nelems=4 spline p=2) and the values the unmodified reference returns here for nelems = 8 and 32 (4.0141e-4, 2.49609e-5).'''
+'''The example scripts of this repository on the B200 path, against known answers of the reference.
+
+examples/laplace.py -- BASELINE.json configs[0], the reference's examples/laplace.py: volume stiffness, Neumann load on the
+right boundary, Dirichlet data by L2 projection on the left and top boundaries (boundary mass matrices and loads with
+coefficient functions: element-set kernel with the surface measure), constrained solve with the device-resident matrix,
+error by Sample.eval on the device.  Known answers: the L2 errors asserted by the reference's own unit tests
+(examples/laplace.py:113-137: 1.63e-3 for nelems=4 std p=1, 8.04e-5 for nelems=4 spline p=2) and the values the unmodified
+reference returns here for nelems = 8 and 32 (4.0141e-4, 2.49609e-5).
+examples/elasticity.py -- the reference's plane-strain example: constraints and displacements of the unmodified reference.
+examples/poisson3d.py, examples/finitecell.py -- properties (maximum principle, convergence of the octree quadrature).'''
 
 import numpy
 import pytest
