@@ -66,3 +66,16 @@ def test_finitecell_example():
     assert abs(fine['volume'] - fine['exact_volume']) < abs(coarse['volume'] - coarse['exact_volume'])
     assert fine['relative_l2_error'] < .5 * coarse['relative_l2_error'] and fine['relative_l2_error'] < 5e-2
     assert fine['cg_iterations'] > 0
+
+
+def test_semilinear_example():
+    # examples/semilinear.py: Newton with solution-dependent pointwise coefficients, every step on the device; quadratic
+    # convergence of the residual and an L2 error that drops with the mesh (degree 2: third order)
+    from examples import semilinear
+    a = semilinear.main(n=6, degree=2)
+    b = semilinear.main(n=12, degree=2)
+    for r in a, b:
+        h = r['residual_history']
+        assert r['newton_iterations'] <= 8 and h[-1] <= 1e-10 * max(h[0], 1.)
+        assert h[-1] < h[-2] ** 1.5 or h[-1] < 1e-12    # superlinear at the end
+    assert b['l2_error'] < a['l2_error'] / 5
