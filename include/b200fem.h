@@ -204,8 +204,14 @@ int64_t b2_elemset_npoints(const b2_elemset* elemset); /* total number of quadra
  *     point is multiplied by the SURFACE measure |det J| |J^-T e_dim| instead of |det J| (function.J on a boundary sample).
  *   b2_elemset_set_coefficient: a scalar per point that multiplies one form of the next assembly calls: which = m for
  *     matrix form m, B2_MAX_FORMS + v for vector form v; coef float64[npoints] in point order (element sets with a tensor
- *     rule: [nsel][nq]), NULL removes it.  The array is copied. */
+ *     rule: [nsel][nq]), NULL removes it.  The array is copied.
+ *   b2_elemset_set_normals: the general form of set_faces for facets that are not aligned with the element faces -- the
+ *     immersed boundary of a trimmed topology (topo.boundary['trimmed'], the simplices of the cut-cell mosaics).  nref
+ *     (float64[npoints][ndims]) is, per point, the reference-space normal of its facet SCALED by the facet's reference measure
+ *     (cross product of the columns of the facet-to-element linear map, transform.py); the weight of the point is multiplied by
+ *     |det J| |J^-T nref| (Nanson).  NULL removes it; it takes precedence over face_dim. */
 int b2_elemset_set_faces(b2_elemset* elemset, const int8_t* face_dim);
+int b2_elemset_set_normals(b2_elemset* elemset, const double* nref, int64_t npoints);
 int b2_elemset_set_coefficient(b2_elemset* elemset, int which, const double* coef, int64_t npoints);
 
 /* Spline geometry x(xi) = sum_i B_i(xi) X_i, or the rational map sum_i B_i w_i X_i / sum_i B_i w_i (the NURBS map of

@@ -85,6 +85,7 @@ SIGNATURES = {
     'b2_elemset_create': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, ctypes.c_int, p_vp]),
     'b2_elemset_destroy': (ctypes.c_int, [c_vp]),
     'b2_elemset_set_faces': (ctypes.c_int, [c_vp, c_vp]),
+    'b2_elemset_set_normals': (ctypes.c_int, [c_vp, c_vp, c_i64]),
     'b2_elemset_set_coefficient': (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_i64]),
     'b2_elemset_ndofs': (c_i64, [c_vp]),
     'b2_elemset_npoints': (c_i64, [c_vp]),

@@ -86,6 +86,46 @@ def tables_from_reference(topo, basis, degree, vertices=None, nodes=None, ischem
     return t
 
 
+def immersed_boundary_tables_from_reference(btopo, basetopo, degree, ischeme='gauss'):
+    '''Points of a boundary topology whose facets are NOT element faces -- the trimmed boundary ``topo.boundary['name']`` of a
+    finite-cell topology -- grouped per volume element of the structured base topology:
+
+        elem_ids, qoff, qcoords, qweights, normals
+
+    Every boundary element's transform chain is split into the base element and the tail that maps facet coordinates into the
+    element (``transforms.index_with_tail``, transformseq.py); the points are pushed through the tail (``transform.apply``) and
+    the scaled reference normal is the generalised cross product of the columns of the tail's linear map, so that
+    |det J| |J^-T n| is the surface measure the reference obtains from function.J on the boundary sample (function.py:2291-2316).'''
+    import importlib
+    transform = importlib.import_module(type(btopo).__module__.partition('.')[0] + '.transform')
+    sample = btopo.sample(ischeme, degree)
+    nd = basetopo.ndims
+    per_elem = {}
+    for i in range(len(btopo)):
+        ielem, tail = basetopo.transforms.index_with_tail(btopo.transforms[i])
+        pts = sample.points.get(i)
+        xi = numpy.asarray(transform.apply(tail, numpy.asarray(pts.coords)), dtype=float)
+        L = numpy.eye(nd)
+        for item in tail:
+            L = L @ numpy.asarray(item.linear, dtype=float)
+        if L.shape != (nd, nd - 1):
+            raise NotImplementedError('boundary elements must be facets (codimension one)')
+        if nd == 3:
+            n = numpy.cross(L[:, 0], L[:, 1])
+        elif nd == 2:
+            n = numpy.array([L[1, 0], -L[0, 0]])
+        else:
+            n = numpy.ones(1)
+        entry = per_elem.setdefault(int(ielem), ([], [], []))
+        entry[0].append(xi)
+        entry[1].append(numpy.asarray(pts.weights, dtype=float))
+        entry[2].append(numpy.tile(n, (len(xi), 1)))
+    elem_ids = numpy.array(sorted(per_elem), dtype=numpy.int64)
+    qoff = numpy.concatenate([[0], numpy.cumsum([sum(len(w) for w in per_elem[e][1]) for e in elem_ids])]).astype(numpy.int64)
+    cat = lambda k: numpy.concatenate([a for e in elem_ids for a in per_elem[e][k]]) if len(elem_ids) else numpy.zeros((0, nd) if k != 1 else 0)
+    return elem_ids, qoff, cat(0), cat(1), cat(2)
+
+
 def nurbs_tables_from_reference(topo, weightfunc, geom, degree, geometry_degree=2):
     '''Tables of a NURBS discretisation built the way examples/platewithhole.py:66-86 builds it: a coarse rational patch
     (`weightfunc`, `geom` = nurbsbasis @ controlpoints) on a topology that has since been refined.

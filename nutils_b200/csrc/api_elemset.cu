@@ -124,6 +124,16 @@ extern "C" int b2_elemset_set_faces(b2_elemset* es, const int8_t* face_dim) {
   return upload_n(ctx, (const signed char*)face_dim, (size_t)es->nsel, &es->d_face_dim);
 }
 
+extern "C" int b2_elemset_set_normals(b2_elemset* es, const double* nref, int64_t npoints) {
+  if (!es) return B2_EINVAL;
+  b2_ctx* ctx = es->ctx;
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (es->d_normals) { cudaFree(es->d_normals); es->d_normals = nullptr; }
+  if (!nref) return B2_OK;
+  if (!es->d_qoff || npoints != es->npoints) return b2_fail(ctx, B2_EINVAL, "facet normals need an element set with its own points, one normal per point");
+  return upload_n(ctx, nref, (size_t)npoints * es->basis->ndims, &es->d_normals);
+}
+
 extern "C" int b2_elemset_set_coefficient(b2_elemset* es, int which, const double* coef, int64_t npoints) {
   if (!es || which < 0 || which >= 2 * B2_MAX_FORMS) return B2_EINVAL;
   b2_ctx* ctx = es->ctx;
@@ -139,6 +149,7 @@ extern "C" int b2_elemset_destroy(b2_elemset* es) {
   if (!es) return B2_OK;
   cudaSetDevice(es->ctx->device);
   if (es->d_face_dim) cudaFree(es->d_face_dim);
+  if (es->d_normals) cudaFree(es->d_normals);
   for (double* p : es->d_coef)
     if (p) cudaFree(p);
   void* ptrs[] = {es->d_elem_ids, es->d_qoff, es->d_qcoords, es->d_qweights, es->d_renumber, es->d_scale, es->d_selmask, es->d_dofmap,
@@ -271,6 +282,7 @@ static int build_views(b2_ctx* ctx, const b2_pattern* pattern, const b2_elemset*
   E.scale = es->d_scale;
   E.rational = es->rational;
   E.face_dim = es->d_face_dim;
+  E.normals = es->d_normals;
   E.nq_uniform = Q.nqt;
   for (int k = 0; k < 2 * B2_MAX_FORMS; k++) {
     E.coef[k] = es->d_coef[k];

@@ -362,7 +362,19 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512, TCMAX == 4 ? 4 : 1) k_
 #pragma unroll
           for (int i = 0; i < DIM * DIM; i++) sJ[ql * JS + i] = Ji[i];
           double meas = fabs(det);
-          if (fdim >= 0) {
+          if (E.normals) {
+            // immersed facet with scaled reference normal n: surface measure |det J| |J^-T n|
+            const double* nr = E.normals + (qbeg + q0 + ql) * DIM;
+            double nn = 0.;
+#pragma unroll
+            for (int i = 0; i < DIM; i++) {
+              double vi = 0.;
+#pragma unroll
+              for (int k = 0; k < DIM; k++) vi = fma(Ji[k * DIM + i], nr[k], vi);
+              nn = fma(vi, vi, nn);
+            }
+            meas *= sqrt(nn);
+          } else if (fdim >= 0) {
             // surface measure of the face normal to reference direction fdim: |det J| |J^-T e_fdim| (row fdim of J^-1)
             double nn = 0.;
 #pragma unroll

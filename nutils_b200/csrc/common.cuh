@@ -68,6 +68,7 @@ struct ElemSetView {
   const int* renumber;         // [nbasis_parent] -> new index, < 0: dropped; null = identity
   const double* scale;         // [nbasis_parent] or null
   int rational;                // 0 none, 1 own weight function, 2 the geometry's weight function
+  const double* normals;       // [npoints][ndims] scaled reference normals of the points' facets (immersed boundaries), or null
   const signed char* face_dim; // [nsel] -1 volume, k: points on a face normal to reference direction k (surface measure); null = volume
   const double* coef[2 * B2_MAX_FORMS];  // per-point scalar coefficient of matrix form m / vector form B2_MAX_FORMS + v, or null
   long long nq_uniform;        // points per element of the tensor rule (indexing of coef when qoff is null)
@@ -196,6 +197,7 @@ struct b2_elemset {
   double* d_scale = nullptr;
   double* d_coeffs[B2_MAXD] = {nullptr, nullptr, nullptr};
   signed char* d_face_dim = nullptr;
+  double* d_normals = nullptr;
   double* d_coef[2 * B2_MAX_FORMS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int64_t coef_len[2 * B2_MAX_FORMS] = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned char* d_selmask = nullptr;  // [ntotal] 1 = element selected (pattern construction); null = all

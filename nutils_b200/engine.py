@@ -379,6 +379,17 @@ class ElemSetPlan:
             raise ValueError('one face code per selected element is needed')
         self.ctx.check(self.ctx.lib.b2_elemset_set_faces(self.elemset, None if fd is None else fd.ctypes.data_as(c_vp)))
 
+    def set_normals(self, normals):
+        '''immersed boundaries: per point the reference-space normal of its facet scaled by the facet's reference measure
+        (float64[npoints, ndims]); the weights are multiplied by |det J| |J^-T n| (b2_elemset_set_normals).  None resets.'''
+        if normals is None:
+            self.ctx.check(self.ctx.lib.b2_elemset_set_normals(self.elemset, None, 0))
+            return
+        nr = as_f64(normals)
+        if nr.shape != (self.npoints, self.ndims):
+            raise ValueError('one normal per quadrature point is needed')
+        self.ctx.check(self.ctx.lib.b2_elemset_set_normals(self.elemset, nr.ctypes.data_as(c_vp), len(nr)))
+
     def set_coefficient(self, kind, index, coef):
         '''a scalar per quadrature point multiplying matrix form `index` (kind 'matrix') or vector form `index` (kind 'vector') of
         the following assembly calls (b2_elemset_set_coefficient); coef None removes it.'''

@@ -60,7 +60,7 @@ class Problem:
     '''
 
     def __init__(self, nelems, degree, coeffs, setidx, start, ndofs_d, qpts, qwts, nodes, ncomp=1, elem_ids=None, qoff=None, qcoords=None,
-                 qweights=None, renumber=None, nbasis_new=None, scale=None, rational=0, geom_spline=None, face_dim=None):
+                 qweights=None, renumber=None, nbasis_new=None, scale=None, rational=0, geom_spline=None, face_dim=None, normals=None):
         self.ndims = len(nelems)
         self.nelems = tuple(int(n) for n in nelems)
         self.degree = tuple(int(p) for p in degree)
@@ -87,6 +87,9 @@ class Problem:
         # boundary integrals: face_dim[isel] = -1 (volume) or the reference direction normal to the face the element's points lie
         # on; the measure is then the surface measure |det J| |J^-T e_dim| (function.J on a boundary sample, function.py:2291-2316)
         self.face_dim = None if face_dim is None else numpy.asarray(face_dim, dtype=numpy.int64)
+        # immersed boundaries (topo.boundary['trimmed']): per point the reference normal of its facet scaled by the facet's reference
+        # measure; the surface measure is |det J| |J^-T n| (Nanson's formula applied to the facet transform, transform.py)
+        self.normals = None if normals is None else numpy.asarray(normals, dtype=float)
         assert geom_spline is not None or self.nodes.shape == (self.ndims,) + tuple(n + 1 for n in self.nelems)
 
     @property
@@ -205,7 +208,10 @@ def element_data(prob, isel, return_x=False):
     det = numpy.linalg.det(J)
     grad = numpy.einsum('qak,qki->qai', dN, Jinv)
     meas = abs(det)
-    if prob.face_dim is not None and prob.face_dim[isel] >= 0:
+    if prob.normals is not None:
+        nr = prob.normals[prob.qoff[isel]:prob.qoff[isel + 1]]
+        meas = meas * numpy.linalg.norm(numpy.einsum('qki,qk->qi', Jinv, nr), axis=-1)
+    elif prob.face_dim is not None and prob.face_dim[isel] >= 0:
         meas = meas * numpy.linalg.norm(Jinv[:, prob.face_dim[isel], :], axis=-1)
     if prob.renumber is not None:
         dofs = prob.renumber[dofs]

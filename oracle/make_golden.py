@@ -339,6 +339,34 @@ def varcoef_case(name, n, degree, warp=.25, seed=0):
                 coef=_coef_g(xq), K_values=kv, rowptr=rp, colidx=ci, F=f)
 
 
+def immersed_boundary_case(name, n, degree, radius, maxrefine, ball=True):
+    '''integrals over the TRIMMED boundary of a finite-cell topology (Nitsche / penalty terms, immersed Neumann data): boundary mass
+    matrix and load with a coefficient function, and the surface area, on the sphere / circle cut out of a structured grid'''
+    sys.path.insert(0, os.path.dirname(HERE))
+    from nutils_b200 import adapter
+    ndims = len(n)
+    verts = [numpy.linspace(-1, 1, ni + 1) for ni in n]
+    topo0, geom = mesh.rectilinear(verts)
+    levelset = radius - numpy.linalg.norm(geom) if ball else numpy.linalg.norm(geom) - radius
+    topo = topo0.trim(levelset, maxrefine=maxrefine, name='trimmed')
+    bt = topo.boundary['trimmed']
+    basis = topo.basis('spline', degree=degree)
+    qd = 2 * degree
+    g = 1. + .5 * numpy.prod(geom, axis=0) + numpy.cosh(geom[0])
+    J = function.J(geom)
+    B = bt.integral(basis[:, None] * basis[None, :] * g * J, degree=qd)
+    F = bt.integral(basis * g * J, degree=qd)
+    area = function.eval(bt.integral(J, degree=qd))
+    (bv, rp, ci), f = function.eval((function.as_csr(B), F))
+    elem_ids, qoff, qcoords, qweights, normals = adapter.immersed_boundary_tables_from_reference(bt, topo0, qd)
+    X = numpy.stack(numpy.meshgrid(*verts, indexing='ij'))
+    xq = _physical_points(X, tuple(n), elem_ids, qoff, qcoords)
+    return dict(kind='elemset_boundary', name=name, ndims=ndims, nelems=numpy.array(n), degree=degree, btype='spline', qdegree=qd, nodes=X, ndofs=len(basis), ncomp=1,
+                elem_ids=elem_ids, qoff=qoff, qcoords=qcoords, qweights=qweights, normals=normals, coef=_coef_g(xq), area=area,
+                renumber=numpy.asarray(basis._renumber, dtype=numpy.int64), nbasis_new=len(basis),
+                M_values=bv, rowptr=rp, colidx=ci, F=f)
+
+
 def eval_case(name, n, degree, ncomp=1, warp=.25, seed=0):
     'Sample.eval of the reference (sample.py:192-215): coordinates, w |det J|, a discrete field and its gradient at the Gauss points'
     ndims = len(n)
@@ -421,6 +449,8 @@ CASES = {
     'bnd3d_right_p2_warp': lambda: boundary_case('bnd3d_right_p2_warp', (4, 3, 5), 2, 'right', warp=.3, seed=9),
     'bnd3d_front_p3': lambda: boundary_case('bnd3d_front_p3', (3, 4, 2), 3, 'front', warp=.2, seed=10),
     'bnd1d_right_p2': lambda: boundary_case('bnd1d_right_p2', (6,), 2, 'right'),
+    'fcm3d_sphere_surface_p2': lambda: immersed_boundary_case('fcm3d_sphere_surface_p2', (4, 4, 4), 2, radius=.8, maxrefine=1),   # the immersed boundary of config 5
+    'fcm2d_circle_boundary_p2': lambda: immersed_boundary_case('fcm2d_circle_boundary_p2', (6, 5), 2, radius=.75, maxrefine=2, ball=False),
     'varcoef3d_p2': lambda: varcoef_case('varcoef3d_p2', (4, 3, 3), 2, seed=11),
     'varcoef2d_p3': lambda: varcoef_case('varcoef2d_p3', (5, 4), 3, seed=12),
     'eval3d_p2': lambda: eval_case('eval3d_p2', (3, 4, 2), 2, seed=13),

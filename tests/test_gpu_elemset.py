@@ -39,6 +39,8 @@ def _plan(ctx, prob):
                               renumber=prob.renumber, nbasis_new=prob.nbasis_new, scale=prob.scale, rational=prob.rational, geom_spline=gs)
     if prob.face_dim is not None:
         plan.set_faces(prob.face_dim)
+    if prob.normals is not None:
+        plan.set_normals(prob.normals)
     return plan
 
 

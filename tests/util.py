@@ -67,7 +67,7 @@ def elemset_problem_from_golden(g):
     b1 = bases_1d(nelems, degree, str(g['btype']))
     rules = points.tensor_gauss(ndims, int(g['qdegree']))
     kw = dict(ncomp=int(g['ncomp']))
-    for key in 'elem_ids', 'qoff', 'qcoords', 'qweights', 'renumber', 'scale', 'face_dim':
+    for key in 'elem_ids', 'qoff', 'qcoords', 'qweights', 'renumber', 'scale', 'face_dim', 'normals':
         if key in g:
             kw[key] = g[key]
     if 'renumber' in g:
