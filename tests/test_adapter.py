@@ -87,6 +87,31 @@ def test_nurbs_tables_reproduce_reference(degree):
     assert util.relerr(mats[0][0], mv) <= 1e-11 and util.relerr(vecs[0], f) <= 1e-11
 
 
+def test_immersed_boundary_tables_reproduce_reference():
+    # the trimmed boundary of a finite-cell topology: facets of the cut-cell mosaics, not element faces
+    _reference()
+    from nutils import mesh, function
+    verts = [numpy.linspace(-1, 1, 5), numpy.linspace(-1, 1, 4)]
+    topo0, geom = mesh.rectilinear(verts)
+    topo = topo0.trim(.7 - numpy.linalg.norm(geom), maxrefine=2, name='trimmed')
+    bt = topo.boundary['trimmed']
+    basis = topo.basis('spline', degree=2)
+    J = function.J(geom)
+    (bv, rp, ci), f, length = function.eval((function.as_csr(bt.integral(basis[:, None] * basis[None, :] * J, degree=4)), bt.integral(basis * J, degree=4), bt.integral(J, degree=4)))
+    assert abs(length - 2 * numpy.pi * .7) < 2e-2
+    elem_ids, qoff, qcoords, qweights, normals = adapter.immersed_boundary_tables_from_reference(bt, topo0, 4)
+    t = adapter.tables_from_reference(topo, basis, 4, vertices=verts)
+    b1 = t['bases']
+    rules = points.tensor_gauss(2, 4)
+    prob = fem_oracle.Problem(t['nelems'], [b.degree for b in b1], [b.coeffs for b in b1], [b.setidx for b in b1], [b.start for b in b1], [b.ndofs for b in b1],
+                              [r[0] for r in rules], [r[1] for r in rules], t['nodes'], elem_ids=elem_ids, qoff=qoff, qcoords=qcoords, qweights=qweights,
+                              normals=normals, renumber=t['renumber'], nbasis_new=t['nbasis_new'])
+    mats, vecs = fem_oracle.assemble(prob, [('mass',)], [('load',)])
+    assert numpy.array_equal(mats[0][1], rp) and numpy.array_equal(mats[0][2], ci)
+    assert util.relerr(mats[0][0], bv) <= 1e-12 and util.relerr(vecs[0], f) <= 1e-12
+    assert abs(vecs[0].sum() - length) <= 1e-12 * length
+
+
 def test_rejects_unstructured_basis():
     _reference()
     from nutils import mesh
