@@ -55,3 +55,57 @@ def octree_ball(n, degree, L, radius=.8):
     renumber = numpy.full(nd ** 3, len(dofs), dtype=numpy.int64)
     renumber[dofs] = numpy.arange(len(dofs))
     return elem_ids, numpy.array(qoff, dtype=numpy.int64), numpy.concatenate(coords), numpy.concatenate(weights), renumber, len(dofs)
+
+
+def sphere_surface(n, radius=.8, ntheta=None):
+    '''Quadrature of the sphere |x| = radius immersed in the n^3 grid on [-1, 1]^3, as tables for an immersed-boundary element set:
+
+        elem_ids, qoff, qcoords, qweights, normals
+
+    Product rule on the sphere (Gauss in cos(theta), trapezoid in phi: exact for polynomials of the matching degree), every point
+    assigned to the grid cell that contains it.  The weights are PHYSICAL surface weights; the scaled reference normal that makes
+    |det J| |J^-T n| = 1 on the uniform grid (J = h I with h the cell size) is n = e_x / h^2, so b2_elemset_set_normals reproduces them.
+    The union of the cells is a subset of the cut cells of octree_ball with the same radius.'''
+    ntheta = ntheta or 4 * n
+    nphi = 2 * ntheta
+    ct, wt = numpy.polynomial.legendre.leggauss(ntheta)
+    phi = (numpy.arange(nphi) + .5) * (2 * numpy.pi / nphi)
+    st = numpy.sqrt(1 - ct ** 2)
+    x = radius * numpy.stack([numpy.outer(st, numpy.cos(phi)), numpy.outer(st, numpy.sin(phi)), numpy.outer(ct, numpy.ones(nphi))], -1).reshape(-1, 3)
+    w = radius ** 2 * numpy.outer(wt, numpy.full(nphi, 2 * numpy.pi / nphi)).ravel()
+    h = 2. / n
+    cell = numpy.clip(numpy.floor((x + 1) / h).astype(int), 0, n - 1)
+    xi = (x + 1) / h - cell
+    ids = numpy.ravel_multi_index(cell.T, (n, n, n))
+    order = numpy.argsort(ids, kind='stable')
+    ids, xi, w = ids[order], xi[order], w[order]
+    elem_ids, counts = numpy.unique(ids, return_counts=True)
+    qoff = numpy.concatenate([[0], numpy.cumsum(counts)]).astype(numpy.int64)
+    normals = numpy.zeros_like(xi)
+    normals[:, 0] = 1. / h ** 2
+    return elem_ids.astype(numpy.int64), qoff, xi, w, normals
+
+
+def merge_point_sets(a, b):
+    '''Union of two ragged point sets on the same grid, each given as (elem_ids, qoff, qcoords, qweights, normals): per element the
+    points of `a` followed by the points of `b`.  Also returns the boolean array "point comes from b", so that per-point
+    coefficients can switch forms on and off -- e.g. volume points (a) carry the stiffness and the load, surface points (b) a
+    penalty term, in ONE assembly into ONE pattern.'''
+    ea, qa, xa, wa, na = a
+    eb, qb, xb, wb, nb = b
+    elem_ids = numpy.union1d(ea, eb)
+    ia = {int(e): k for k, e in enumerate(ea)}
+    ib = {int(e): k for k, e in enumerate(eb)}
+    xs, ws, ns, fb, qoff = [], [], [], [], [0]
+    for e in elem_ids:
+        cnt = 0
+        for src, idx, (q, x, w, n) in ((0, ia, (qa, xa, wa, na)), (1, ib, (qb, xb, wb, nb))):
+            k = idx.get(int(e))
+            if k is None:
+                continue
+            sl = slice(q[k], q[k + 1])
+            xs.append(x[sl]); ws.append(w[sl]); ns.append(n[sl])
+            fb.append(numpy.full(q[k + 1] - q[k], bool(src)))
+            cnt += q[k + 1] - q[k]
+        qoff.append(qoff[-1] + cnt)
+    return elem_ids, numpy.array(qoff, dtype=numpy.int64), numpy.concatenate(xs), numpy.concatenate(ws), numpy.concatenate(ns), numpy.concatenate(fb)

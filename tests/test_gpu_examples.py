@@ -79,3 +79,12 @@ def test_semilinear_example():
         assert r['newton_iterations'] <= 8 and h[-1] <= 1e-10 * max(h[0], 1.)
         assert h[-1] < h[-2] ** 1.5 or h[-1] < 1e-12    # superlinear at the end
     assert b['l2_error'] < a['l2_error'] / 5
+
+
+def test_finitecell_dirichlet_example():
+    # Dirichlet data on the IMMERSED sphere by a penalty term on the trimmed boundary: volume and surface points in one element
+    # set, per-point normals for the measures, per-point coefficients to switch the forms
+    from examples import finitecell
+    r = finitecell.main_dirichlet(n=10, degree=2, depth=3)
+    assert abs(r['surface_area'] - r['exact_area']) <= 1e-10 * r['exact_area']
+    assert r['relative_l2_error'] < 6e-2 and r['boundary_rms_error'] < 6e-2 and r['cg_iterations'] > 0
