@@ -154,7 +154,9 @@ __device__ __forceinline__ void s1_item(const RowParams& prm, const double* __re
     const int e2 = i2 - P + k;
     if (e2 < 0 || e2 >= n2) continue;
     const int a = P - k, e2l = i2l + k;
-#pragma unroll
+    // the point loop indexes no registers: at degree >= 3 it stays rolled -- fully unrolled the item is several thousand
+    // instructions per term group and the kernel thrashes the instruction cache (ncu at p=4: 60 % of the S1 samples "no instruction")
+#pragma unroll(P <= 2 ? NQ : 1)
     for (int q2 = 0; q2 < NQ; q2++) {
       const double* g = sG + (e2l * NQ + q2) * LS + L;
       const double* tb = sTb2 + (e2l * NQ + q2) * NB * 2;
@@ -254,7 +256,7 @@ __device__ __forceinline__ void s2_item(const RowParams& prm, const double* __re
     const int e1 = i1 - P + k;
     if (e1 < 0 || e1 >= n1) continue;
     const int a = P - k, e1l = i1l + k;
-#pragma unroll
+#pragma unroll(P <= 2 ? NQ : 1)
     for (int q1 = 0; q1 < NQ; q1++) {
       const int Q1 = e1l * NQ + q1;
       const double* x = sT1 + Q1 * C::T1QS + L;
