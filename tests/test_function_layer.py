@@ -76,3 +76,28 @@ def test_outside_the_closed_form():
         topo.integral(basis, degree=4)                       # no jacobian: not an integral over the geometry
     with pytest.raises(NotImplementedError):
         topo.basis('discont', degree=1)
+
+
+def test_fcm_generators():
+    # own finite-cell table generators (octree volume quadrature, sphere surface quadrature, merged point sets)
+    from nutils_b200 import fcm
+    n, p = 8, 2
+    elem_ids, qoff, qc, qw, ren, nbn = fcm.octree_ball(n, p, 2)
+    assert (numpy.diff(elem_ids) > 0).all() and len(qoff) == len(elem_ids) + 1 and qoff[-1] == len(qw) == len(qc)
+    assert (qc >= 0).all() and (qc <= 1).all() and (qw > 0).all()
+    vol = qw.sum() * (2. / n) ** 3
+    assert abs(vol - 4 / 3 * numpy.pi * .8 ** 3) < .03 * vol
+    kept = ren[(ren >= 0) & (ren < nbn)]
+    assert len(kept) == nbn and (numpy.diff(kept) > 0).all()              # monotone pruned numbering, like PrunedBasis
+    se, sq, sx, sw, sn = fcm.sphere_surface(n)
+    assert abs(sw.sum() - 4 * numpy.pi * .64) < 1e-12 and set(se) <= set(elem_ids)
+    assert (sx >= 0).all() and (sx <= 1).all()
+    vn = numpy.zeros((len(qw), 3))
+    vn[:, 0] = 2. / n
+    me, mq, mx, mw, mn, on_surface = fcm.merge_point_sets((elem_ids, qoff, qc, qw, vn), (se, sq, sx, sw, sn))
+    assert numpy.array_equal(me, elem_ids) and mq[-1] == len(qw) + len(sw) and on_surface.sum() == len(sw)
+    assert abs(mw[on_surface].sum() - sw.sum()) < 1e-12 and abs(mw[~on_surface].sum() - qw.sum()) < 1e-12
+    # per element the volume points come first
+    k = int(numpy.searchsorted(elem_ids, se[0]))
+    seg = on_surface[mq[k]:mq[k + 1]]
+    assert not seg[0] and seg[-1] and (numpy.diff(seg.astype(int)) >= 0).all()
