@@ -98,6 +98,6 @@ def test_fcm_generators():
     assert numpy.array_equal(me, elem_ids) and mq[-1] == len(qw) + len(sw) and on_surface.sum() == len(sw)
     assert abs(mw[on_surface].sum() - sw.sum()) < 1e-12 and abs(mw[~on_surface].sum() - qw.sum()) < 1e-12
     # per element the volume points come first
-    k = int(numpy.searchsorted(elem_ids, se[0]))
-    seg = on_surface[mq[k]:mq[k + 1]]
-    assert not seg[0] and seg[-1] and (numpy.diff(seg.astype(int)) >= 0).all()
+    for k in numpy.searchsorted(elem_ids, se):
+        seg = on_surface[mq[k]:mq[k + 1]]
+        assert seg[-1] and (numpy.diff(seg.astype(int)) >= 0).all()
