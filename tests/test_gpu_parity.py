@@ -133,6 +133,21 @@ def test_element_ranges_accumulate(ctx):
     assert util.relerr(sum(p[1][0] for p in parts), full_r[0]) <= 1e-14
 
 
+@pytest.mark.parametrize('nelems,degree,btype,ncomp', [((9, 7), 3, 'std', 1), ((5, 4, 3), 3, 'spline', 1), ((6, 5), 2, 'spline', 2)])
+def test_element_ranges_accumulate_coverage(ctx, nelems, degree, btype, ncomp):
+    # the same contract on the coverage route (element-set kernel on the element set "everything": the element range becomes a
+    # range of the selection), against the oracle
+    prob = _random_problem(5, nelems, degree, ncomp=ncomp, btype=btype)
+    plan = _plan(ctx, prob)
+    nd = prob.ndims
+    D, C = [engine.form_stiffness(nd, ncomp) + .5 * engine.form_mass(nd, ncomp)], [engine.form_load(nd, ncomp)]
+    mats, vecs = c_oracle.assemble(prob, [('generic', D[0])], [('generic', C[0])])
+    n = prob.ntotal
+    parts = [plan.assemble_host(D, C, elem_range=r) for r in ((0, n // 3), (n // 3, n // 3), (n // 3, n))]
+    assert util.relerr(sum(p[0][0] for p in parts), mats[0][0]) <= TOL
+    assert util.relerr(sum(p[1][0] for p in parts), vecs[0]) <= TOL
+
+
 ROWS_CASES = [
     dict(nelems=(10, 9, 11), degree=2), dict(nelems=(9, 8, 7), degree=1), dict(nelems=(3, 13, 18), degree=2), dict(nelems=(1, 1, 1), degree=2),
     dict(nelems=(2, 1, 1), degree=1), dict(nelems=(6, 5, 4), degree=2, btype='std'), dict(nelems=(5, 4, 6), degree=3), dict(nelems=(12, 15), degree=2),
