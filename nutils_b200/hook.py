@@ -1,0 +1,613 @@
+'''The reference-side half of the drop-in: evalf/nutils' own ``Sample.integral`` routed to the CUDA path.
+
+The reference offers exactly one interception point on the integration path, the ``__nutils_dispatch__`` protocol
+(src/nutils/_util.py:813-832): a positional argument whose TYPE defines ``__nutils_dispatch__`` is offered the call first
+and returns ``NotImplemented`` to decline.  ``Sample.integral`` is a dispatched method (sample.py:177) and ``self`` is
+positional argument 0, so
+
+    import nutils_b200.hook; nutils_b200.hook.install()
+
+gives ``nutils.sample.Sample`` that attribute (nothing else of the reference is touched) and every
+``topo.integral(...)`` / ``sample.integral(...)`` / ``topo.integrate(...)`` of an UNMODIFIED script lands in
+:func:`_dispatch`.  What comes back is a ``function.Array`` like the reference's own ``_Integral`` (sample.py:944-956)
+whose lowering is an evaluable node (:class:`B200Sum`) with the semantics of the stock ``LoopSum`` over the elements:
+
+* it supports everything ``solver.System`` does with an integral before evaluating it -- ``evaluable.derivative`` to the
+  test and trial arguments (solver.py:239-251), ``simplified``, ``replace_arguments``, ``as_csr`` (evaluable.py:5679);
+* when it is about to be EVALUATED (``_optimized_for_numpy`` / ``_assparse``, i.e. inside ``evaluable.compile``,
+  evaluable.py:6532) the integrand is recognised by PROBING: the stock per-element evaluable is evaluated for a handful
+  of elements and fitted with the closed form the kernels assemble,
+
+      A[(i,c),(j,e)] = sum_q w_q |det J| sum_xy D[c][x][e][y] d_x N_i d_y N_j ,   b[(i,c)] = sum_q w_q |det J| sum_x C[c][x] d_x N_i
+
+  (d_0 = value, d_k = d/dx_k) with CONSTANT D, C; the fit is verified on further elements;
+* recognised: values come from ``b2_assemble_host`` (engine.Plan), the CSR pattern from ``b2_pattern_export_host``;
+* anything else -- integrands with solution-dependent or position-dependent coefficients, samples that are not plain
+  tensor Gauss samples of a structured topology, bases that are not StructuredBasis -- DECLINES: the node turns itself
+  back into the stock ``LoopSum`` and the reference evaluates it as if the hook were not there (the reference's own
+  convention for "not mine", _util.py:826-829).
+
+The recognition is numerical, so it does not depend on how the script spells the integrand (namespace expressions,
+``function.outer(basis.grad(geom))``, fields and ``System``): mass, Laplace / anisotropic diffusion, elasticity, loads.
+'''
+
+import importlib
+import itertools
+import typing
+
+import numpy
+
+from . import adapter, engine
+
+_NT = {}            # the reference's modules, filled by install()
+_REGISTRY = {}      # token -> _Info (python-side state of an integral; evaluable nodes only carry the token)
+_PLANS = {}         # plan id -> recognised closed form (B200Values nodes only carry the id)
+_COUNTER = itertools.count(1)
+STATS = {'offered': 0, 'accelerated': 0, 'declined': 0, 'reasons': []}
+PROBE_TOL = 1e-10   # relative misfit of the closed form on the probe elements above which the integrand is declined
+
+
+class Declined(Exception):
+    'the integral is not one the CUDA path assembles; the stock evaluable takes over'
+
+
+# ---- backend: the only place that touches the device (tests on a CPU-only box substitute the oracle here) --------------
+
+class GpuBackend:
+    'engine.Plan per (basis, rules, geometry); values through b2_assemble_host, pattern through b2_pattern_export_host'
+
+    def __init__(self, device=0):
+        self.device = device
+        self._plans = {}
+
+    def plan(self, spec):
+        key = spec['key']
+        plan = self._plans.get(key)
+        if plan is None:
+            ctx = engine.Context.get(self.device)
+            plan = self._plans[key] = engine.Plan(ctx, spec['bases'], spec['rules'], spec['nodes'], ncomp=spec['ncomp'])
+        return plan
+
+    def pattern(self, spec):
+        return self.plan(spec).csr_pattern()
+
+    def assemble(self, spec, Ds, Cs):
+        return self.plan(spec).assemble_host(Ds, Cs)
+
+
+BACKEND = GpuBackend()
+
+
+def set_backend(backend):
+    global BACKEND
+    BACKEND = backend
+
+
+# ---- host-side jets of the local basis functions (recognition only; the assembly never runs on the host) ---------------
+
+def element_jets(bases, nodes, eidx, xi):
+    '''Values and PHYSICAL gradients of the local functions of element `eidx` (index per dimension) at local points
+    xi[nq, nd] for a multilinear nodal geometry: returns (phi[nq, n_e, 1+nd], detJ[nq]); local functions in C order.'''
+    nd = len(bases)
+    nq = len(xi)
+    N = numpy.ones((nq, 1))
+    dN = [numpy.ones((nq, 1)) for _ in range(nd)]
+    for d, b in enumerate(bases):
+        c = b.coeffs[b.setidx[eidx[d]]]
+        p = b.degree
+        v = numpy.stack([numpy.polyval(c[a], xi[:, d]) for a in range(p + 1)], 1)
+        g = numpy.stack([numpy.polyval(c[a, :-1] * numpy.arange(p, 0, -1.), xi[:, d]) if p else numpy.zeros(nq) for a in range(p + 1)], 1)
+        N = (N[:, :, None] * v[:, None, :]).reshape(nq, -1)
+        dN = [(dN[k][:, :, None] * (g if k == d else v)[:, None, :]).reshape(nq, -1) for k in range(nd)]
+    J = numpy.zeros((nq, nd, nd))
+    for corner in itertools.product((0, 1), repeat=nd):
+        X = nodes[(slice(None),) + tuple(e + c for e, c in zip(eidx, corner))]
+        for k in range(nd):
+            dphi = numpy.ones(nq)
+            for d in range(nd):
+                dphi = dphi * ((1. if corner[d] else -1.) if d == k else (xi[:, d] if corner[d] else 1. - xi[:, d]))
+            J[:, :, k] += X[None, :] * dphi[:, None]
+    Jinv = numpy.linalg.inv(J)
+    det = abs(numpy.linalg.det(J))
+    phi = numpy.empty((nq, N.shape[1], 1 + nd))
+    phi[:, :, 0] = N
+    phi[:, :, 1:] = numpy.einsum('kqa,qkj->qaj', numpy.stack(dN), Jinv)
+    return phi, det
+
+
+def element_dofs(bases, eidx):
+    'global (scalar) dofs of the local functions of element `eidx`, C order (function.py:3080-3093)'
+    dofs = numpy.zeros(1, dtype=numpy.int64)
+    for b, e in zip(bases, eidx):
+        dofs = (dofs[:, None] * b.ndofs + (b.start[e] + numpy.arange(b.degree + 1))[None, :]).ravel()
+    return dofs
+
+
+# ---- python-side state of one intercepted integral ---------------------------------------------------------------------
+
+class _Info:
+    def __init__(self, sample, integrand, shape, coords, weights, rules):
+        self.sample = sample
+        self.integrand = integrand
+        self.shape = shape          # elements per dimension
+        self.coords = coords        # points of one element [nq, nd]
+        self.weights = weights
+        self.rules = rules          # per-dimension (points, weights)
+        self._tree = None
+        self._nodes = None
+        self._digest = None
+
+    def tree(self):
+        'bases and geometries that occur in the integrand (function.Array tree walk)'
+        if self._tree is None:
+            F = _NT['function']
+            bases, geoms, seen = [], [], set()
+            stack = [self.integrand]
+            while stack:
+                a = stack.pop()
+                if id(a) in seen:
+                    continue
+                seen.add(id(a))
+                if isinstance(a, F.Basis):
+                    if not any(a is b for b in bases):
+                        bases.append(a)
+                    continue
+                name = type(a).__name__
+                if name in ('_Jacobian', '_Gradient', '_SurfaceGradient', '_Normal', '_ExteriorNormal') and hasattr(a, '_geom'):
+                    geoms.append(a._geom)
+                for k, v in vars(a).items():
+                    if k.startswith('_Array__'):
+                        continue
+                    if isinstance(v, F.Array):
+                        stack.append(v)
+                    elif isinstance(v, (tuple, list)):
+                        stack.extend(w for w in v if isinstance(w, F.Array))
+                    elif isinstance(v, dict):
+                        stack.extend(w for w in v.values() if isinstance(w, F.Array))
+            self._tree = bases, geoms
+        return self._tree
+
+    def corner_sample(self):
+        'a sample on the same transforms whose points are the 2^nd corners of every element'
+        nd = len(self.shape)
+        corners = numpy.array(list(itertools.product((0., 1.), repeat=nd)))
+        pts = _NT['pointsseq'].PointsSequence.uniform(_NT['points'].CoordsPoints(_NT['types'].arraydata(corners)), self.sample.nelems)
+        return _NT['sample'].Sample.new(self.sample.spaces[0], self.sample.transforms, pts)
+
+    def nodes(self):
+        '''nodal coordinates float64[nd, n0+1, ...] of the geometry of the integrand, evaluated by the reference at the
+        element corners (one-off, host); declines if the integrand has no or more than one geometry, or if the geometry is
+        discontinuous across elements.  Whether it is MULTILINEAR inside the elements is settled by the probing.'''
+        if self._nodes is None:
+            bases, geoms = self.tree()
+            if not geoms:
+                raise Declined('no geometry in the integrand')
+            nd = len(self.shape)
+            cs = self.corner_sample()
+            vals = []
+            for g in geoms:
+                if g.shape[-1] != nd:
+                    raise Declined('geometry dimension differs from the topology dimension')
+                if g.arguments:
+                    raise Declined('geometry depends on arguments')
+                x = numpy.asarray(cs.eval(g))
+                x = x.reshape(x.shape[0], -1, nd)[:, 0, :]   # broadcast copies of the geometry carry leading axes
+                vals.append(x)
+            scale = abs(vals[0]).max() or 1.
+            if any(abs(v - vals[0]).max() > 1e-13 * scale for v in vals[1:]):
+                raise Declined('more than one geometry in the integrand')
+            x = vals[0].reshape(self.shape + (2,) * nd + (nd,))
+            nodes = numpy.full((nd,) + tuple(n + 1 for n in self.shape), numpy.nan)
+            for corner in itertools.product((0, 1), repeat=nd):
+                sl = tuple(slice(c, n + c) for c, n in zip(corner, self.shape))
+                v = numpy.moveaxis(x[(Ellipsis,) + corner + (slice(None),)], -1, 0)
+                old = nodes[(slice(None),) + sl]
+                if (abs(numpy.where(numpy.isnan(old), v, old) - v) > 1e-12 * scale).any():
+                    raise Declined('geometry is discontinuous across elements')
+                nodes[(slice(None),) + sl] = v
+            self._nodes = nodes
+        return self._nodes
+
+    def nodes_digest(self):
+        if self._digest is None:
+            import hashlib
+            self._digest = hashlib.sha1(numpy.ascontiguousarray(self.nodes()).tobytes()).hexdigest()
+        return self._digest
+
+
+def _sample_info(sample):
+    'shape / points of a sample the CUDA path covers, else Declined'
+    if type(sample).__name__ != '_DefaultIndex' or len(sample.spaces) != 1:
+        raise Declined('sample type {}'.format(type(sample).__name__))
+    trans = sample.transforms[0]
+    if type(trans).__name__ != 'StructuredTransforms' or not all(getattr(a, 'isdim', False) and not a.isperiodic for a in trans._axes):
+        raise Declined('not a volume sample of a non-periodic structured topology')
+    shape = tuple(len(a) for a in trans._axes)
+    if type(sample.points).__name__ != '_Uniform' or sample.nelems == 0:
+        raise Declined('points differ per element')
+    pts = sample.points.get(0)
+    try:
+        coords = numpy.asarray(pts.coords, dtype=float)
+        weights = numpy.asarray(pts.weights, dtype=float)
+    except Exception:
+        raise Declined('points without weights')
+    nd = len(shape)
+    if coords.ndim != 2 or coords.shape[1] != nd or not 1 <= nd <= 3:
+        raise Declined('dimension')
+    # tensor rule?  per-dimension points ascending, C-order outer product (points.py:144-164)
+    rules = []
+    nq = [len(numpy.unique(numpy.round(coords[:, d], 14))) for d in range(nd)]
+    if int(numpy.prod(nq)) != len(weights):
+        raise Declined('points are not a tensor rule')
+    W = weights.reshape(nq)
+    X = coords.reshape(tuple(nq) + (nd,))
+    for d in range(nd):
+        idx = [0] * nd
+        idx[d] = slice(None)
+        x = X[tuple(idx) + (d,)]
+        w = W.sum(axis=tuple(k for k in range(nd) if k != d))
+        rules.append((numpy.array(x), numpy.array(w)))
+    from . import points as _points
+    tc, tw = _points.tensor_points(rules)
+    if abs(tc - coords).max() > 1e-14 or abs(tw - weights).max() > 1e-14 * abs(weights).max() or any(len(r[0]) > 5 for r in rules):
+        raise Declined('points are not a tensor rule')
+    return shape, coords, weights, rules
+
+
+# ---- dispatch ----------------------------------------------------------------------------------------------------------
+
+def _dispatch(cls, func, args, kwargs):
+    'the __nutils_dispatch__ classmethod given to nutils.sample.Sample (_util.py:813-832)'
+    S = _NT['sample'].Sample
+    if func is not S.integral or len(args) != 2 or kwargs:
+        return NotImplemented
+    sample, integrand = args
+    STATS['offered'] += 1
+    try:
+        shape, coords, weights, rules = _sample_info(sample)
+    except Declined as e:
+        _note_declined(str(e))
+        return NotImplemented
+    integrand = _NT['function'].Array.cast(integrand)
+    if integrand.dtype == complex:
+        _note_declined('complex integrand')
+        return NotImplemented
+    token = next(_COUNTER)
+    _REGISTRY[token] = _Info(sample, integrand, shape, coords, weights, rules)
+    return _NT['Integral'](integrand, sample, token)
+
+
+def _note_declined(reason):
+    STATS['declined'] += 1
+    if len(STATS['reasons']) < 100:
+        STATS['reasons'].append(reason)
+
+
+def install(nutils=None):
+    '''Activate the hook on the reference package `nutils` (default: ``import nutils``).  Idempotent.'''
+    nt = nutils or importlib.import_module('nutils')
+    if _NT.get('nutils') is nt:
+        return
+    for name in ('sample', 'function', 'evaluable', 'points', 'pointsseq', 'types', '_util', 'util'):
+        try:
+            _NT[name] = importlib.import_module(nt.__name__ + '.' + name)
+        except ImportError:
+            if name != 'util':
+                raise
+    _NT['nutils'] = nt
+    _define_classes()
+    _NT['sample'].Sample.__nutils_dispatch__ = classmethod(_dispatch)
+
+
+def uninstall():
+    if 'sample' in _NT and '__nutils_dispatch__' in vars(_NT['sample'].Sample):
+        del _NT['sample'].Sample.__nutils_dispatch__
+    _NT.clear()
+
+
+# ---- recognition by probing --------------------------------------------------------------------------------------------
+
+def _probe_elements(shape, rng, n):
+    'corner, centre and pseudo-random elements (index tuples), no duplicates'
+    out = []
+    for c in itertools.product(*[(0, m - 1) for m in shape]):
+        if c not in out:
+            out.append(c)
+    c = tuple(m // 2 for m in shape)
+    if c not in out:
+        out.append(c)
+    for _ in range(4 * n):
+        if len(out) >= n:
+            break
+        c = tuple(int(rng.randint(m)) for m in shape)
+        if c not in out:
+            out.append(c)
+    return out
+
+
+def _recognise(node):
+    'closed form of a B200Sum node -> dict(spec, kind, D or C, ...) or Declined'
+    ev = _NT['evaluable']
+    info = _REGISTRY[node.token]
+    if any(isinstance(a, ev.Argument) for a in node.arguments):
+        raise Declined('integrand depends on arguments (nonlinear or not yet linearised)')
+    groups = node.groups
+    if len(groups) not in (1, 2) or any(g not in (1, 2) for g in groups):
+        raise Declined('{} array axes groups'.format(len(groups)))
+    dims = [int(n.__index__()) for n in node.shape]
+    nd = len(info.shape)
+    na = nd + 1
+    # axes of every group: basis axis [, component axis]
+    pos = 0
+    gaxes = []
+    for g in groups:
+        gaxes.append(tuple(range(pos, pos + g)))
+        pos += g
+    ncomp = [dims[ax[1]] if len(ax) == 2 else 1 for ax in gaxes]
+    if len(groups) == 2 and ncomp[0] != ncomp[1]:
+        raise Declined('test and trial spaces with different numbers of components')
+    nc = ncomp[0]
+    if nc > 3:
+        raise Declined('more than three components')
+    fbases, _ = info.tree()
+    cands = [b for b in fbases if hasattr(b, '_start_dofs') and tuple(b._transforms_shape) == info.shape and all(len(b) == dims[ax[0]] for ax in gaxes)]
+    if not cands:
+        raise Declined('no structured basis of the topology matches the array axes')
+    nodes = info.nodes()
+    # stock sparse chunks of the per-element integral with the loop index turned into an argument
+    probe_arg = ev.InRange(ev.Argument('_b200_ielem', (), int), node.length)
+    index = node.index
+    chunks = tuple(tuple(_replace_index(a, index, probe_arg) for a in chunk) for chunk in node.func.simplified._assparse)
+    if not chunks:
+        raise Declined('integrand is identically zero')
+    f = ev.compile(chunks)
+    rng = numpy.random.RandomState(len(dims) * 7919 + info.sample.nelems)
+    elems = _probe_elements(info.shape, rng, 10 + 2 * nd)
+    data = []
+    for e in elems:
+        ielem = int(numpy.ravel_multi_index(e, info.shape))
+        data.append([tuple(numpy.asarray(a).ravel() for a in chunk) for chunk in f({'_b200_ielem': ielem})])
+    last = None
+    for basis in cands:
+        try:
+            return _fit(node, info, basis, nodes, elems, data, gaxes, nc)
+        except Declined as e:
+            last = e
+    raise last
+
+
+def _fit(node, info, basis, nodes, elems, data, gaxes, nc):
+    nd = len(info.shape)
+    na = nd + 1
+    bases = adapter.bases1d_from_structured_basis(basis)
+    k = len(gaxes)
+    A_rows, rhs = [], []
+    blocks = []
+    for e, chunks in zip(elems, data):
+        ldofs = element_dofs(bases, e)
+        lookup = {int(d): a for a, d in enumerate(ldofs)}
+        ne = len(ldofs)
+        T = numpy.zeros((ne, nc) * k)
+        for chunk in chunks:
+            *idx, vals = chunk
+            if not len(vals):
+                continue
+            # entries outside the element's own functions are tolerated when they are exact zeros (dense chunks)
+            keep = numpy.ones(len(vals), dtype=bool)
+            for ax in gaxes:
+                keep &= numpy.isin(idx[ax[0]], ldofs)
+            if (vals[~keep] != 0).any():
+                raise Declined('dofs of the integrand are not those of the structured basis')
+            idx = [i[keep] for i in idx]
+            vals = vals[keep]
+            where = []
+            for ax in gaxes:
+                where.append(numpy.array([lookup[int(i)] for i in idx[ax[0]]], dtype=int))
+                where.append(idx[ax[1]] if len(ax) == 2 else numpy.zeros(len(vals), dtype=int))
+            numpy.add.at(T, tuple(where), vals)
+        phi, det = element_jets(bases, nodes, e, info.coords)
+        wdet = info.weights * det
+        if k == 2:
+            E = numpy.einsum('q,qax,qby->xyab', wdet, phi, phi).reshape(na * na, ne * ne)
+        else:
+            E = numpy.einsum('q,qax->xa', wdet, phi)
+        blocks.append((T, E))
+    nfit = max(len(blocks) - 4, (len(blocks) + 1) // 2)   # the last elements are the hold-out set
+    scale = max(abs(T).max() for T, E in blocks)
+    if scale == 0.:
+        raise Declined('integrand vanishes on the probe elements')
+    if k == 2:
+        D = numpy.zeros((nc, na, nc, na))
+        for c in range(nc):
+            for e_ in range(nc):
+                A = numpy.concatenate([E.T for T, E in blocks[:nfit]])
+                b = numpy.concatenate([T[:, c, :, e_].ravel() for T, E in blocks[:nfit]])
+                sol = numpy.linalg.lstsq(A, b, rcond=None)[0]
+                D[c, :, e_, :] = sol.reshape(na, na)
+        for T, E in blocks:
+            model = numpy.einsum('cxey,xyab->acbe', D, E.reshape(na, na, T.shape[0], T.shape[0]))
+            if abs(model - T).max() > PROBE_TOL * scale:
+                raise Declined('integrand is not a constant-coefficient bilinear form in (N, grad N)')
+        D[abs(D) < 1e-13 * abs(D).max()] = 0.
+        Dt = D.transpose(2, 3, 0, 1)
+        if abs(D - Dt).max() <= 1e-13 * abs(D).max():
+            D = .5 * (D + Dt)
+        coef = D
+    else:
+        C = numpy.zeros((nc, na))
+        for c in range(nc):
+            A = numpy.concatenate([E.T for T, E in blocks[:nfit]])
+            b = numpy.concatenate([T[:, c] for T, E in blocks[:nfit]])
+            C[c] = numpy.linalg.lstsq(A, b, rcond=None)[0]
+        for T, E in blocks:
+            if abs(numpy.einsum('cx,xa->ac', C, E) - T).max() > PROBE_TOL * scale:
+                raise Declined('integrand is not a constant-coefficient linear form in (N, grad N)')
+        C[abs(C) < 1e-13 * abs(C).max()] = 0.
+        coef = C
+    spec = dict(bases=bases, rules=info.rules, nodes=nodes, ncomp=nc, key=(id(basis), id(info.sample), nc, info.nodes_digest()))
+    plan = dict(spec=spec, kind='matrix' if k == 2 else 'vector', coef=coef, nc=nc, nbasis=len(basis), gaxes=gaxes, keep=(basis, info), id=next(_COUNTER))
+    _PLANS[plan['id']] = plan
+    return plan
+
+
+def _plan(node):
+    d = node.__dict__
+    if '_b200_plan' not in d:
+        try:
+            d['_b200_plan'] = _recognise(node)
+            STATS['accelerated'] += 1
+        except Declined as e:
+            d['_b200_plan'] = None
+            _note_declined(str(e))
+    return d['_b200_plan']
+
+
+def _replace_index(value, index, new):
+    return _NT['replace_index'](value, index, new)
+
+
+# ---- the classes that subclass the reference's (created once the reference is imported) --------------------------------
+
+def _define_classes():
+    ev = _NT['evaluable']
+    F = _NT['function']
+    util = _NT['_util']
+
+    @util.shallow_replace
+    def replace_index(value, index, new):
+        if value is index:
+            return new
+    _NT['replace_index'] = replace_index
+
+    class Integral(F.Array):
+        'the counterpart of nutils.sample._Integral (sample.py:944-956) whose lowering is a B200Sum instead of a LoopSum'
+
+        def __init__(self, integrand, sample, token):
+            self._integrand = integrand
+            self._sample = sample
+            self._token = token
+            super().__init__(shape=integrand.shape, dtype=float if integrand.dtype in (bool, int) else integrand.dtype,
+                             spaces=integrand.spaces - frozenset(sample.spaces), arguments=integrand.arguments)
+
+        def lower(self, args):
+            ielem = ev.loop_index('_sample_{}'.format(len(args.args)), self._sample.nelems)
+            weights = ev.astype(self._sample.get_evaluable_weights(ielem), self.dtype)
+            integrand = ev.astype(self._integrand.lower(args * self._sample.get_lower_args(ielem)), self.dtype)
+            elem_integral = ev.einsum('B,ABC->AC', weights, integrand, B=weights.ndim, C=self.ndim)
+            if len(args.points_shape):   # an integral evaluated inside another sample: not ours
+                return ev.loop_sum(elem_integral, ielem)
+            return B200Sum(elem_integral, elem_integral.shape, ielem.loop_id, ielem.length, self._token, (1,) * self.ndim)
+
+    class B200Sum(ev.Array):
+        '''sum over the elements of `func` (which depends on the loop index): the semantics of evaluable.LoopSum
+        (evaluable.py:5234-5343), evaluated by the CUDA path when the integrand is recognised, by the stock loop otherwise'''
+
+        func: ev.Array
+        shape: typing.Tuple[ev.Array, ...]
+        loop_id: ev._LoopId
+        length: ev.Array
+        token: int
+        groups: typing.Tuple[int, ...]
+
+        @property
+        def dtype(self):
+            return self.func.dtype
+
+        @property
+        def index(self):
+            return ev._LoopIndex(self.loop_id, self.length)
+
+        @property
+        def dependencies(self):
+            args = sorted((a for a in self.func.arguments if isinstance(a, ev.Argument)), key=lambda a: a.name)
+            return (*self.shape, self.length, *args)
+
+        @property
+        def stock(self):
+            return ev.loop_sum(self.func, self.index)
+
+        def _derivative(self, var, seen):
+            if var.dtype in (bool, int) or var not in self.arguments:
+                return ev.Zeros(self.shape + var.shape, dtype=self.dtype)
+            return B200Sum(ev.derivative(self.func, var, seen), self.shape + var.shape, self.loop_id, self.length, self.token, self.groups + (len(var.shape),))
+
+        def _simplified(self):
+            if ev.iszero(self.func):
+                return ev.zeros_like(self)
+
+        def _optimized_for_numpy(self):
+            # the last rewriting stage of evaluable.compile (evaluable.py:6691-6694): decide who evaluates this integral
+            if _plan(self) is None:
+                return self.stock
+
+        def _argument_degree(self, argument):
+            return self.func.argument_degree(argument)
+
+        @property
+        def _assparse(self):
+            plan = _plan(self)
+            if plan is None or plan['kind'] != 'matrix':
+                return self.stock._assparse if plan is None else super()._assparse
+            rowptr, colidx = BACKEND.pattern(plan['spec'])
+            rows = numpy.repeat(numpy.arange(len(rowptr) - 1, dtype=numpy.int64), numpy.diff(rowptr))
+            nc = plan['nc']
+            idx = []
+            for ax, dof in zip(plan['gaxes'], (rows, colidx)):
+                if len(ax) == 2:
+                    idx += [dof // nc, dof % nc]
+                else:
+                    idx.append(dof)
+            return (*(ev.constant(i) for i in idx), B200Values(plan['id'])),
+
+        def _evalf(self, *args):
+            plan = _plan(self)
+            if plan is None:
+                raise RuntimeError('B200Sum evaluated without a plan (evaluable.compile(_optimize=False) is not supported)')
+            shape = tuple(int(n) for n in args[:len(self.shape)])
+            if plan['kind'] == 'vector':
+                (), (rhs,) = BACKEND.assemble(plan['spec'], [], [plan['coef']])
+                return rhs.reshape(shape)
+            (values,), () = BACKEND.assemble(plan['spec'], [plan['coef']], [])
+            rowptr, colidx = BACKEND.pattern(plan['spec'])
+            n = len(rowptr) - 1
+            dense = numpy.zeros((n, n))
+            dense[numpy.repeat(numpy.arange(n), numpy.diff(rowptr)), colidx] = values
+            nb, nc = plan['nbasis'], plan['nc']
+            if nc > 1 or any(len(ax) == 2 for ax in plan['gaxes']):
+                dense = dense.reshape(nb, nc, nb, nc)
+            return dense.reshape(shape)
+
+        def _compile(self, builder):
+            args = builder.compile(self.dependencies)
+            evalf = builder.add_constant(self._evalf)
+            out = builder.get_variable_for_evaluable(self)
+            builder.get_block_for_evaluable(self).assign_to(out, evalf.call(*args))
+            return out
+
+    class B200Values(ev.Array):
+        'the stored values (CSR order of the analytic pattern) of a recognised, argument-free matrix-valued B200Sum'
+
+        plan_id: int
+
+        dtype = float
+        dependencies = ()
+
+        @property
+        def shape(self):
+            rowptr, colidx = BACKEND.pattern(_PLANS[self.plan_id]['spec'])
+            return ev.constant(len(colidx)),
+
+        def _evalf(self):
+            plan = _PLANS[self.plan_id]
+            (values,), () = BACKEND.assemble(plan['spec'], [plan['coef']], [])
+            return values
+
+        def _compile(self, builder):
+            evalf = builder.add_constant(self._evalf)
+            out = builder.get_variable_for_evaluable(self)
+            builder.get_block_for_evaluable(self).assign_to(out, evalf.call())
+            return out
+
+    _NT['Integral'] = Integral
+    _NT['B200Sum'] = B200Sum
+    _NT['B200Values'] = B200Values

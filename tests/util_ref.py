@@ -1,0 +1,52 @@
+'''Access to the UNMODIFIED reference installed under baseline/_ref (scripts/install_reference.py; git-ignored, travels to
+the GPU box) and an oracle-backed stand-in for the device backend of nutils_b200.hook, so that the hook's plumbing can be
+tested where there is no GPU.  TEST INFRASTRUCTURE.'''
+
+import os
+import sys
+import numpy
+
+from tests import util
+
+REFDIR = os.path.join(util.ROOT, 'baseline', '_ref')
+
+
+def have_reference():
+    return os.path.isdir(os.path.join(REFDIR, 'nutils'))
+
+
+def reference():
+    'import the reference package (returns the nutils module)'
+    for path in (os.path.join(REFDIR, 'examples'), REFDIR):
+        if path not in sys.path:
+            sys.path.insert(0, path)
+    os.environ.setdefault('NUTILS_MATRIX', 'scipy')
+    import nutils
+    from nutils import export
+    export.triplot = lambda *args, **kwargs: None   # matplotlib is absent; the examples only plot with it
+    return nutils
+
+
+class OracleBackend:
+    'what hook.GpuBackend does, computed by the numpy oracle (checker for the host-side logic of the hook)'
+
+    def __init__(self):
+        self.calls = 0
+
+    def _problem(self, spec):
+        from oracle import fem_oracle
+        b1, rules = spec['bases'], spec['rules']
+        return fem_oracle.Problem(tuple(b.nelems for b in b1), [b.degree for b in b1], [b.coeffs for b in b1], [b.setidx for b in b1], [b.start for b in b1],
+                                  [b.ndofs for b in b1], [r[0] for r in rules], [r[1] for r in rules], spec['nodes'], ncomp=spec['ncomp'])
+
+    def pattern(self, spec):
+        from oracle import fem_oracle
+        na, nc = len(spec['bases']) + 1, spec['ncomp']
+        mats, vecs = fem_oracle.assemble(self._problem(spec), [('generic', numpy.zeros((nc, na, nc, na)))], [])
+        return mats[0][1], mats[0][2]
+
+    def assemble(self, spec, Ds, Cs):
+        from oracle import fem_oracle
+        self.calls += 1
+        mats, vecs = fem_oracle.assemble(self._problem(spec), [('generic', numpy.asarray(D)) for D in Ds], [('generic', numpy.asarray(C)) for C in Cs])
+        return [m[0] for m in mats], list(vecs)
