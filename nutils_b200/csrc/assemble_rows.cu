@@ -28,6 +28,8 @@
 //
 // Dimension names inside this file: 0 = marching (slowest dof index), 1, 2 = tile dimensions.
 
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstring>
 
@@ -60,15 +62,18 @@ struct RowParams {
   double* valK;
   double* valM;
   double* rhs;
+  int g_ebeg;  // first element layer held by the precomputed geometry array (GPRE launches)
+  void* host_gcache;  // host only: GeomCache shared by the launches of one b2_assemble_rows_device call
 };
 
-template <int P_, int T1_, int T2_, int QC_, int NT_, int SPLIT_, int NG_ = 7>
+template <int P_, int T1_, int T2_, int QC_, int NT_, int SPLIT_, int NG_ = 7, int OCC_ = 1>
 struct RCfg {
+  static constexpr int OCC = OCC_;  // CTAs per SM the configuration is sized for (registers, shared memory)
   static constexpr int NG = NG_;  // components of the coefficient per point: 7 = symmetric Ghat (6) + w|det|, 10 = general Ghat (9) + w|det|
   static constexpr int P = P_, NB = P + 1, NQ = P + 1, WD = 2 * P + 1;
   static constexpr int T1 = T1_, T2 = T2_, QC = QC_, NT = NT_, NW = NT / 32;
   // one CTA per SM; the register file is split over the 4 sub-partitions (16384 each), warps are dealt round-robin
-  static constexpr int MAXREG = (16384 / ((NW + 3) / 4) / 32 / 8 * 8) > 255 ? 255 : (16384 / ((NW + 3) / 4) / 32 / 8 * 8);
+  static constexpr int MAXREG = (16384 / (((NW + 3) / 4) * OCC) / 32 / 8 * 8) > 255 ? 255 : (16384 / (((NW + 3) / 4) * OCC) / 32 / 8 * 8);
   static constexpr int SPLIT = SPLIT_;                    // bit 0: S1 warp items split in three term groups, bit 1: S2 items in two (true = both)
   static constexpr int H1 = T1 + P, H2 = T2 + P;          // halo elements per tile dimension
   static constexpr int NQ1 = H1 * NQ, NQ2 = H2 * NQ;      // halo points
@@ -429,13 +434,121 @@ __device__ __forceinline__ void g_column(const RowParams& prm, int form, const d
   }
 }
 
+// ---- precomputed geometry (GPRE launches): Ghat and w|det J| of EVERY quadrature point are computed ONCE by k_geom3d into HBM,
+// laid out [component][Q2][Q0][Q1] so that the halo box of a CTA and layer -- (T1+P)(P+1) x QC x (T2+P)(P+1) points x NG
+// components -- is ONE TMA tensor copy (cp.async.bulk.tensor.4d) straight into sG, out-of-domain points zero-filled by the
+// hardware.  The tile kernel then spends no FP64 instruction on geometry (the halo made it 2.25x redundant at tile 4x4: a third of
+// all instructions); the price is HBM traffic (8 NG bytes per point written once, read ~(1+P/T)^2 times), which this FP64-bound
+// kernel has to spare.
+struct GeomParams {
+  GeomView G;
+  QuadView Q;
+  int n0, n1, n2, ebeg, iso;
+  double kc[6];
+  double* out;
+  long long pitch1, sQ2, scomp;  // strides in doubles: Q0 -> pitch1, Q2 -> sQ2, component -> scomp
+};
+
+template <int P>
+__global__ void __launch_bounds__(128) k_geom3d(const GeomParams prm) {
+  constexpr int NQ = P + 1;
+  const int Q1 = blockIdx.x * 128 + threadIdx.x, Q2 = blockIdx.y, e0 = prm.ebeg + blockIdx.z;
+  if (Q1 >= NQ * prm.n1) return;
+  const int e1 = Q1 / NQ, q1 = Q1 % NQ, e2 = Q2 / NQ, q2 = Q2 % NQ;
+  const double x1 = prm.Q.x[1][q1], x2 = prm.Q.x[2][q2];
+  const double w12 = prm.Q.w[1][q1] * prm.Q.w[2][q2];
+  double J0[3], D1a[3], D1d[3], D2a[3], D2d[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double* X = prm.G.nodes + i * prm.G.nnodes + (long long)e0 * prm.G.stride[0] + (long long)e1 * prm.G.stride[1] + e2;
+    const long long SP = prm.G.stride[0], S1 = prm.G.stride[1];
+    const double c000 = __ldg(X), c001 = __ldg(X + 1), c010 = __ldg(X + S1), c011 = __ldg(X + S1 + 1);
+    const double c100 = __ldg(X + SP), c101 = __ldg(X + SP + 1), c110 = __ldg(X + SP + S1), c111 = __ldg(X + SP + S1 + 1);
+    const double d00 = c001 - c000, d01 = c011 - c010, d10 = c101 - c100, d11 = c111 - c110;
+    const double m00 = fma(x2, d00, c000), m01 = fma(x2, d01, c010), m10 = fma(x2, d10, c100), m11 = fma(x2, d11, c110);
+    const double g0 = fma(x1, d01 - d00, d00), g1 = fma(x1, d11 - d10, d10);
+    const double f0 = m01 - m00, f1 = m11 - m10;
+    const double h0 = fma(x1, f0, m00), h1 = fma(x1, f1, m10);
+    J0[i] = h1 - h0;
+    D1a[i] = f0; D1d[i] = f1 - f0;
+    D2a[i] = g0; D2d[i] = g1 - g0;
+  }
+  double* o = prm.out + (long long)Q2 * prm.sQ2 + (long long)blockIdx.z * NQ * prm.pitch1 + Q1;
+#pragma unroll
+  for (int q0 = 0; q0 < NQ; q0++) {
+    const double x0 = prm.Q.x[0][q0];
+    double J1[3], J2[3], A[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      J1[i] = fma(x0, D1d[i], D1a[i]);
+      J2[i] = fma(x0, D2d[i], D2a[i]);
+    }
+    A[0] = J1[1] * J2[2] - J1[2] * J2[1]; A[1] = J1[2] * J2[0] - J1[0] * J2[2]; A[2] = J1[0] * J2[1] - J1[1] * J2[0];
+    A[3] = J2[1] * J0[2] - J2[2] * J0[1]; A[4] = J2[2] * J0[0] - J2[0] * J0[2]; A[5] = J2[0] * J0[1] - J2[1] * J0[0];
+    A[6] = J0[1] * J1[2] - J0[2] * J1[1]; A[7] = J0[2] * J1[0] - J0[0] * J1[2]; A[8] = J0[0] * J1[1] - J0[1] * J1[0];
+    const double det = J0[0] * A[0] + J0[1] * A[1] + J0[2] * A[2];
+    const double adet = fabs(det), w = prm.Q.w[0][q0] * w12;
+    const double sc = w * rcp_pos(adet);
+    double* oq = o + q0 * prm.pitch1;
+    if (prm.iso) {
+      const double sk = sc * prm.kc[0];
+      oq[0 * prm.scomp] = sk * (A[0] * A[0] + A[1] * A[1] + A[2] * A[2]);
+      oq[1 * prm.scomp] = sk * (A[0] * A[3] + A[1] * A[4] + A[2] * A[5]);
+      oq[2 * prm.scomp] = sk * (A[0] * A[6] + A[1] * A[7] + A[2] * A[8]);
+      oq[3 * prm.scomp] = sk * (A[3] * A[3] + A[4] * A[4] + A[5] * A[5]);
+      oq[4 * prm.scomp] = sk * (A[3] * A[6] + A[4] * A[7] + A[5] * A[8]);
+      oq[5 * prm.scomp] = sk * (A[6] * A[6] + A[7] * A[7] + A[8] * A[8]);
+    } else {
+      double T[9];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        T[k * 3 + 0] = A[k * 3] * prm.kc[0] + A[k * 3 + 1] * prm.kc[1] + A[k * 3 + 2] * prm.kc[2];
+        T[k * 3 + 1] = A[k * 3] * prm.kc[1] + A[k * 3 + 1] * prm.kc[3] + A[k * 3 + 2] * prm.kc[4];
+        T[k * 3 + 2] = A[k * 3] * prm.kc[2] + A[k * 3 + 1] * prm.kc[4] + A[k * 3 + 2] * prm.kc[5];
+      }
+      int t = 0;
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int l = k; l < 3; l++) oq[(t++) * prm.scomp] = sc * (T[k * 3] * A[l * 3] + T[k * 3 + 1] * A[l * 3 + 1] + T[k * 3 + 2] * A[l * 3 + 2]);
+    }
+    oq[6 * prm.scomp] = w * adet;
+  }
+}
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst), "l"(map), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+               : "memory");
+}
+
 // The kernel.  Per element layer l two barrier-separated phases, software-pipelined so that every phase mixes FP64-heavy and
 // shared-memory-heavy work of different layers and idle warps of one task pick up the other (dynamic warp-level work queue):
 //   phase X:  S3(l-1) + store(l-1)  [static: the thread owns its dof pair's accumulators]   ||   S1(l)   [queue]
 //   phase Y:  S2(l)  [queue]   ||   G(l+1)  [queue, 32 columns per item]
 // NFORM > 1: vector-valued stiffness-like launch, forms = column components, one pipeline step per (layer, form, chunk)
-template <class C, bool FK, bool FM, int NFORM, bool VEC>
-__global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
+template <class C, bool FK, bool FM, int NFORM, bool VEC, bool GPRE>
+__global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __grid_constant__ CUtensorMap gmap) {
+  static_assert(!GPRE || (C::NG == 7 && NFORM == 1 && !VEC), "precomputed geometry: scalar forms");
   static_assert(NFORM == 1 || (FK && !FM && C::NG == 10), "several forms per launch: general stiffness-like forms only");
   constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, QC = C::QC, NT = C::NT, NW = C::NW;
   constexpr int T1 = C::T1, T2 = C::T2, H1 = C::H1, H2 = C::H2, NQ1 = C::NQ1, NQ2 = C::NQ2;
@@ -449,7 +562,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
   const BasisView& B = prm.B;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   double* sG = smem + C::OFF_G;       // [7][NQ2][q0 NQ1 + Q1]
   double* sT2 = smem + C::OFF_T2;     // [q0][group][N12P] with stride T2QS per q0
   double* sT1 = smem + C::OFF_T1;     // [NQ1][T1QS] = [NQ1][term][q0 NP2P + pair2]
@@ -464,6 +577,8 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
   int* sRowB = reinterpret_cast<int*>(smem + C::OFF_ROW);  // 2 x [NB][4] = lo, wid, cum of dof e0+a along dimension 0
   int* sSet0 = reinterpret_cast<int*>(smem + C::OFF_SET);  // [MAXL] coefficient set of the layers of this segment
   int* sCnt = sSet0 + C::MAXL;                             // [2] work-queue heads of phases X and Y
+  const unsigned gbar = smem_addr(sCnt + 2);               // mbarrier of the TMA loads of sG (GPRE)
+  unsigned gphase = 0;
 
   // ---- work unit ----
   const int t2 = blockIdx.x % prm.tiles2, t1 = (blockIdx.x / prm.tiles2) % prm.tiles1, seg = blockIdx.x / (prm.tiles2 * prm.tiles1);
@@ -491,6 +606,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
   }
   for (int t = tid; t <= eend - ebeg; t += NT) sSet0[t] = B.setidx[0][ebeg + t];
   if (tid < 2) sCnt[tid] = NW;
+  if (GPRE && tid == 0) mbar_init(gbar, 1);
   // do all elements of the halo carry the dominant coefficient set?  (then S1/S2 take their 1-D factors from the constant bank)
   bool mine = true;
   if (tid < H1) { const int e = e1base + tid; if (e >= 0 && e < n1 && B.setidx[1][e] != prm.cset[1]) mine = false; }
@@ -545,8 +661,10 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
     if (tid < C::SZ_TB0) sTb0B[(e & 1) * C::SZ_TB0 + tid] = pf_tb0;
     if (tid < 4 * NB) sRowB[(e & 1) * 4 * NB + tid] = pf_row;
   };
-  fetch_nodes(ebeg);
-  park_nodes(ebeg);
+  if (!GPRE) {
+    fetch_nodes(ebeg);
+    park_nodes(ebeg);
+  }
 
   // ---- S3 items owned by this thread: dof pairs (i1, j1) x (i2, j2) ----
   // packed per item: wid1*wid2 | position of (j1, j2) in that box << 8 | tile-local (i1, i2) << 16 | valid << 24 | diagonal << 25;
@@ -593,7 +711,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
     if (s >= 0) {
     const int l = ebeg + s / NSUB, ch = s % NSUB;
     // ======================= phase X: S3(s-1) [+ store of its layer]  ||  S1(s) =======================
-    if (ch == NSUB - 1) fetch_nodes(l + 1);
+    if (!GPRE && ch == NSUB - 1) fetch_nodes(l + 1);
     if (ch == 0) fetch_row(l);
     if (tid == 0) sCnt[1] = NW;
     if (s > 0) {
@@ -715,6 +833,10 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
       }
     }
     if (s < nstep) {
+      if (GPRE) {  // the box of this step has landed in sG
+        mbar_wait(gbar, gphase);
+        gphase ^= 1;
+      }
       // work queue: the first item of a warp is static, the rest is handed out by a shared counter (starts at NW)
       for (int wi = warp; wi < NS1;) {
         const int part = wi % NPARTS1, wj = wi / NPARTS1;
@@ -738,7 +860,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
         wi = __shfl_sync(0xffffffffu, wi, 0);
       }
     }
-    if (ch == NSUB - 1) park_nodes(l + 1);
+    if (!GPRE && ch == NSUB - 1) park_nodes(l + 1);
     if (ch == 0) park_row(l);
     __syncthreads();
     if (s >= nstep) break;
@@ -746,8 +868,14 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
 
     // ======================= phase Y: S2(s)  ||  G(s+1) =======================
     if (tid == 0) sCnt[0] = NW;
-    const int ngc = s + 1 < nstep ? NGC : 0;
+    const int ngc = (!GPRE && s + 1 < nstep) ? NGC : 0;
     const int ln = ebeg + (s + 1) / NSUB, qcn = ((s + 1) % NCH) * QC, formn = ((s + 1) % NSUB) / NCH;
+    if (GPRE && s + 1 < nstep && tid == 0) {
+      // sG was last read by S1 of step s (phase X, generic proxy): order those reads before the async-proxy writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(gbar, (unsigned)(sizeof(double) * C::SZ_G));
+      tma_load_4d(smem_addr(sG), &gmap, NQ * e1base, (ln - prm.g_ebeg) * NQ + qcn, NQ * e2base, 0, gbar);
+    }
     const int ns2 = s >= 0 ? NS2 : 0;
     for (int wi = warp; wi < ns2 + ngc;) {
       if (wi >= ns2) {
@@ -776,17 +904,113 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm) {
   }
 }
 
-template <class C, bool FK, bool FM, int NFORM = 1, bool VEC = false>
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// driver entry point without linking libcuda (the library links the static runtime only)
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// the geometry array of one assembly call and its TMA descriptor (the K and M launches of degrees 3 and 4 share it)
+struct GeomCache {
+  bool valid = false;
+  int box[4] = {0, 0, 0, 0};
+  int g_ebeg = 0;
+  CUtensorMap map;
+};
+
+// GPRE launches: run k_geom3d over the element layers the launch touches and describe the result to the TMA unit
+template <class C>
+int prepare_geometry(b2_ctx* ctx, RowParams& prm, CUtensorMap* map) {
+  constexpr int P = C::P, NQ = C::NQ;
+  GeomCache* gc = (GeomCache*)prm.host_gcache;
+  if (gc && gc->valid && gc->box[0] == C::NQ1 && gc->box[1] == C::QC && gc->box[2] == C::NQ2 && gc->box[3] == C::NG) {
+    *map = gc->map;
+    prm.g_ebeg = gc->g_ebeg;
+    return B2_OK;
+  }
+  const int n0 = prm.B.nel[0], n1 = prm.B.nel[1], n2 = prm.B.nel[2];
+  const int ebeg = std::max(0, prm.plane_begin - P), eend = std::min(n0 - 1, prm.plane_end - 1);
+  const long long nlay = eend - ebeg + 1;
+  if (nlay <= 0) return B2_OK;
+  EncodeTiledFn encode = get_encode_tiled();
+  if (!encode) return b2_fail(ctx, B2_ECUDA, "cuTensorMapEncodeTiled is not available");
+  const long long pitch1 = ((long long)NQ * n1 + 1) & ~1LL;  // rows of Q1 start on 16-byte boundaries
+  const long long sQ2 = nlay * NQ * pitch1, scomp = (long long)NQ * n2 * sQ2;
+  const size_t need = sizeof(double) * (size_t)(C::NG * scomp);
+  if (ctx->gbuf_bytes < need) {
+    if (ctx->gbuf) cudaFree(ctx->gbuf);
+    ctx->gbuf = nullptr;
+    ctx->gbuf_bytes = 0;
+    if (cudaMalloc(&ctx->gbuf, need) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->gbuf = nullptr;
+      return B2_ENOMEM;
+    }
+    ctx->gbuf_bytes = need;
+  }
+  GeomParams gp;
+  gp.G = prm.G;
+  gp.Q = prm.Q;
+  gp.n0 = n0; gp.n1 = n1; gp.n2 = n2;
+  gp.ebeg = ebeg;
+  gp.iso = prm.iso;
+  for (int t = 0; t < 6; t++) gp.kc[t] = prm.kc[t];
+  gp.out = (double*)ctx->gbuf;
+  gp.pitch1 = pitch1; gp.sQ2 = sQ2; gp.scomp = scomp;
+  if ((long long)NQ * n2 > 65535 || nlay > 65535) return B2_EUNSUPPORTED;
+  {
+    KernelTimer timer(ctx);
+    k_geom3d<P><<<dim3((unsigned)((NQ * n1 + 127) / 128), (unsigned)(NQ * n2), (unsigned)nlay), 128, 0, ctx->stream>>>(gp);
+  }
+  ctx->launches++;
+  {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+      return b2_fail(ctx, B2_ECUDA, std::string("k_geom3d launch failed: ") + cudaGetErrorString(e) + " grid " + std::to_string((NQ * n1 + 127) / 128) + "x" + std::to_string(NQ * n2) + "x" +
+                                        std::to_string(nlay) + " ebeg " + std::to_string(ebeg) + " planes " + std::to_string(prm.plane_begin) + ":" + std::to_string(prm.plane_end));
+  }
+  prm.g_ebeg = ebeg;
+  const cuuint64_t gdim[4] = {(cuuint64_t)NQ * n1, (cuuint64_t)(nlay * NQ), (cuuint64_t)NQ * n2, (cuuint64_t)C::NG};
+  const cuuint64_t gstr[3] = {(cuuint64_t)pitch1 * 8, (cuuint64_t)sQ2 * 8, (cuuint64_t)scomp * 8};
+  const cuuint32_t box[4] = {(cuuint32_t)C::NQ1, (cuuint32_t)C::QC, (cuuint32_t)C::NQ2, (cuuint32_t)C::NG};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, ctx->gbuf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return b2_fail(ctx, B2_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  if (gc) {
+    gc->valid = true;
+    gc->box[0] = C::NQ1; gc->box[1] = C::QC; gc->box[2] = C::NQ2; gc->box[3] = C::NG;
+    gc->g_ebeg = ebeg;
+    gc->map = *map;
+  }
+  return B2_OK;
+}
+
+template <class C, bool FK, bool FM, int NFORM = 1, bool VEC = false, bool GPRE = false>
 int launch_rows_cfg(b2_ctx* ctx, RowParams& prm) {
-  auto kern = k_rows3d<C, FK, FM, NFORM, VEC>;
+  auto kern = k_rows3d<C, FK, FM, NFORM, VEC, GPRE>;
   const size_t smem = sizeof(double) * C::TOTAL;
   static_assert(sizeof(double) * C::TOTAL <= 227 * 1024, "tile does not fit in shared memory");
   B2_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUtensorMap gmap;
+  memset(&gmap, 0, sizeof(gmap));
+  if (GPRE) {
+    const int rc = prepare_geometry<C>(ctx, prm, &gmap);
+    if (rc != B2_OK) return rc;
+  }
   prm.tiles1 = (prm.B.ndofs[1] + C::T1 - 1) / C::T1;
   prm.tiles2 = (prm.B.ndofs[2] + C::T2 - 1) / C::T2;
   // segments along the marching direction: trade redundant layers (P per segment) against wave quantisation
   const long long tiles = (long long)prm.tiles1 * prm.tiles2, npl = prm.plane_end - prm.plane_begin;
-  const int slots = ctx->sm_count;  // one CTA per SM
+  const int slots = ctx->sm_count * C::OCC;  // CTAs resident at a time
   int best = 1;
   double bestcost = 1e300;
   const int64_t forced = ctx->opts.count("rows_nseg") ? ctx->opts["rows_nseg"] : 0;
@@ -802,18 +1026,35 @@ int launch_rows_cfg(b2_ctx* ctx, RowParams& prm) {
   if (blocks > 0x7fffffffLL) return B2_EUNSUPPORTED;
   {
     KernelTimer timer(ctx);
-    kern<<<(unsigned)blocks, C::NT, smem, ctx->stream>>>(prm);
+    kern<<<(unsigned)blocks, C::NT, smem, ctx->stream>>>(prm, gmap);
   }
   ctx->launches++;
-  B2_CUDA(ctx, cudaGetLastError());
+  {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+      return b2_fail(ctx, B2_ECUDA, std::string("k_rows3d launch failed: ") + cudaGetErrorString(e) + " blocks " + std::to_string(blocks) + " threads " + std::to_string(C::NT) + " smem " +
+                                        std::to_string(smem) + " gpre " + std::to_string((int)GPRE) + " planes " + std::to_string(prm.plane_begin) + ":" + std::to_string(prm.plane_end));
+  }
   return B2_OK;
+}
+
+// scalar forms: with the geometry precomputed (default; option "rows_gpre" = 0 disables it, as does a failed allocation of
+// the geometry array) or evaluated inside the tile kernel
+template <class C, bool FK, bool FM>
+int launch_rows_scalar(b2_ctx* ctx, RowParams& prm) {
+  const bool gpre = !(ctx->opts.count("rows_gpre") && ctx->opts["rows_gpre"] == 0);
+  if (gpre) {
+    const int rc = launch_rows_cfg<C, FK, FM, 1, false, true>(ctx, prm);
+    if (rc != B2_ENOMEM) return rc;
+  }
+  return launch_rows_cfg<C, FK, FM, 1, false, false>(ctx, prm);
 }
 
 template <class C>
 int launch_rows_forms(b2_ctx* ctx, RowParams& prm, bool fk, bool fm) {
-  if (fk && fm) return launch_rows_cfg<C, true, true>(ctx, prm);
-  if (fk) return launch_rows_cfg<C, true, false>(ctx, prm);
-  return launch_rows_cfg<C, false, true>(ctx, prm);
+  if (fk && fm) return launch_rows_scalar<C, true, true>(ctx, prm);
+  if (fk) return launch_rows_scalar<C, true, false>(ctx, prm);
+  return launch_rows_scalar<C, false, true>(ctx, prm);
 }
 
 // Vector-valued space (3 components): one launch per (matrix form, row component).  Stiffness-like forms (any 3x3 block
@@ -921,6 +1162,8 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
   prm.rho = 1.;
   prm.kc[0] = prm.kc[3] = prm.kc[5] = 1.;
   prm.ncomp = B.ncomp;
+  GeomCache gcache;
+  prm.host_gcache = &gcache;
   // dominant coefficient set per dimension and its table at the 1-D points (host copy of what get_tabs uploaded)
   for (int d = 0; d < 3; d++) {
     std::vector<int> count(basis->nsets[d], 0);
@@ -995,29 +1238,29 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
     if (!(fk && fm)) return launch_rows_forms<C4>(ctx, prm, fk, fm);
     RowParams pk = prm;
     pk.valM = nullptr;
-    int rc = launch_rows_cfg<C4, true, false>(ctx, pk);
+    int rc = launch_rows_scalar<C4, true, false>(ctx, pk);
     if (rc != B2_OK) return rc;
     RowParams pm = prm;
     pm.valK = nullptr;
     pm.has_f = 0;
-    return launch_rows_cfg<C4, false, true>(ctx, pm);
+    return launch_rows_scalar<C4, false, true>(ctx, pm);
   }
   if (P == 3) {
     // two chunks of two point-planes per layer
     using C3 = RCfg<3, 3, 3, 2, 256, 3>;
     // K and M together: 512 threads (one dof pair per thread: 2 x 16 accumulators, 128 registers) -- 96^3: 14.5 ms
-    if (fk && fm && !(ctx->opts.count("rows_split_forms") && ctx->opts["rows_split_forms"])) return launch_rows_cfg<RCfg<3, 3, 3, 2, 512, 3>, true, true>(ctx, prm);
+    if (fk && fm && !(ctx->opts.count("rows_split_forms") && ctx->opts["rows_split_forms"])) return launch_rows_scalar<RCfg<3, 3, 3, 2, 512, 3>, true, true>(ctx, prm);
     // K and M in one launch (the geometry stage runs once; 2 x 2 x 16 accumulators per thread spill ~0.7 KB to L1, still
     // 10 % faster than two launches: 96^3 17.7 -> 15.9 ms); option "rows_split_forms" = 1 selects the two launches
     if (!(fk && fm) || !(ctx->opts.count("rows_split_forms") && ctx->opts["rows_split_forms"])) return launch_rows_forms<C3>(ctx, prm, fk, fm);
     RowParams pk = prm;
     pk.valM = nullptr;
-    int rc = launch_rows_cfg<C3, true, false>(ctx, pk);
+    int rc = launch_rows_scalar<C3, true, false>(ctx, pk);
     if (rc != B2_OK) return rc;
     RowParams pm = prm;
     pm.valK = nullptr;
     pm.has_f = 0;
-    return launch_rows_cfg<C3, false, true>(ctx, pm);
+    return launch_rows_scalar<C3, false, true>(ctx, pm);
   }
 #ifdef B2_EXPERIMENT
   if (fk && fm) {
@@ -1034,6 +1277,14 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
     if (variant == 11) return launch_rows_cfg<RCfg<2, 4, 4, 3, 512, 1>, true, true>(ctx, prm);
     if (variant == 12) return launch_rows_cfg<RCfg<2, 4, 4, 3, 512, 0>, true, true>(ctx, prm);
     if (variant == 13) return launch_rows_cfg<RCfg<2, 4, 4, 3, 384, 1>, true, true>(ctx, prm);
+    if (variant == 30) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 0>, true, true, 1, false, true>(ctx, prm);
+    if (variant == 31) return launch_rows_cfg<RCfg<2, 4, 4, 3, 512, 1>, true, true, 1, false, true>(ctx, prm);
+    if (variant == 20) return launch_rows_cfg<RCfg<2, 4, 4, 1, 256, 1, 7, 2>, true, true>(ctx, prm);
+    if (variant == 21) return launch_rows_cfg<RCfg<2, 4, 4, 1, 256, 3, 7, 2>, true, true>(ctx, prm);
+    if (variant == 22) return launch_rows_cfg<RCfg<2, 4, 4, 1, 256, 0, 7, 2>, true, true>(ctx, prm);
+    if (variant == 24) return launch_rows_cfg<RCfg<2, 4, 4, 1, 256, 0, 7, 1>, true, true>(ctx, prm);
+    if (variant == 25) return launch_rows_cfg<RCfg<2, 4, 4, 1, 256, 1, 7, 1>, true, true>(ctx, prm);
+    if (variant == 26) return launch_rows_cfg<RCfg<2, 4, 4, 1, 128, 1, 7, 3>, true, true>(ctx, prm);
   }
 #endif
   return launch_rows_forms<RCfg<2, 4, 4, 3, 256, 0>>(ctx, prm, fk, fm);

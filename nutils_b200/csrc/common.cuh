@@ -115,6 +115,9 @@ struct b2_ctx {
   // scratch for b2_assemble_host
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  // per-point geometry coefficients of the owner-computes path (k_geom3d -> TMA loads of k_rows3d)
+  void* gbuf = nullptr;
+  size_t gbuf_bytes = 0;
   // small upload buffer for form descriptions
   void* formbuf = nullptr;
   size_t formbuf_bytes = 0;

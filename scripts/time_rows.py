@@ -20,6 +20,7 @@ vecs = [torch.empty(plan.ndofs, dtype=torch.float64, device=dev) for _ in Cs]
 variant = int(os.environ.get('ROWS_VARIANT', 0))
 ctx.set_option('rows_variant', variant)
 ctx.set_option('rows_split_forms', int(os.environ.get('ROWS_SPLIT_FORMS', 0)))
+ctx.set_option('rows_gpre', int(os.environ.get('ROWS_GPRE', 1)))
 for nseg in [int(a) for a in sys.argv[3:]] or [0]:
     ctx.set_option('rows_nseg', nseg)
     for _ in range(2):
