@@ -29,7 +29,10 @@ class Geometry:
 
     def __init__(self, topo, nodes):
         self.topo = topo
-        self.nodes = numpy.ascontiguousarray(nodes, dtype=float)
+        # own, READ-ONLY copy: device-resident plans are cached per geometry object, so the coordinates must not change
+        # behind their back -- a deformed mesh is a new geometry (topo.nodal_geometry(new_nodes))
+        self.nodes = numpy.array(nodes, dtype=float, order='C')
+        self.nodes.setflags(write=False)
         self.ndims = self.nodes.shape[0]
         self.shape = (self.ndims,)
 

@@ -11,8 +11,8 @@ def rectilinear(richshape, periodic=(), space='X'):
     array.  The geometry is the multilinear interpolation of the vertex grid --
     the reference builds exactly this for non-integer vertices (a degree-1
     spline times nodal coordinates, mesh.py:55-57); integer grids are the same
-    function.  The nodal coordinates may be deformed afterwards through
-    ``geom.nodes`` / ``topology.nodal_geometry``.'''
+    function.  ``geom.nodes`` is read-only; a deformed mesh is a new geometry,
+    ``topo.nodal_geometry(geom.nodes + displacement)``.'''
     if periodic:
         raise NotImplementedError('periodic meshes are outside the accelerated path')
     verts = [numpy.arange(v + 1, dtype=float) if numpy.ndim(v) == 0 else numpy.asarray(v, dtype=float) for v in richshape]

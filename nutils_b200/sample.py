@@ -42,14 +42,25 @@ class Sample:
         res = tuple(matrix.assemble_csr(*o, ncols=len(o[1]) - 1) if i.kind == 'matrix' else o for i, o in zip(integrals, outs))
         return res[0] if single else res
 
-    def integrate_device(self, funcs, arguments=None):
+    def integrate_device(self, funcs, arguments=None, out=None):
         '''like integrate_sparse, but the values of 2-D integrands STAY in HBM: matrices come back as matrix.DeviceMatrix
-        (products and constrained CG solves on the device), vectors as numpy arrays.'''
+        (products and constrained CG solves on the device), vectors as numpy arrays.
+
+        out : the result of a previous call with the same integrands; its device buffers are written again instead of
+              allocating new ones (a re-assembly inside a time or Newton loop), vectors then stay on the device as
+              engine.DeviceBuffer objects (``.to_host()`` copies them).'''
         from . import matrix
         if arguments:
             raise NotImplementedError('integrands with arguments are outside the accelerated path')
         single = not isinstance(funcs, (tuple, list))
         integrals = [self.integral(f) for f in ((funcs,) if single else funcs)]
+        if self.faces is not None or any(i.func.coef is not None for i in integrals):
+            # boundary samples and pointwise coefficients run on the element-set route, which assembles through host buffers
+            raise NotImplementedError('integrate_device covers volume integrals with constant coefficients; use integrate_sparse for boundary '
+                                      'samples and integrands with coefficient functions')
+        prev = None if out is None else ([out] if single else list(out))
+        if prev is not None and len(prev) != len(integrals):
+            raise ValueError('out does not match the integrands')
         res = [None] * len(integrals)
         groups = {}
         for k, integral in enumerate(integrals):
@@ -58,13 +69,33 @@ class Sample:
             plan = self.plan(integrals[ks[0]].func.space, integrals[ks[0]].func.jac)
             mats = [k for k in ks if integrals[k].kind == 'matrix']
             vecs = [k for k in ks if integrals[k].kind == 'vector']
-            vbufs = [plan.ctx.device_alloc(8 * plan.nnz) for _ in mats]
-            rbufs = [plan.ctx.device_alloc(8 * plan.ndofs) for _ in vecs]
+            if prev is None:
+                vbufs = [plan.ctx.device_alloc(8 * plan.nnz) for _ in mats]
+                rbufs = [plan.ctx.device_alloc(8 * plan.ndofs) for _ in vecs]
+            else:
+                vbufs = [prev[k].values for k in mats]
+                rbufs = [prev[k] for k in vecs]
+                if any(getattr(prev[k], 'plan', None) is not plan for k in mats) or any(not isinstance(b, engine.DeviceBuffer) or b.nbytes != 8 * plan.ndofs for b in rbufs):
+                    raise ValueError('out does not match the integrands')
             plan.assemble_rows_device([integrals[k].tensor for k in mats], [integrals[k].tensor for k in vecs], vbufs, rbufs)
             for k, buf in zip(mats, vbufs):
-                res[k] = matrix.DeviceMatrix(plan, buf)
+                res[k] = prev[k] if prev is not None else matrix.DeviceMatrix(plan, buf)
             for k, buf in zip(vecs, rbufs):
-                res[k] = buf.to_host()
+                res[k] = buf if prev is not None else buf.to_host()
+        return res[0] if single else tuple(res)
+
+    def integrate_device_buffers(self, funcs):
+        'first call of a re-assembly loop: like integrate_device, but vectors stay on the device too (engine.DeviceBuffer); pass the result as ``out=``'
+        single = not isinstance(funcs, (tuple, list))
+        integrals = [self.integral(f) for f in ((funcs,) if single else funcs)]
+        res = self.integrate_device(funcs)
+        res = [res] if single else list(res)
+        for k, integral in enumerate(integrals):
+            if integral.kind == 'vector':
+                plan = self.plan(integral.func.space, integral.func.jac)
+                buf = plan.ctx.device_alloc(8 * plan.ndofs)
+                buf.from_host(res[k])
+                res[k] = buf
         return res[0] if single else tuple(res)
 
     # -- engine --------------------------------------------------------------------------------------
@@ -79,7 +110,7 @@ class Sample:
                 plan = entry[0]
             else:
                 plan = engine.Plan(ctx, space.bases1d, self.rules, geom.nodes, ncomp=space.ncomp)
-            entry = self._plans[key] = plan, geom.nodes
+            entry = self._plans[key] = plan, geom.nodes, space, geom   # space and geom are held so that their ids cannot be reused
         return entry[0]
 
     # -- element-set route: boundary samples and integrands with coefficient functions ---------------
@@ -134,7 +165,7 @@ class Sample:
                 plan = engine.ElemSetPlan(ctx, space.bases1d, nodes=geom.nodes, ncomp=space.ncomp, elem_ids=elem_ids, qoff=qoff,
                                           qcoords=numpy.tile(xi, (len(elem_ids), 1)), qweights=numpy.tile(w, len(elem_ids)))
                 plan.set_faces(numpy.full(len(elem_ids), face[0], dtype=numpy.int8))
-            entry = self._esplans[key] = plan, geom.nodes, elem_ids, xi
+            entry = self._esplans[key] = plan, geom.nodes, elem_ids, xi, space, geom
         return entry[0], entry[2], entry[3]
 
     def eval_fields(self, space, geom, fields=(), grads=False):
