@@ -267,10 +267,41 @@ int b2_diagonal_device(b2_ctx* ctx, const b2_pattern* pattern, const double* val
 int b2_cg_device(b2_ctx* ctx, const b2_pattern* pattern, const double* values_dev, const double* rhs_dev, double* x_dev,
                  const unsigned char* constrained_dev, double atol, double rtol, int maxiter, int* iterations, double* resnorm);
 
+/* ---- general dof maps ---------------------------------------------------------------
+ * b2_pattern_create_csr: a pattern from explicit CSR index arrays (int64, rowptr[0] = 0, columns strictly increasing per
+ * row and < ncols): what nutils.matrix.assemble_csr(values, rowptr, colidx, ncols) validates and hands to a backend
+ * (src/nutils/matrix/__init__.py:30-70).  b2_spmv_device / b2_diagonal_device / b2_cg_device / b2_pattern_export_* accept it.
+ *
+ * b2_pattern_general: the pattern of  sum_e rowdofs(e) x coldofs(e)  for explicit element dof lists (CSR-of-lists:
+ * rowdofs[rowoff[e] .. rowoff[e+1])), any basis -- simplex meshes (topology.py:2493 SimplexTopology.basis_std), mixed
+ * meshes (mesh.py:737-753), hierarchical bases.  Replaces the reference's post-loop flatten / stable argsort / unique /
+ * compress_indices (evaluable.py:588-616, 5646-5682; numeric.py:687-711): keys row << 32 | col are generated, radix-sorted
+ * and made unique on the device.  dof lists hold BASIS indices; with ncomp > 1 the pattern is expanded with the field
+ * numbering dof = basis * ncomp + component (function.py:2623-2626).  rowptr/colidx (b2_pattern_export_*) are bit-equal to
+ * evaluable.as_csr. */
+int b2_pattern_create_csr(b2_ctx* ctx, int64_t nrows, int64_t ncols, const int64_t* rowptr, const int64_t* colidx, b2_pattern** out);
+int b2_pattern_general(b2_ctx* ctx, int64_t nelems, const int64_t* rowoff, const int64_t* rowdofs, const int64_t* coloff, const int64_t* coldofs,
+                       int64_t nrows, int64_t ncols, int ncomp, b2_pattern** out);
+
+/* Element loop on a general pattern for element types described by TABULATED reference data -- the generated loop of the
+ * reference (evaluable.py:6773-6787) for bases given as per-element coefficient arrays (function.PlainBasis,
+ * function.py:2881-2913).  Per element type t (etype[e] selects it): nq[t] points with weights[t][q]; the nfun[t] local
+ * functions and their reference gradients phi[t][q][a], dphi[t][q][a][k]; the nvert[t] geometry shape functions'
+ * reference gradients gdphi[t][q][v][k] (linear on simplices, multilinear on tensor cells; gphi is accepted for symmetry
+ * and not needed).  Per element: its dofs (basis indices, CSR-of-lists dofoff/dofs, the lists given to
+ * b2_pattern_general) and its vertex coordinates vertcoords[vertoff[e] + v][ndims].  Forms D, C as in b2_assemble_device.
+ * Zero-fills, integrates every element (J, J^-1, |det J| per point), scatters with fp64 atomics and copies to the host. */
+int b2_assemble_general_host(b2_ctx* ctx, const b2_pattern* pattern, int ndims, int ncomp, int64_t nelems, int ntypes, const int32_t* etype,
+                             const int32_t* nq, const int32_t* nfun, const int32_t* nvert, const double* const* weights, const double* const* phi,
+                             const double* const* dphi, const double* const* gphi, const double* const* gdphi, const int64_t* dofoff, const int64_t* dofs,
+                             const int64_t* vertoff, const double* vertcoords, int nmat, const double* const* D_host, double* const* values_host, int nvec,
+                             const double* const* C_host, double* const* rhs_host);
+
 /* Experiments and profiling.  "kernel": 0 = automatic, 1 = generic (coverage) kernel only, 2 = specialised kernel or
  * B2_EUNSUPPORTED.  "path": 0 = b2_assemble_host uses the owner-computes rows path for the whole topology, 1 = always
  * the element-scatter path.  "rows_nseg": force the number of marching segments of the rows kernel (0 = automatic).
- * "time_kernels": see b2_ctx_kernel_time. */
+ * "time_kernels": see b2_ctx_kernel_time (2: report the longest launch instead of the sum).  "rows_gpre": 0 = the rows
+ * kernel evaluates the geometry itself instead of fetching the precomputed array by TMA. */
 int b2_ctx_set_option(b2_ctx* ctx, const char* name, int64_t value);
 
 #if defined(__GNUC__)

@@ -97,6 +97,10 @@ SIGNATURES = {
     'b2_spmv_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b2_diagonal_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     'b2_cg_device': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)]),
+    'b2_pattern_create_csr': (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, p_vp]),
+    'b2_pattern_general': (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, p_vp]),
+    'b2_assemble_general_host': (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, pp_f64, pp_f64, pp_f64, pp_f64, pp_f64,
+                                                c_vp, c_vp, c_vp, c_vp, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
     'b2_assemble_host': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, pp_f64, p_vp, ctypes.c_int, pp_f64, p_vp]),
 }
 

@@ -160,3 +160,100 @@ def plan_from_reference(ctx, topo, basis, degree, vertices=None, nodes=None, nco
         return engine.ElemSetPlan(ctx, t['bases'], nodes=t['nodes'], ncomp=ncomp, elem_ids=t['elem_ids'], qoff=t['qoff'], qcoords=t['qcoords'],
                                   qweights=t['qweights'], renumber=t['renumber'], nbasis_new=t['nbasis_new'])
     return engine.Plan(ctx, t['bases'], points.tensor_gauss(len(t['bases']), degree), t['nodes'], ncomp=ncomp)
+
+
+# ---- general dof maps: simplex and mixed meshes, bases given per element ---------------------------------------
+
+def _poly_powers(nvars, degree):
+    '''exponents of the coefficients of a polynomial in `nvars` variables of total degree `degree` in the reference's order:
+    descending in (k_{n-1}, ..., k_0) -- last variable most significant, highest power first (evaluable.py:4328-4350)'''
+    import itertools
+    pw = [k for k in itertools.product(range(degree + 1), repeat=nvars) if sum(k) <= degree]
+    pw.sort(key=lambda k: k[::-1], reverse=True)
+    return numpy.array(pw, dtype=int).reshape(len(pw), nvars)
+
+
+def poly_tabulate(coeffs, points):
+    '(values[nq, nfun], gradients[nq, nfun, nvars]) of polynomials given as coefficient rows coeffs[nfun, ncoeffs] (reference order)'
+    import math
+    coeffs = numpy.asarray(coeffs, dtype=float)
+    points = numpy.asarray(points, dtype=float)
+    nvars = points.shape[1]
+    degree = 0
+    while math.comb(nvars + degree, nvars) < coeffs.shape[1]:
+        degree += 1
+    if math.comb(nvars + degree, nvars) != coeffs.shape[1]:
+        raise ValueError('invalid number of polynomial coefficients')
+    pw = _poly_powers(nvars, degree)
+    mono = numpy.prod(points[:, None, :] ** pw[None], axis=2)                      # [nq, ncoeffs]
+    vals = mono @ coeffs.T
+    grads = numpy.empty((len(points), len(coeffs), nvars))
+    for k in range(nvars):
+        dpw = pw.copy()
+        dpw[:, k] = numpy.maximum(dpw[:, k] - 1, 0)
+        dmono = pw[:, k][None] * numpy.prod(points[:, None, :] ** dpw[None], axis=2)
+        grads[:, :, k] = dmono @ coeffs.T
+    return vals, grads
+
+
+def _vertex_shape_gradients(vertices, points):
+    'reference gradients [nq, nvert, nd] of the (multi)linear nodal shape functions of a reference element with the given vertices'
+    import itertools
+    vertices = numpy.asarray(vertices, dtype=float)
+    nv, nd = vertices.shape
+    if nv == nd + 1:
+        pw = numpy.concatenate([numpy.zeros((1, nd), dtype=int), numpy.eye(nd, dtype=int)])
+    elif nv == 2 ** nd:
+        pw = numpy.array(list(itertools.product((0, 1), repeat=nd)), dtype=int)
+    else:
+        raise NotImplementedError('reference element with {} vertices in {} dimensions'.format(nv, nd))
+    V = numpy.prod(vertices[:, None, :] ** pw[None], axis=2)   # V[v, m] = monomial m at vertex v; shape function v = sum_m inv(V)[m, v] monomial m
+    coef = numpy.linalg.inv(V)
+    out = numpy.empty((len(points), nv, nd))
+    for k in range(nd):
+        dpw = pw.copy()
+        dpw[:, k] = numpy.maximum(dpw[:, k] - 1, 0)
+        dmono = pw[:, k][None] * numpy.prod(numpy.asarray(points)[:, None, :] ** dpw[None], axis=2)
+        out[:, :, k] = dmono @ coef
+    return out
+
+
+def general_tables_from_reference(topo, basis, geom, degree, ischeme='gauss'):
+    '''Tables of ``topo.integral(<form in basis> * J(geom), degree=degree)`` for ANY topology and basis of the reference -- simplex
+    (topology.py:2493), mixed (mesh.py:737-753) -- with a piecewise (multi)linear geometry: the arguments of
+    :class:`engine.GeneralPlan`.  Per element the reference's own objects are read out: ``basis.get_dofs`` /
+    ``get_coefficients`` (function.py:2795-2830), ``sample.points.get(i)`` (pointsseq.py:324-332), ``topo.references[i].vertices``;
+    elements with identical reference data share one type table.'''
+    import importlib
+    pkg = type(topo).__module__.partition('.')[0]
+    smp = importlib.import_module(pkg + '.sample')
+    pseq = importlib.import_module(pkg + '.pointsseq')
+    pts = importlib.import_module(pkg + '.points')
+    types_mod = importlib.import_module(pkg + '.types')
+    sample = topo.sample(ischeme, degree)
+    nd = topo.ndims
+    types, index, etype, dofs = [], {}, [], []
+    refverts = []
+    for i in range(len(topo)):
+        p = sample.points.get(i)
+        coords, weights = numpy.asarray(p.coords, dtype=float), numpy.asarray(p.weights, dtype=float)
+        coeffs = numpy.asarray(basis.get_coefficients(i), dtype=float)
+        verts = numpy.asarray(topo.references[i].vertices, dtype=float)
+        key = coords.tobytes(), weights.tobytes(), coeffs.shape, coeffs.tobytes(), verts.tobytes()
+        t = index.get(key)
+        if t is None:
+            phi, dphi = poly_tabulate(coeffs, coords)
+            t = index[key] = len(types)
+            types.append(dict(weights=weights, phi=phi, dphi=dphi, gdphi=_vertex_shape_gradients(verts, coords), vertices=verts))
+        etype.append(t)
+        dofs.append(numpy.asarray(basis.get_dofs(i), dtype=numpy.int64))
+        refverts.append(pts.CoordsPoints(types_mod.arraydata(verts)))
+    # physical vertex coordinates: the geometry evaluated by the reference at the reference vertices of every element
+    vsample = smp.Sample.new(sample.spaces[0], sample.transforms, pseq.PointsSequence.from_iter(refverts, nd))
+    x = numpy.asarray(vsample.eval(geom))
+    verts, pos = [], 0
+    for i in range(len(topo)):
+        nv = len(types[etype[i]]['vertices'])
+        verts.append(x[pos:pos + nv])
+        pos += nv
+    return dict(ndims=nd, types=types, etype=numpy.array(etype, dtype=numpy.int32), dofs=dofs, verts=verts, nbasis=len(basis))

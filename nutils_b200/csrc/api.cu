@@ -113,12 +113,14 @@ extern "C" int b2_ctx_synchronize(b2_ctx* ctx) {
 
 extern "C" int b2_ctx_timer_start(b2_ctx* ctx) {
   if (!ctx) return B2_EINVAL;
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
   B2_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   return B2_OK;
 }
 
 extern "C" int b2_ctx_timer_stop(b2_ctx* ctx, float* ms) {
   if (!ctx || !ms) return B2_EINVAL;
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
   B2_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   B2_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
   B2_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
@@ -150,6 +152,7 @@ KernelTimer::~KernelTimer() {
 
 extern "C" int b2_ctx_kernel_time(b2_ctx* ctx, double* ms, int64_t* launches) {
   if (!ctx || !ms || !launches) return B2_EINVAL;
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
   B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   // option time_kernels = 2: the longest single launch instead of the sum (the dominant kernel of a multi-kernel step)
   const bool want_max = ctx->opts.count("time_kernels") && ctx->opts["time_kernels"] == 2;
@@ -194,12 +197,14 @@ extern "C" int b2_device_alloc(b2_ctx* ctx, int64_t nbytes, void** out) {
 
 extern "C" int b2_device_free(b2_ctx* ctx, void* p) {
   if (!ctx) return B2_EINVAL;
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
   if (p) B2_CUDA(ctx, cudaFree(p));
   return B2_OK;
 }
 
 extern "C" int b2_memcpy_d2h(b2_ctx* ctx, void* dst, const void* src, int64_t nbytes) {
   if (!ctx || nbytes < 0 || (nbytes && (!dst || !src))) return B2_EINVAL;
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
   B2_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDeviceToHost, ctx->stream));
   B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return B2_OK;
@@ -207,6 +212,7 @@ extern "C" int b2_memcpy_d2h(b2_ctx* ctx, void* dst, const void* src, int64_t nb
 
 extern "C" int b2_memcpy_h2d(b2_ctx* ctx, void* dst, const void* src, int64_t nbytes) {
   if (!ctx || nbytes < 0 || (nbytes && (!dst || !src))) return B2_EINVAL;
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
   B2_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyHostToDevice, ctx->stream));
   B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return B2_OK;
@@ -214,6 +220,7 @@ extern "C" int b2_memcpy_h2d(b2_ctx* ctx, void* dst, const void* src, int64_t nb
 
 extern "C" int b2_memset_zero(b2_ctx* ctx, void* dev, int64_t nbytes) {
   if (!ctx || nbytes < 0 || (nbytes && !dev)) return B2_EINVAL;
+  B2_CUDA(ctx, cudaSetDevice(ctx->device));
   B2_CUDA(ctx, cudaMemsetAsync(dev, 0, (size_t)nbytes, ctx->stream));
   return B2_OK;
 }
@@ -477,8 +484,8 @@ extern "C" int64_t b2_pattern_row_offset(const b2_pattern* p, int64_t row) {
   if (!p || row < 0 || row > p->nrows) return -1;
   if (row == p->nrows) return p->nnz;
   const b2_basis* b = p->basis;
-  const int nc = b->ncomp;
-  if (p->elemset) {
+  const int nc = pattern_ncomp(p);
+  if (pattern_general(p)) {
     const int64_t In = row / nc, c = row % nc;
     const long long r0 = p->rowptr_b[In], len = p->rowptr_b[In + 1] - r0;
     return (r0 * nc + c * len) * nc;
@@ -498,7 +505,7 @@ extern "C" int64_t b2_pattern_row_offset(const b2_pattern* p, int64_t row) {
 extern "C" int b2_pattern_export_device(b2_pattern* p, int64_t* rowptr_dev, int64_t* colidx_dev) {
   if (!p || !rowptr_dev || !colidx_dev) return B2_EINVAL;
   B2_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
-  if (p->elemset) return launch_pattern_export_general(p->ctx, p->d_rowptr_b, p->d_colidx_b, p->nrows / p->basis->ncomp, p->basis->ncomp, (long long*)rowptr_dev, (long long*)colidx_dev);
+  if (pattern_general(p)) return launch_pattern_export_general(p->ctx, p->d_rowptr_b, p->d_colidx_b, p->nrows / pattern_ncomp(p), pattern_ncomp(p), (long long*)rowptr_dev, (long long*)colidx_dev);
   return launch_pattern_export(p->ctx, p->basis->view(), (long long*)rowptr_dev, (long long*)colidx_dev);
 }
 
@@ -510,7 +517,7 @@ extern "C" int b2_pattern_export_host(b2_pattern* p, int64_t* rowptr_host, int64
   B2_CUDA(ctx, cudaMalloc((void**)&d_rp, sizeof(long long) * (p->nrows + 1)));
   cudaError_t e = cudaMalloc((void**)&d_ci, sizeof(long long) * std::max<int64_t>(p->nnz, 1));
   if (e != cudaSuccess) { cudaFree(d_rp); return b2_cuda_fail(ctx, e, "cudaMalloc(colidx)"); }
-  int rc = p->elemset ? launch_pattern_export_general(ctx, p->d_rowptr_b, p->d_colidx_b, p->nrows / p->basis->ncomp, p->basis->ncomp, d_rp, d_ci)
+  int rc = pattern_general(p) ? launch_pattern_export_general(ctx, p->d_rowptr_b, p->d_colidx_b, p->nrows / pattern_ncomp(p), pattern_ncomp(p), d_rp, d_ci)
                       : launch_pattern_export(ctx, p->basis->view(), d_rp, d_ci);
   if (rc == B2_OK) {
     e = cudaMemcpyAsync(rowptr_host, d_rp, sizeof(long long) * (p->nrows + 1), cudaMemcpyDeviceToHost, ctx->stream);

@@ -6,7 +6,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 OUT="$HERE/../libb200fem.so"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -cudart static"
 mkdir -p "$HERE/_obj"
-SRCS="api api_elemset pattern pattern_elemset assemble_generic assemble_elemset assemble_fast assemble_rows spmv"
+SRCS="api api_elemset pattern pattern_elemset pattern_general assemble_generic assemble_elemset assemble_fast assemble_rows spmv"
 OBJS=""
 PIDS=""
 for f in $SRCS; do

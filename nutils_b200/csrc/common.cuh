@@ -213,6 +213,10 @@ struct b2_pattern {
   b2_ctx* ctx;
   const b2_basis* basis;
   int64_t nnz, nrows;
+  // explicit patterns (b2_pattern_create_csr, b2_pattern_general): basis == nullptr, rows at basis level in d_rowptr_b /
+  // d_colidx_b with ncomp_gen components per basis function, ncols columns
+  int64_t ncols = 0;
+  int ncomp_gen = 1;
   // general pattern of an element set (b2_pattern_create_elemset); analytic otherwise
   const b2_elemset* elemset = nullptr;
   long long* d_rowptr_b = nullptr;  // [nbasis_new+1]
@@ -224,6 +228,10 @@ struct b2_pattern {
   b2_pattern* aux_pattern = nullptr;
   bool aux_failed = false;
 };
+
+// components per basis function / is the pattern materialised (element sets, explicit patterns)?
+inline int pattern_ncomp(const b2_pattern* p) { return p->basis ? p->basis->ncomp : p->ncomp_gen; }
+inline bool pattern_general(const b2_pattern* p) { return p->elemset != nullptr || p->basis == nullptr; }
 
 // ---- error helpers -------------------------------------------------------------------------------
 

@@ -583,12 +583,12 @@ int grid_for(b2_ctx* ctx, long long work_items, int per_block) {
 
 int spmv_launch(b2_ctx* ctx, const b2_pattern* p, const double* values, const double* x, double* y, const unsigned char* mask, double* dot) {
   const b2_basis* basis = p->basis;
-  const int nc = basis->ncomp;
+  const int nc = pattern_ncomp(p);
   const long long nbasis = p->nrows / nc;
   const int blocks = grid_for(ctx, nbasis, 8);  // 8 warps per block, one basis row per warp and step
   {
     KernelTimer timer(ctx);
-    if (p->elemset) {
+    if (pattern_general(p)) {
       k_spmv_general<<<blocks, 256, 0, ctx->stream>>>(p->d_rowptr_b, p->d_colidx_b, nbasis, nc, values, x, y, mask, dot);
     } else {
       const BasisView B = basis->view();
@@ -639,10 +639,10 @@ int spmv_launch(b2_ctx* ctx, const b2_pattern* p, const double* values, const do
 
 int diagonal_launch(b2_ctx* ctx, const b2_pattern* p, const double* values, double* diag) {
   const b2_basis* basis = p->basis;
-  const int nc = basis->ncomp;
+  const int nc = pattern_ncomp(p);
   const long long nbasis = p->nrows / nc;
   const int blocks = grid_for(ctx, p->nrows, 256);
-  if (p->elemset) {
+  if (pattern_general(p)) {
     k_diagonal_general<<<blocks, 256, 0, ctx->stream>>>(p->d_rowptr_b, p->d_colidx_b, nbasis, nc, values, diag);
   } else {
     const BasisView B = basis->view();
@@ -737,5 +737,7 @@ extern "C" int b2_cg_device(b2_ctx* ctx, const b2_pattern* pattern, const double
   if (resnorm) *resnorm = std::sqrt(rr);
   if (rc != B2_OK) return rc;
   if (explicit_tol && std::sqrt(rr) > target) return b2_fail(ctx, B2_ENOTCONVERGED, "tolerance not reached");
+  // atol = rtol = 0 asks for machine precision (matrix/_base.py:126-129): running out of iterations far above it is not a solution
+  if (!explicit_tol && it >= maxiter && std::sqrt(rr) > 1e3 * target) return b2_fail(ctx, B2_ENOTCONVERGED, "iteration limit reached before machine precision");
   return B2_OK;
 }

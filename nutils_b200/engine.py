@@ -462,6 +462,106 @@ class ElemSetPlan:
                                                                len(Ds), pD, pv, len(Cs), pC, pr))
 
 
+class CsrPattern:
+    '''An explicit CSR pattern on the device (b2_pattern_create_csr): what ``matrix.assemble_csr(values, rowptr, colidx, ncols)``
+    receives (src/nutils/matrix/__init__.py:30-70).  Carries the device-resident matrix operations of a plan.'''
+
+    def __init__(self, ctx, rowptr, colidx, ncols):
+        self.ctx = ctx
+        rowptr = numpy.ascontiguousarray(rowptr, dtype=numpy.int64)
+        colidx = numpy.ascontiguousarray(colidx, dtype=numpy.int64)
+        h = c_vp()
+        ctx.check(ctx.lib.b2_pattern_create_csr(ctx.handle, len(rowptr) - 1, int(ncols), rowptr.ctypes.data_as(c_vp), colidx.ctypes.data_as(c_vp), ctypes.byref(h)))
+        self.pattern = h
+        self._fin = [weakref.finalize(self, ctx.lib.b2_pattern_destroy, h)]
+        self.nnz = int(ctx.lib.b2_pattern_nnz(h))
+        self.ndofs = int(ctx.lib.b2_pattern_nrows(h))
+        self.ncols = int(ncols)
+        self._csr = rowptr, colidx
+
+    csr_pattern = Plan.csr_pattern
+    csr_pattern_device = Plan.csr_pattern_device
+    spmv_device = Plan.spmv_device
+    diagonal_device = Plan.diagonal_device
+    cg_device = Plan.cg_device
+    row_offset = Plan.row_offset
+
+
+class GeneralPlan:
+    '''Assembly on a GENERAL dof map: simplex and mixed meshes, any basis given per element as tabulated
+    reference data.  The CSR pattern is built on the device from the element dof lists (b2_pattern_general: key generation,
+    radix sort, unique -- the reference's argsort / unique / compress_indices, evaluable.py:5646-5682), the element loop is
+    b2_assemble_general_host.
+
+    ndims, ncomp
+    types   : list of dicts, one per element type: weights[nq], phi[nq, nfun], dphi[nq, nfun, ndims], gdphi[nq, nvert, ndims]
+    etype   : int32[nelems] type of every element
+    dofs    : list of int arrays (basis indices of the local functions of every element)  -- or (dofoff, dofs) arrays
+    verts   : list of float arrays [nvert, ndims] (vertex coordinates of every element)   -- or (vertoff, coords) arrays
+    nbasis  : number of basis functions
+    '''
+
+    def __init__(self, ctx, ndims, types, etype, dofs, verts, nbasis, ncomp=1):
+        self.ctx = ctx
+        self.ndims, self.ncomp = int(ndims), int(ncomp)
+        self.etype = numpy.ascontiguousarray(etype, dtype=numpy.int32)
+        self.nelems = len(self.etype)
+        self.types = [dict(weights=as_f64(t['weights']), phi=as_f64(t['phi']), dphi=as_f64(t['dphi']), gdphi=as_f64(t['gdphi'])) for t in types]
+        for t in self.types:
+            nq, nf = t['phi'].shape
+            if t['weights'].shape != (nq,) or t['dphi'].shape != (nq, nf, self.ndims) or t['gdphi'].ndim != 3 or t['gdphi'].shape[0] != nq or t['gdphi'].shape[2] != self.ndims:
+                raise ValueError('inconsistent element tables')
+        if isinstance(dofs, tuple):
+            self.dofoff, self.dofs = (numpy.ascontiguousarray(a, dtype=numpy.int64) for a in dofs)
+        else:
+            self.dofoff = numpy.concatenate([[0], numpy.cumsum([len(d) for d in dofs])]).astype(numpy.int64)
+            self.dofs = numpy.ascontiguousarray(numpy.concatenate([numpy.asarray(d, dtype=numpy.int64) for d in dofs]) if len(dofs) else numpy.zeros(0, dtype=numpy.int64))
+        if isinstance(verts, tuple):
+            self.vertoff, self.vertcoords = numpy.ascontiguousarray(verts[0], dtype=numpy.int64), as_f64(verts[1])
+        else:
+            self.vertoff = numpy.concatenate([[0], numpy.cumsum([len(v) for v in verts])]).astype(numpy.int64)
+            self.vertcoords = as_f64(numpy.concatenate([numpy.asarray(v, dtype=float).reshape(-1, self.ndims) for v in verts]) if len(verts) else numpy.zeros((0, self.ndims)))
+        for e in range(self.nelems):
+            t = self.types[self.etype[e]]
+            if self.dofoff[e + 1] - self.dofoff[e] != t['phi'].shape[1] or self.vertoff[e + 1] - self.vertoff[e] != t['gdphi'].shape[1]:
+                raise ValueError('element {} does not match its type tables'.format(e))
+        self.nbasis = int(nbasis)
+        h = c_vp()
+        ctx.check(ctx.lib.b2_pattern_general(ctx.handle, self.nelems, self.dofoff.ctypes.data_as(c_vp), self.dofs.ctypes.data_as(c_vp), self.dofoff.ctypes.data_as(c_vp),
+                                             self.dofs.ctypes.data_as(c_vp), self.nbasis, self.nbasis, self.ncomp, ctypes.byref(h)))
+        self.pattern = h
+        self._fin = [weakref.finalize(self, ctx.lib.b2_pattern_destroy, h)]
+        self.nnz = int(ctx.lib.b2_pattern_nnz(h))
+        self.ndofs = int(ctx.lib.b2_pattern_nrows(h))
+        self._csr = None
+
+    csr_pattern = Plan.csr_pattern
+    csr_pattern_device = Plan.csr_pattern_device
+    spmv_device = Plan.spmv_device
+    diagonal_device = Plan.diagonal_device
+    cg_device = Plan.cg_device
+    row_offset = Plan.row_offset
+    _form_args = Plan._form_args
+
+    def assemble_host(self, Ds=(), Cs=()):
+        'zero-fill, integrate every element, copy to host: ([values...], [rhs...]) (b2_assemble_general_host)'
+        Ds, Cs, pD, pC = self._form_args(Ds, Cs)
+        vals = [numpy.empty(self.nnz) for _ in Ds]
+        rhs = [numpy.empty(self.ndofs) for _ in Cs]
+        pv = (c_vp * max(len(vals), 1))(*[v.ctypes.data_as(c_vp) for v in vals])
+        pr = (c_vp * max(len(rhs), 1))(*[r.ctypes.data_as(c_vp) for r in rhs])
+        i32 = lambda a: numpy.ascontiguousarray(a, dtype=numpy.int32)
+        nq = i32([t['phi'].shape[0] for t in self.types])
+        nf = i32([t['phi'].shape[1] for t in self.types])
+        nv = i32([t['gdphi'].shape[1] for t in self.types])
+        tab = lambda key: _lib.ptr_array([t[key] for t in self.types], _lib.p_f64)
+        self.ctx.check(self.ctx.lib.b2_assemble_general_host(
+            self.ctx.handle, self.pattern, self.ndims, self.ncomp, self.nelems, len(self.types), self.etype.ctypes.data_as(c_vp), nq.ctypes.data_as(c_vp),
+            nf.ctypes.data_as(c_vp), nv.ctypes.data_as(c_vp), tab('weights'), tab('phi'), tab('dphi'), tab('gdphi'), tab('gdphi'), self.dofoff.ctypes.data_as(c_vp),
+            self.dofs.ctypes.data_as(c_vp), self.vertoff.ctypes.data_as(c_vp), self.vertcoords.ctypes.data_as(c_vp), len(Ds), pD, pv, len(Cs), pC, pr))
+        return vals, rhs
+
+
 # ---- coefficient tensors of the north-star forms -------------------------------------------------------
 
 def form_mass(ndims, ncomp=1):

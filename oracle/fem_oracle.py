@@ -334,3 +334,37 @@ def assemble(prob, matrix_forms=(), vector_forms=(), matrix_coefs=None, vector_c
             numpy.add.at(rhs[k], vdofs, element_vector(form, N, grad, wdet * c, nc))
     mats = [coo_to_csr(v.ravel(), rows.ravel(), cols.ravel(), prob.ndofs, prob.ndofs) for v in vals]
     return mats, rhs
+
+
+def assemble_general(ndims, types, etype, dofs, verts, nbasis, matrix_forms=(), vector_forms=(), ncomp=1):
+    '''General dof maps (simplex / mixed meshes; TEST INFRASTRUCTURE): the reference's element loop for bases given per element
+    (function.PlainBasis, function.py:2881-2913: Inflate(Polyval(coeffs, points), dofs)), a (multi)linear geometry
+    (x = sum_v X_v phi_v, J = sum_v X_v (x) dphi_v; function.py:1207-1295), einsum + weighted sum (sample.py:951-956), and the
+    sparse post-processing of coo_to_csr (evaluable.py:588-616, 5646-5682).  Forms: ('generic', D[nc, na, nc, na]) /
+    ('generic', C[nc, na]).  Returns ([(values, rowptr, colidx)...], [rhs...]).'''
+    na = ndims + 1
+    rows, cols, vals = [], [], [[] for _ in matrix_forms]
+    rhs = [numpy.zeros(nbasis * ncomp) for _ in vector_forms]
+    for e in range(len(etype)):
+        t = types[etype[e]]
+        X = numpy.asarray(verts[e], dtype=float)                                   # [nvert, nd]
+        J = numpy.einsum('vi,qvk->qik', X, t['gdphi'])                               # dx_i / dxi_k
+        Jinv = numpy.linalg.inv(J)
+        wdet = t['weights'] * abs(numpy.linalg.det(J))
+        g = numpy.concatenate([t['phi'][:, :, None], numpy.einsum('qak,qkj->qaj', t['dphi'], Jinv)], axis=2)   # [nq, nfun, na]
+        d = numpy.asarray(dofs[e], dtype=numpy.int64)
+        full = (d[:, None] * ncomp + numpy.arange(ncomp)[None, :]).ravel()
+        rows.append(numpy.repeat(full, len(full)))
+        cols.append(numpy.tile(full, len(full)))
+        for m, (kind, D) in enumerate(matrix_forms):
+            blk = numpy.einsum('q,qax,cxey,qby->acbe', wdet, g, numpy.asarray(D, dtype=float).reshape(ncomp, na, ncomp, na), g)
+            vals[m].append(blk.reshape(len(full), len(full)).ravel())
+        for v, (kind, C) in enumerate(vector_forms):
+            numpy.add.at(rhs[v], full, numpy.einsum('q,qax,cx->ac', wdet, g, numpy.asarray(C, dtype=float).reshape(ncomp, na)).ravel())
+    rows = numpy.concatenate(rows) if rows else numpy.zeros(0, dtype=numpy.int64)
+    cols = numpy.concatenate(cols) if cols else numpy.zeros(0, dtype=numpy.int64)
+    n = nbasis * ncomp
+    mats = [coo_to_csr(numpy.concatenate(v) if v else numpy.zeros(0), rows, cols, n, n) for v in vals]
+    if not matrix_forms:
+        mats = []
+    return mats, rhs

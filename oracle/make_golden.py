@@ -421,6 +421,41 @@ def known_answer_mass_1d():
                 nodes=X, ndofs=3, K_values=numpy.zeros(0), M_values=v, rowptr=rp, colidx=ci, F=F)
 
 
+
+# ---- general dof maps: simplex and mixed meshes ------------------------------------------------------
+
+def general_case(name, nelems, etype, degree, ncomp=1):
+    '''mesh.unitsquare(nelems, 'triangle' | 'mixed') (mesh.py:686-783) with basis('std') (topology.py:2493): K, M, f through
+    function.eval(as_csr(...)); next to them the element tables read out of the reference's objects by
+    nutils_b200.adapter.general_tables_from_reference -- the inputs of engine.GeneralPlan / fem_oracle.assemble_general'''
+    sys.path.insert(0, os.path.dirname(HERE))
+    from nutils_b200 import adapter
+    topo, geom = mesh.unitsquare(nelems, etype)
+    basis = topo.basis('std', degree=degree)
+    J = function.J(geom)
+    qd = 2 * degree
+    t = adapter.general_tables_from_reference(topo, basis, geom, qd)
+    d = dict(kind='general', name=name, ndims=2, degree=degree, qdegree=qd, ncomp=ncomp, nbasis=len(basis), ndofs=len(basis) * ncomp, ntypes=len(t['types']),
+             etype=t['etype'], dofoff=numpy.concatenate([[0], numpy.cumsum([len(x) for x in t['dofs']])]), dofs=numpy.concatenate(t['dofs']),
+             vertoff=numpy.concatenate([[0], numpy.cumsum([len(x) for x in t['verts']])]), vertcoords=numpy.concatenate(t['verts']))
+    for k, ty in enumerate(t['types']):
+        for key in ('weights', 'phi', 'dphi', 'gdphi'):
+            d['{}_{}'.format(key, k)] = ty[key]
+    if ncomp == 1:
+        g = basis.grad(geom)
+        K = topo.integral((g[:, None, :] * g[None, :, :]).sum(-1) * J, degree=qd)
+        M = topo.integral(basis[:, None] * basis[None, :] * J, degree=qd)
+        F = topo.integral(basis * J, degree=qd)
+        (kv, rp, ci), (mv, mrp, mci), f = function.eval((function.as_csr(K), function.as_csr(M), F))
+        assert numpy.array_equal(rp, mrp) and numpy.array_equal(ci, mci)
+        d.update(K_values=kv, M_values=mv, rowptr=rp, colidx=ci, F=f)
+    else:
+        lmbda, mu = .6, .7
+        kv, rp, ci, r = _elasticity_system(topo, geom, basis, ncomp, lmbda, mu, qd, load=[.3, -1.])
+        d.update(K_values=kv, rowptr=rp, colidx=ci, F=r, lmbda=lmbda, mu=mu, load=numpy.array([.3, -1.]))
+    return d
+
+
 CASES = {
     'mass1d_known': known_answer_mass_1d,
     'line_p2': lambda: scalar_case('line_p2', (7,), 2),
@@ -459,6 +494,10 @@ CASES = {
     'example_elasticity_p2': lambda: example_elasticity_case('example_elasticity_p2', 4, 2),
     'example_elasticity_spline': lambda: example_elasticity_case('example_elasticity_spline', 6, 2, btype='spline', poisson=.3),
     'elast3d_p2_warp': lambda: elasticity_case('elast3d_p2_warp', (3, 3, 2), 2, warp=.3, seed=7),  # config 3 at toy size
+    'general_tri_p1': lambda: general_case('general_tri_p1', 4, 'triangle', 1),     # SimplexTopology.basis_std (topology.py:2493)
+    'general_tri_p2': lambda: general_case('general_tri_p2', 4, 'triangle', 2),
+    'general_mixed_p2': lambda: general_case('general_mixed_p2', 5, 'mixed', 2),   # mesh.py:737-753
+    'general_tri_elast_p2': lambda: general_case('general_tri_elast_p2', 3, 'triangle', 2, ncomp=2),
 }
 
 
