@@ -227,6 +227,13 @@ int b2_geom_create_spline(b2_ctx* ctx, const b2_basis* gbasis, const double* ctr
  * _row_offset work on it like on the analytic pattern. */
 int b2_pattern_create_elemset(b2_ctx* ctx, const b2_elemset* elemset, b2_pattern** out);
 
+/* Solution-dependent coefficients (what System.assemble_jacobian_residual re-evaluates per Newton step,
+ * src/nutils/solver.py:357-425): matrix form `which` (or vector form which - B2_MAX_FORMS) is multiplied at every point by
+ * scale * u_h(x_q)^power, with u_h = sum_i field_dev[i] N_i evaluated INSIDE the assembly kernel from the caller-owned device
+ * vector field_dev (float64[ndofs], read at launch time: update it in place between Newton steps).  Combines with
+ * b2_elemset_set_coefficient (product).  field_dev NULL removes it.  Scalar, non-rational spaces. */
+int b2_elemset_set_coefficient_field(b2_elemset* elemset, int which, const double* field_dev, int power, double scale);
+
 /* Element-scatter assembly of the selected elements [sel_begin, sel_end) (positions in elem_ids; 0, -1 = all):
  * same forms and the same ACCUMULATE semantics as b2_assemble_device.  quad may be NULL when the element set
  * carries its own points.  The slot of (row, col) is found by bisection in the row's sorted column list. */

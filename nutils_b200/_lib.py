@@ -87,6 +87,7 @@ SIGNATURES = {
     'b2_elemset_set_faces': (ctypes.c_int, [c_vp, c_vp]),
     'b2_elemset_set_normals': (ctypes.c_int, [c_vp, c_vp, c_i64]),
     'b2_elemset_set_coefficient': (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_i64]),
+    'b2_elemset_set_coefficient_field': (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_double]),
     'b2_elemset_ndofs': (c_i64, [c_vp]),
     'b2_elemset_npoints': (c_i64, [c_vp]),
     'b2_geom_create_spline': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, p_vp]),

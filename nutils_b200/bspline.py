@@ -117,27 +117,14 @@ def spline_basis_1d(nelems, degree, continuity=-1, knotvalues=None, knotmultipli
             raise ValueError('incorrect knot multiplicities')
     if p == 0:
         return Basis1D(0, n, numpy.ones((1, 1, 1)), numpy.zeros(n, dtype=numpy.int32), numpy.arange(n), n, False)
-    if periodic and not m[0] == m[n] == p + 1:
-        if m[0] != m[n]:
-            raise ValueError('periodic spline multiplicity expected')
-        dk = k[n] - k[0]
-        m = m[:n]
-        k = k[:n]
-        nd = int(m.sum())
-        while m[n:].sum() < p - m[0] + 2:
-            k = numpy.concatenate([k, k + dk])
-            m = numpy.concatenate([m, m])
-            dk *= 2
-        km = numpy.repeat(k, m).astype(float)
-        if p > m[0]:
-            km = numpy.concatenate([km[-p + m[0]:] - dk, km])
-        isperiodic = True
-    else:
-        m = m.copy()
-        m[0] = m[-1] = p
-        nd = int(m[:n].sum()) + 1
-        km = numpy.repeat(k, m).astype(float)
-        isperiodic = False
+    if periodic:
+        raise NotImplementedError('periodic spline spaces are outside the accelerated path')
+    # open knot vector: the end knots are repeated p + 1 times in all, interior knot i mult[i] times
+    mult = m.copy()
+    mult[0] = mult[-1] = p
+    nd = int(mult[:n].sum()) + 1
+    km = numpy.repeat(k, mult).astype(float)
+    m = mult
     offsets = numpy.cumsum(m[:n]) - m[0]
     sets = []
     keys = {}
@@ -149,4 +136,4 @@ def spline_basis_1d(nelems, degree, continuity=-1, knotvalues=None, knotmultipli
             keys[key] = len(sets)
             sets.append(local_polynomials(lk))
         setidx[ielem] = keys[key]
-    return Basis1D(p, n, numpy.array(sets), setidx, offsets, nd, isperiodic)
+    return Basis1D(p, n, numpy.array(sets), setidx, offsets, nd, False)

@@ -145,6 +145,16 @@ extern "C" int b2_elemset_set_coefficient(b2_elemset* es, int which, const doubl
   return upload_n(ctx, coef, (size_t)npoints, &es->d_coef[which]);
 }
 
+extern "C" int b2_elemset_set_coefficient_field(b2_elemset* es, int which, const double* field_dev, int power, double scale) {
+  if (!es || which < 0 || which >= 2 * B2_MAX_FORMS) return B2_EINVAL;
+  if (field_dev && (power < 0 || power > 8)) return b2_fail(es->ctx, B2_EINVAL, "power of the field coefficient must be 0..8");
+  if (field_dev && (es->basis->ncomp != 1 || es->rational)) return b2_fail(es->ctx, B2_EUNSUPPORTED, "field coefficients: scalar, non-rational spaces");
+  es->d_field[which] = field_dev;
+  es->field_power[which] = power;
+  es->field_scale[which] = scale;
+  return B2_OK;
+}
+
 extern "C" int b2_elemset_destroy(b2_elemset* es) {
   if (!es) return B2_OK;
   cudaSetDevice(es->ctx->device);
@@ -286,6 +296,9 @@ static int build_views(b2_ctx* ctx, const b2_pattern* pattern, const b2_elemset*
   E.nq_uniform = Q.nqt;
   for (int k = 0; k < 2 * B2_MAX_FORMS; k++) {
     E.coef[k] = es->d_coef[k];
+    E.field[k] = es->d_field[k];
+    E.field_power[k] = es->field_power[k];
+    E.field_scale[k] = es->field_scale[k];
     if (es->d_coef[k] && !es->d_qoff && es->coef_len[k] != es->nsel * (int64_t)Q.nqt) return b2_fail(ctx, B2_EINVAL, "coefficient array does not match nsel x points of the tensor rule");
   }
   E.nbasis_new = es->nbasis_new;

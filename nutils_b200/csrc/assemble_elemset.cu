@@ -301,6 +301,37 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512, TCMAX == 4 ? 4 : 1) k_
           }
         }
         __syncthreads();
+        // P1b: solution-dependent coefficients: u_h at the points from the element's dofs of the field vector,
+        // folded into the pointwise coefficient of the form -- what the reference evaluates per element as
+        // Polyval(coeffs, points) . take(arg, dofs) inside its loop (function.py:2758-2762, 2598-2626)
+        {
+          bool anyfield = false;
+#pragma unroll
+          for (int k = 0; k < 2 * B2_MAX_FORMS; k++) anyfield |= E.field[k] != nullptr;
+          if (anyfield) {
+            for (int ql = tid; ql < nqc; ql += T) {
+              double uh[2 * B2_MAX_FORMS];
+#pragma unroll
+              for (int k = 0; k < 2 * B2_MAX_FORMS; k++) uh[k] = 0.;
+              for (int a = 0; a < nb; a++) {
+                if (sDof[a] < 0) continue;
+                double N, dxi[DIM];
+                tensor_eval<DIM>(sA + ql * DIM * pm1 * 2, pm1, sMi[a], N, dxi);
+#pragma unroll
+                for (int k = 0; k < 2 * B2_MAX_FORMS; k++)
+                  if (E.field[k]) uh[k] = fma(N, E.field[k][sDof[a]], uh[k]);
+              }
+#pragma unroll
+              for (int k = 0; k < 2 * B2_MAX_FORMS; k++)
+                if (E.field[k]) {
+                  double c = E.field_scale[k];
+                  for (int j = 0; j < E.field_power[k]; j++) c *= uh[k];
+                  sK[ql * 2 * B2_MAX_FORMS + k] *= c;
+                }
+            }
+            __syncthreads();
+          }
+        }
         // P2: geometry at the points of the chunk (and the weight function of rational bases)
         for (int ql = tid; ql < nqc; ql += T) {
           const double* pt = sPt + ql * NA;

@@ -445,11 +445,13 @@ struct GeomParams {
   QuadView Q;
   int n0, n1, n2, ebeg, iso;
   double kc[6];
+  int nform;        // GEN: number of general 3x3 coefficient blocks (column components of a vector-valued launch)
+  double dm[3][9];  // GEN: Ghat^(f)[k][l] = w/|det| sum_xy adj[k][x] dm[f][x][y] adj[l][y]
   double* out;
   long long pitch1, sQ2, scomp;  // strides in doubles: Q0 -> pitch1, Q2 -> sQ2, component -> scomp
 };
 
-template <int P>
+template <int P, bool GEN>
 __global__ void __launch_bounds__(128) k_geom3d(const GeomParams prm) {
   constexpr int NQ = P + 1;
   const int Q1 = blockIdx.x * 128 + threadIdx.x, Q2 = blockIdx.y, e0 = prm.ebeg + blockIdx.z;
@@ -490,6 +492,23 @@ __global__ void __launch_bounds__(128) k_geom3d(const GeomParams prm) {
     const double adet = fabs(det), w = prm.Q.w[0][q0] * w12;
     const double sc = w * rcp_pos(adet);
     double* oq = o + q0 * prm.pitch1;
+    if (GEN) {
+      // per form f: 9 components of the general coefficient + w |det J| (the layout [NG = 10] of the tile kernel's sG)
+      for (int f = 0; f < prm.nform; f++) {
+        const double* M = prm.dm[f];
+        double T[9];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int y = 0; y < 3; y++) T[k * 3 + y] = A[k * 3] * M[y] + A[k * 3 + 1] * M[3 + y] + A[k * 3 + 2] * M[6 + y];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int l = 0; l < 3; l++) oq[(f * 10 + k * 3 + l) * prm.scomp] = sc * (T[k * 3] * A[l * 3] + T[k * 3 + 1] * A[l * 3 + 1] + T[k * 3 + 2] * A[l * 3 + 2]);
+        oq[(f * 10 + 9) * prm.scomp] = w * adet;
+      }
+      continue;
+    }
     if (prm.iso) {
       const double sk = sc * prm.kc[0];
       oq[0 * prm.scomp] = sk * (A[0] * A[0] + A[1] * A[1] + A[2] * A[2]);
@@ -548,7 +567,7 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map
 // NFORM > 1: vector-valued stiffness-like launch, forms = column components, one pipeline step per (layer, form, chunk)
 template <class C, bool FK, bool FM, int NFORM, bool VEC, bool GPRE>
 __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __grid_constant__ CUtensorMap gmap) {
-  static_assert(!GPRE || (C::NG == 7 && NFORM == 1 && !VEC), "precomputed geometry: scalar forms");
+  static_assert(!GPRE || C::NG == 7 || C::NG == 10, "precomputed geometry: symmetric scalar forms or general forms");
   static_assert(NFORM == 1 || (FK && !FM && C::NG == 10), "several forms per launch: general stiffness-like forms only");
   constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, QC = C::QC, NT = C::NT, NW = C::NW;
   constexpr int T1 = C::T1, T2 = C::T2, H1 = C::H1, H2 = C::H2, NQ1 = C::NQ1, NQ2 = C::NQ2;
@@ -874,7 +893,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
       // sG was last read by S1 of step s (phase X, generic proxy): order those reads before the async-proxy writes
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(gbar, (unsigned)(sizeof(double) * C::SZ_G));
-      tma_load_4d(smem_addr(sG), &gmap, NQ * e1base, (ln - prm.g_ebeg) * NQ + qcn, NQ * e2base, 0, gbar);
+      tma_load_4d(smem_addr(sG), &gmap, NQ * e1base, (ln - prm.g_ebeg) * NQ + qcn, NQ * e2base, formn * C::NG, gbar);
     }
     const int ns2 = s >= 0 ? NS2 : 0;
     for (int wi = warp; wi < ns2 + ngc;) {
@@ -927,11 +946,13 @@ struct GeomCache {
 };
 
 // GPRE launches: run k_geom3d over the element layers the launch touches and describe the result to the TMA unit
-template <class C>
+template <class C, int NFORM>
 int prepare_geometry(b2_ctx* ctx, RowParams& prm, CUtensorMap* map) {
   constexpr int P = C::P, NQ = C::NQ;
+  constexpr bool GEN = C::NG == 10;
+  constexpr int NCOMP = C::NG * NFORM;
   GeomCache* gc = (GeomCache*)prm.host_gcache;
-  if (gc && gc->valid && gc->box[0] == C::NQ1 && gc->box[1] == C::QC && gc->box[2] == C::NQ2 && gc->box[3] == C::NG) {
+  if (!GEN && gc && gc->valid && gc->box[0] == C::NQ1 && gc->box[1] == C::QC && gc->box[2] == C::NQ2 && gc->box[3] == C::NG) {
     *map = gc->map;
     prm.g_ebeg = gc->g_ebeg;
     return B2_OK;
@@ -944,7 +965,7 @@ int prepare_geometry(b2_ctx* ctx, RowParams& prm, CUtensorMap* map) {
   if (!encode) return b2_fail(ctx, B2_ECUDA, "cuTensorMapEncodeTiled is not available");
   const long long pitch1 = ((long long)NQ * n1 + 1) & ~1LL;  // rows of Q1 start on 16-byte boundaries
   const long long sQ2 = nlay * NQ * pitch1, scomp = (long long)NQ * n2 * sQ2;
-  const size_t need = sizeof(double) * (size_t)(C::NG * scomp);
+  const size_t need = sizeof(double) * (size_t)(NCOMP * scomp);
   if (ctx->gbuf_bytes < need) {
     if (ctx->gbuf) cudaFree(ctx->gbuf);
     ctx->gbuf = nullptr;
@@ -963,12 +984,15 @@ int prepare_geometry(b2_ctx* ctx, RowParams& prm, CUtensorMap* map) {
   gp.ebeg = ebeg;
   gp.iso = prm.iso;
   for (int t = 0; t < 6; t++) gp.kc[t] = prm.kc[t];
+  gp.nform = NFORM;
+  for (int f = 0; f < 3; f++)
+    for (int t = 0; t < 9; t++) gp.dm[f][t] = prm.dm[f][t];
   gp.out = (double*)ctx->gbuf;
   gp.pitch1 = pitch1; gp.sQ2 = sQ2; gp.scomp = scomp;
   if ((long long)NQ * n2 > 65535 || nlay > 65535) return B2_EUNSUPPORTED;
   {
     KernelTimer timer(ctx);
-    k_geom3d<P><<<dim3((unsigned)((NQ * n1 + 127) / 128), (unsigned)(NQ * n2), (unsigned)nlay), 128, 0, ctx->stream>>>(gp);
+    k_geom3d<P, GEN><<<dim3((unsigned)((NQ * n1 + 127) / 128), (unsigned)(NQ * n2), (unsigned)nlay), 128, 0, ctx->stream>>>(gp);
   }
   ctx->launches++;
   {
@@ -978,14 +1002,14 @@ int prepare_geometry(b2_ctx* ctx, RowParams& prm, CUtensorMap* map) {
                                         std::to_string(nlay) + " ebeg " + std::to_string(ebeg) + " planes " + std::to_string(prm.plane_begin) + ":" + std::to_string(prm.plane_end));
   }
   prm.g_ebeg = ebeg;
-  const cuuint64_t gdim[4] = {(cuuint64_t)NQ * n1, (cuuint64_t)(nlay * NQ), (cuuint64_t)NQ * n2, (cuuint64_t)C::NG};
+  const cuuint64_t gdim[4] = {(cuuint64_t)NQ * n1, (cuuint64_t)(nlay * NQ), (cuuint64_t)NQ * n2, (cuuint64_t)NCOMP};
   const cuuint64_t gstr[3] = {(cuuint64_t)pitch1 * 8, (cuuint64_t)sQ2 * 8, (cuuint64_t)scomp * 8};
   const cuuint32_t box[4] = {(cuuint32_t)C::NQ1, (cuuint32_t)C::QC, (cuuint32_t)C::NQ2, (cuuint32_t)C::NG};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, ctx->gbuf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return b2_fail(ctx, B2_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
-  if (gc) {
+  if (gc && !GEN) {
     gc->valid = true;
     gc->box[0] = C::NQ1; gc->box[1] = C::QC; gc->box[2] = C::NQ2; gc->box[3] = C::NG;
     gc->g_ebeg = ebeg;
@@ -1003,7 +1027,7 @@ int launch_rows_cfg(b2_ctx* ctx, RowParams& prm) {
   CUtensorMap gmap;
   memset(&gmap, 0, sizeof(gmap));
   if (GPRE) {
-    const int rc = prepare_geometry<C>(ctx, prm, &gmap);
+    const int rc = prepare_geometry<C, NFORM>(ctx, prm, &gmap);
     if (rc != B2_OK) return rc;
   }
   prm.tiles1 = (prm.B.ndofs[1] + C::T1 - 1) / C::T1;
@@ -1048,6 +1072,17 @@ int launch_rows_scalar(b2_ctx* ctx, RowParams& prm) {
     if (rc != B2_ENOMEM) return rc;
   }
   return launch_rows_cfg<C, FK, FM, 1, false, false>(ctx, prm);
+}
+
+// vector-valued launches: the same choice
+template <class C, bool FK, bool FM, int NFORM>
+int launch_rows_vec(b2_ctx* ctx, RowParams& prm) {
+  const bool gpre = !(ctx->opts.count("rows_gpre") && ctx->opts["rows_gpre"] == 0);
+  if (gpre) {
+    const int rc = launch_rows_cfg<C, FK, FM, NFORM, true, true>(ctx, prm);
+    if (rc != B2_ENOMEM) return rc;
+  }
+  return launch_rows_cfg<C, FK, FM, NFORM, true, false>(ctx, prm);
 }
 
 template <class C>
@@ -1104,7 +1139,7 @@ int launch_rows_vector(b2_ctx* ctx, RowParams& base, const FormView& F, const do
         prm.valK = F.values[m];
         if (P <= 2) {
           // degree 2: 512 threads (one dof pair per thread: 3 x 9 accumulators) with the S1 items split in term groups -- 48^3 elasticity 6.25 -> 4.82 ms
-          rc = P == 1 ? launch_rows_cfg<RCfg<1, 8, 8, 2, 512, 0, 10>, true, false, 3, true>(ctx, prm) : launch_rows_cfg<RCfg<2, 4, 4, 3, 512, 1, 10>, true, false, 3, true>(ctx, prm);
+          rc = P == 1 ? launch_rows_vec<RCfg<1, 8, 8, 2, 512, 0, 10>, true, false, 3>(ctx, prm) : launch_rows_vec<RCfg<2, 4, 4, 3, 512, 1, 10>, true, false, 3>(ctx, prm);
         } else {
           // degrees 3 and 4: the accumulators of three column components do not fit the register file together --
           // one launch per column component e, writing the slots (J, e) of the rows (I, crow)
@@ -1114,7 +1149,7 @@ int launch_rows_vector(b2_ctx* ctx, RowParams& base, const FormView& F, const do
             for (int t = 0; t < 9; t++) pe.dm[0][t] = prm.dm[e][t];
             pe.valK = F.values[m] + e;
             if (e) pe.has_f = 0;
-            rc = P == 3 ? launch_rows_cfg<RCfg<3, 3, 3, 2, 256, 3, 10>, true, false, 1, true>(ctx, pe) : launch_rows_cfg<RCfg<4, 2, 2, 1, 256, 3, 10>, true, false, 1, true>(ctx, pe);
+            rc = P == 3 ? launch_rows_vec<RCfg<3, 3, 3, 2, 256, 3, 10>, true, false, 1>(ctx, pe) : launch_rows_vec<RCfg<4, 2, 2, 1, 256, 3, 10>, true, false, 1>(ctx, pe);
           }
         }
       } else {

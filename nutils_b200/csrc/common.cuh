@@ -71,6 +71,10 @@ struct ElemSetView {
   const double* normals;       // [npoints][ndims] scaled reference normals of the points' facets (immersed boundaries), or null
   const signed char* face_dim; // [nsel] -1 volume, k: points on a face normal to reference direction k (surface measure); null = volume
   const double* coef[2 * B2_MAX_FORMS];  // per-point scalar coefficient of matrix form m / vector form B2_MAX_FORMS + v, or null
+  // solution-dependent coefficient of form k: scale * u_h(x_q)^power with u_h = sum_i field[i] N_i evaluated in the kernel
+  const double* field[2 * B2_MAX_FORMS];
+  int field_power[2 * B2_MAX_FORMS];
+  double field_scale[2 * B2_MAX_FORMS];
   long long nq_uniform;        // points per element of the tensor rule (indexing of coef when qoff is null)
   long long nbasis_new;
   const double* coeffs[B2_MAXD];  // local polynomials of the solution basis per dimension
@@ -203,6 +207,9 @@ struct b2_elemset {
   double* d_normals = nullptr;
   double* d_coef[2 * B2_MAX_FORMS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int64_t coef_len[2 * B2_MAX_FORMS] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const double* d_field[2 * B2_MAX_FORMS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // caller-owned device vectors
+  int field_power[2 * B2_MAX_FORMS] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double field_scale[2 * B2_MAX_FORMS] = {1., 1., 1., 1., 1., 1., 1., 1.};
   unsigned char* d_selmask = nullptr;  // [ntotal] 1 = element selected (pattern construction); null = all
   long long* d_dofmap = nullptr;       // [nbasis_new] parent index of each kept basis function; null = identity
   int* d_efirst[B2_MAXD] = {nullptr, nullptr, nullptr};  // [ndofs_d] first / last supporting element of the 1-D functions

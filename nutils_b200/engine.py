@@ -400,6 +400,18 @@ class ElemSetPlan:
         coef = as_f64(coef).ravel()
         self.ctx.check(self.ctx.lib.b2_elemset_set_coefficient(self.elemset, which, coef.ctypes.data_as(c_vp), len(coef)))
 
+    def set_coefficient_field(self, kind, index, field, power=1, scale=1.):
+        '''solution-dependent coefficient scale * u_h^power of matrix form `index` (kind 'matrix') or vector form `index` (kind
+        'vector'), u_h = sum_i field[i] N_i evaluated inside the kernel (b2_elemset_set_coefficient_field).  `field` is a device
+        vector (DeviceBuffer / torch tensor / pointer) that the caller may update in place between assemblies; None removes it.'''
+        which = int(index) + (0 if kind == 'matrix' else 4)
+        self._keep = [k for k in getattr(self, '_keep', []) if k[0] != which]
+        if field is None:
+            self.ctx.check(self.ctx.lib.b2_elemset_set_coefficient_field(self.elemset, which, None, 0, 1.))
+            return
+        self._keep.append((which, field))
+        self.ctx.check(self.ctx.lib.b2_elemset_set_coefficient_field(self.elemset, which, _devptr(field), int(power), float(scale)))
+
     def evaluate(self, fields=(), x=True, weights=True, values=True, grads=False):
         '''Sample.eval on the device (b2_evaluate_elemset_device): returns a dict with the requested arrays in point order:
         'x' [npoints, ndims], 'weights' [npoints] (w |det J|), 'values' [npoints, nfields, ncomp] and 'grads'

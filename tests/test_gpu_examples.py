@@ -79,6 +79,40 @@ def test_semilinear_example():
         assert r['newton_iterations'] <= 8 and h[-1] <= 1e-10 * max(h[0], 1.)
         assert h[-1] < h[-2] ** 1.5 or h[-1] < 1e-12    # superlinear at the end
     assert b['l2_error'] < a['l2_error'] / 5
+    # the in-kernel coefficients (b2_elemset_set_coefficient_field, the default) and the evaluate-then-attach route agree
+    c = semilinear.main(n=6, degree=2, fused=False)
+    assert a['fused'] and not c['fused'] and c['newton_iterations'] == a['newton_iterations']
+    assert numpy.allclose(a['residual_history'][:-1], c['residual_history'][:-1], rtol=1e-8) and abs(a['l2_error'] - c['l2_error']) <= 1e-9
+
+
+def test_field_coefficient_against_pointwise():
+    'b2_elemset_set_coefficient_field: scale * u_h^power inside the kernel == the same coefficient evaluated at the points and attached per point'
+    import torch
+    from nutils_b200 import engine, bspline, points
+    ctx = engine.Context.get(0)
+    rng = numpy.random.RandomState(2)
+    b1 = [bspline.spline_basis_1d(n, 2) for n in (5, 4, 3)]
+    verts = [numpy.linspace(0, 1, n + 1) for n in (5, 4, 3)]
+    nodes = numpy.stack(numpy.meshgrid(*verts, indexing='ij')) + .02 * (rng.rand(3, 6, 5, 4) - .5)
+    plan = engine.ElemSetPlan(ctx, b1, nodes=nodes, rules=points.tensor_gauss(3, 6))
+    u = rng.rand(plan.ndofs)
+    uq = plan.evaluate([u], x=False, weights=False)['values'][:, 0, 0]
+    M, L = engine.form_mass(3), engine.form_load(3)
+    plan.set_coefficient('matrix', 0, 3 * uq ** 2)
+    plan.set_coefficient('vector', 0, .5 * uq ** 3)
+    (ref_m,), (ref_v,) = plan.assemble_host([M], [L])
+    plan.set_coefficient('matrix', 0, None)
+    plan.set_coefficient('vector', 0, None)
+    ud = ctx.device_alloc(8 * plan.ndofs)
+    ud.from_host(u)
+    plan.set_coefficient_field('matrix', 0, ud, power=2, scale=3.)
+    plan.set_coefficient_field('vector', 0, ud, power=3, scale=.5)
+    (m,), (v,) = plan.assemble_host([M], [L])
+    plan.set_coefficient_field('matrix', 0, None)
+    plan.set_coefficient_field('vector', 0, None)
+    assert numpy.linalg.norm(m - ref_m) <= 1e-13 * numpy.linalg.norm(ref_m) and numpy.linalg.norm(v - ref_v) <= 1e-13 * numpy.linalg.norm(ref_v)
+    (m0,), _ = plan.assemble_host([M], [])
+    assert abs(m0 - ref_m).max() > 1e-3 * abs(ref_m).max()   # and it is gone again
 
 
 def test_finitecell_dirichlet_example():

@@ -265,7 +265,7 @@ def test_rows_single_forms(ctx):
 
 
 def test_properties_large(ctx):
-    # size-independent properties at a size the oracle would not finish quickly: 48^3, p=2
+    # size-independent properties at 48^3, p=2 (the value-by-value oracle comparison at bench scale is test_bench_workload_against_oracle)
     n = 48
     b1 = util.bases_1d((n,) * 3, 2, 'spline')
     rules = points.tensor_gauss(3, 4)
@@ -353,3 +353,27 @@ def test_errors(ctx):
         plan.assemble_host([engine.form_mass(2)], [], elem_range=(5, 100))
     with pytest.raises(ValueError):
         engine.Plan(ctx, plan.bases, plan.rules, prob.nodes[:, :-1])
+
+
+@pytest.mark.parametrize('workload,degree,n', [('poisson', 1, 40), ('poisson', 2, 40), ('poisson', 3, 24), ('poisson', 4, 16), ('elasticity', 2, 24), ('elasticity', 1, 24)])
+def test_bench_workload_against_oracle(ctx, workload, degree, n):
+    '''The TIMED configuration of bench.py (same geometry generator, forms, entry point and kernels: k_geom3d + k_rows3d through
+    b2_assemble_host) at the size of bench.py's CPU sample, value by value against the C oracle: pattern bit-exact, relative
+    Frobenius / row-sum / rhs errors <= 1e-12.  bench.py repeats this comparison inside every run (`parity`).'''
+    import bench
+    rate, dt, ndofs, cores, mats, vecs, (prob, b1, rules) = bench.port_assemble(workload, n, degree)
+    Ds, Cs = bench.structured_forms(workload)
+    plan = engine.Plan(ctx, b1, rules, prob.nodes, ncomp=prob.ncomp)
+    n0 = ctx.launch_count
+    vals, rhs = plan.assemble_host(Ds, Cs)
+    assert ctx.launch_count > n0
+    rec = bench.parity_record(vals, [m[0] for m in mats], plan.csr_pattern(), (mats[0][1], mats[0][2]), rhs, vecs, 'test')
+    assert rec['ok'], rec
+    # and the same numbers without the precomputed geometry (in-kernel evaluation): the two routes are interchangeable
+    ctx.set_option('rows_gpre', 0)
+    try:
+        vals0, rhs0 = plan.assemble_host(Ds, Cs)
+    finally:
+        ctx.set_option('rows_gpre', 1)
+    for a, b in zip(vals + rhs, vals0 + rhs0):
+        assert util.relerr(a, b) <= 1e-13
