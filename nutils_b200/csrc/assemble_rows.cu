@@ -241,7 +241,7 @@ __device__ __forceinline__ void s1_item(const RowParams& prm, const double* __re
 
 // ---- S2: contract Q1.  One warp item = (dof i1 of the tile, 32 lanes of (q0, pair2), group set PART) ----
 // groups by the dimension-0 factor still to be applied (a-side, b-side): 0 DD, 1 DV, 2 VD, 3 VV, NGK: M
-template <class C, bool FK, bool FM, int PART, int NPARTS, bool CONST>
+template <class C, bool FK, bool FM, int PART, int NPARTS, bool CONST, bool SYM = false>
 __device__ __forceinline__ void s2_item(const RowParams& prm, const double* __restrict__ sT1, const double* __restrict__ sTb1, const double* __restrict__ sL1, double* __restrict__ sT2,
                                         double* __restrict__ sL2, int i1, int i1l, int L, int n1, bool want_f) {
   constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, T1 = C::T1, T2 = C::T2, NP2 = C::NP2, L2S = C::L2S, N12P = C::N12P;
@@ -283,6 +283,7 @@ __device__ __forceinline__ void s2_item(const RowParams& prm, const double* __re
       for (int b = 0; b <= P; b++) {
         const double vb = CONST ? prm.ctab[1][q1][b][0] : tb[b * 2], db = CONST ? prm.ctab[1][q1][b][1] : tb[b * 2 + 1];
         const int d = b + k;
+        if (SYM && d < P) continue;  // symmetric forms: the pairs (i1, j1 < i1) are produced by the tile of j1 and stored transposed
         if (GA) {
           u[d][0] = fma(X[0], vb, u[d][0]);
           u[d][1] = fma(X[1], db, fma(X[2], vb, u[d][1]));
@@ -295,7 +296,7 @@ __device__ __forceinline__ void s2_item(const RowParams& prm, const double* __re
   }
   double* o = sT2 + q0l * C::T2QS + (i1l * WD) * NP2 + pair2;
 #pragma unroll
-  for (int d = 0; d < WD; d++) {
+  for (int d = SYM ? P : 0; d < WD; d++) {
     if (GA) { o[0 * N12P + d * NP2] = u[d][0]; o[1 * N12P + d * NP2] = u[d][1]; o[2 * N12P + d * NP2] = u[d][2]; }
     if (GB) o[3 * N12P + d * NP2] = u[d][3];
     if (GM) o[NGK * N12P + d * NP2] = u[d][4];
@@ -309,10 +310,10 @@ template <class C, bool FK, bool FM, int PART, int NPARTS>
 __device__ __noinline__ void s1_item_tab(const RowParams& prm, const double* sG, const double* sTb2, double* sT1, double* sL1, int i2, int i2l, int L, int n2) {
   s1_item<C, FK, FM, PART, NPARTS, false>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
 }
-template <class C, bool FK, bool FM, int PART, int NPARTS>
+template <class C, bool FK, bool FM, int PART, int NPARTS, bool SYM = false>
 __device__ __noinline__ void s2_item_tab(const RowParams& prm, const double* sT1, const double* sTb1, const double* sL1, double* sT2, double* sL2, int i1, int i1l, int L,
                                          int n1, bool want_f) {
-  s2_item<C, FK, FM, PART, NPARTS, false>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, want_f);
+  s2_item<C, FK, FM, PART, NPARTS, false, SYM>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, want_f);
 }
 
 // 1/a for the normal, positive |det J| of a valid mesh: hardware seed (>= 20 bits) + two Newton steps (error < 2 ulp);
@@ -565,14 +566,20 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map
 //   phase X:  S3(l-1) + store(l-1)  [static: the thread owns its dof pair's accumulators]   ||   S1(l)   [queue]
 //   phase Y:  S2(l)  [queue]   ||   G(l+1)  [queue, 32 columns per item]
 // NFORM > 1: vector-valued stiffness-like launch, forms = column components, one pipeline step per (layer, form, chunk)
-template <class C, bool FK, bool FM, int NFORM, bool VEC, bool GPRE>
+template <class C, bool FK, bool FM, int NFORM, bool VEC, bool GPRE, bool SYM>
 __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __grid_constant__ CUtensorMap gmap) {
+  static_assert(!SYM || (!VEC && NFORM == 1 && C::NG == 7), "symmetric variant: scalar forms with a symmetric coefficient");
   static_assert(!GPRE || C::NG == 7 || C::NG == 10, "precomputed geometry: symmetric scalar forms or general forms");
   static_assert(NFORM == 1 || (FK && !FM && C::NG == 10), "several forms per launch: general stiffness-like forms only");
   constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, QC = C::QC, NT = C::NT, NW = C::NW;
   constexpr int T1 = C::T1, T2 = C::T2, H1 = C::H1, H2 = C::H2, NQ1 = C::NQ1, NQ2 = C::NQ2;
   constexpr int NP2 = C::NP2, LS = C::LS, L2S = C::L2S;
-  constexpr int N12 = C::N12, N12P = C::N12P, IPT = C::IPT;
+  constexpr int N12 = C::N12, N12P = C::N12P;
+  // SYM: a thread owns a dof pair {(i1, i2), (j1, j2)} with (j1, j2) >= (i1, i2) -- (WD^2 + 1) / 2 partners per tile dof -- and stores
+  // its entries twice, as (i, j) and transposed as (j, i): half the S3 work and two thirds of the S2 work of the full variant
+  constexpr int NSYM = (WD * WD + 1) / 2, N12S = T1 * T2 * NSYM;
+  constexpr int IPT = SYM ? (N12S + NT - 1) / NT : C::IPT;
+  static_assert(!SYM || 2 * IPT <= C::IPT || IPT * NT * 2 <= C::IPT * NT, "the transposed row-start factors share the sIc array");
   constexpr int NGK = FK ? 4 : 0;  // S2 output groups: DD DV VD VV [M]
   constexpr int NPARTS1 = ((C::SPLIT & 1) && FK) ? 3 : 1, NPARTS = ((C::SPLIT & 2) && FK) ? 2 : 1;  // term groups of S1 / S2 items
   static_assert(NQ % QC == 0, "the points q0 of a layer are processed in NQ/QC chunks");
@@ -689,20 +696,43 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
   // packed per item: wid1*wid2 | position of (j1, j2) in that box << 8 | tile-local (i1, i2) << 16 | valid << 24 | diagonal << 25;
   // the 64-bit row-start factor lives in shared memory (read once per layer), the rest is re-derived when needed
   int imeta[IPT];
-  long long* sIc = reinterpret_cast<long long*>(smem + C::OFF_IC);  // [IPT][NT]
+  int imetaT[SYM ? IPT : 1];   // SYM: the same for the transposed entry (row (j1, j2), column (i1, i2)); bit 24 = it exists (off-diagonal pair)
+  int t2idx[IPT];              // index of the pair in the T2 arrays
+  long long* sIc = reinterpret_cast<long long*>(smem + C::OFF_IC);  // [IPT][NT] (SYM: [2 IPT][NT], direct then transposed)
 #pragma unroll
   for (int it = 0; it < IPT; it++) {
     const int item = tid + it * NT;
-    const int pair1 = item / NP2, pair2 = item % NP2;
-    const int i1l = pair1 / WD, d1 = pair1 % WD, i2l = pair2 / WD, d2 = pair2 % WD;
+    int i1l, d1, i2l, d2;
+    bool inrange;
+    if (SYM) {
+      const int t = item / NSYM, k = item % NSYM;
+      i1l = t / T2; i2l = t % T2;
+      if (k <= P) { d1 = P; d2 = P + k; }                                  // (0, 0..P)
+      else { d1 = P + 1 + (k - P - 1) / WD; d2 = (k - P - 1) % WD; }        // (1..P, -P..P)
+      inrange = item < N12S;
+    } else {
+      const int pair1 = item / NP2, pair2 = item % NP2;
+      i1l = pair1 / WD; d1 = pair1 % WD; i2l = pair2 / WD; d2 = pair2 % WD;
+      inrange = item < N12;
+    }
+    t2idx[it] = inrange ? (i1l * WD + d1) * NP2 + i2l * WD + d2 : 0;
     const int i1 = i1lo + i1l, j1 = i1 + d1 - P, i2 = i2lo + i2l, j2 = i2 + d2 - P;
-    const bool v = item < N12 && i1 < nd1 && i2 < nd2 && j1 >= 0 && j1 < nd1 && j2 >= 0 && j2 < nd2;
+    const bool v = inrange && i1 < nd1 && i2 < nd2 && j1 >= 0 && j1 < nd1 && j2 >= 0 && j2 < nd2;
     imeta[it] = (i1l * T2 + i2l) << 16;
     sIc[it * NT + tid] = 0;
+    if (SYM) {
+      imetaT[it] = 0;
+      sIc[(IPT + it) * NT + tid] = 0;
+    }
     if (v) {
       const int w1 = B.wid[1][i1], w2 = B.wid[2][i2];
       sIc[it * NT + tid] = (long long)B.cum[1][i1] * B.W[2] + (long long)w1 * B.cum[2][i2];
       imeta[it] |= (w1 * w2) | ((j1 - B.lo[1][i1]) * w2 + (j2 - B.lo[2][i2])) << 8 | 1 << 24 | (d1 == P && d2 == P ? 1 << 25 : 0);
+      if (SYM && !(d1 == P && d2 == P)) {
+        const int v1 = B.wid[1][j1], v2 = B.wid[2][j2];
+        sIc[(IPT + it) * NT + tid] = (long long)B.cum[1][j1] * B.W[2] + (long long)v1 * B.cum[2][j2];
+        imetaT[it] = (v1 * v2) | ((i1 - B.lo[1][j1]) * v2 + (i2 - B.lo[2][j2])) << 8 | 1 << 24;
+      }
     }
   }
   const long long W12 = B.W[1] * B.W[2];
@@ -747,9 +777,8 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
         }
 #pragma unroll
         for (int it = 0; it < IPT; it++) {
-          const int item = tid + it * NT;
-          if (item < N12) {
-            const double* x = sT2 + q0l * C::T2QS + item;
+          if (SYM ? (imeta[it] >> 24 & 1) : (tid + it * NT < N12)) {
+            const double* x = sT2 + q0l * C::T2QS + t2idx[it];
             double gDD = 0., gDV = 0., gVD = 0., gVV = 0., gM = 0.;
             if (FK) { gDD = x[0]; gDV = x[N12P]; gVD = x[2 * N12P]; gVV = x[3 * N12P]; }
             if (FM) gM = x[NGK * N12P];
@@ -802,6 +831,23 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
               const int il = imeta[it] >> 16 & 255;
               prm.rhs[((long long)e0 * nd1 + i1lo + il / T2) * nd2 + i2lo + il % T2] = accF[it][0] * prm.vcoef;
             }
+            if (SYM && (imetaT[it] >> 24 & 1)) {
+              // the transposed entries: row (e0 + b, j1, j2), column (e0 + a, i1, i2)
+              const int iwT = imetaT[it] & 255;
+              const long long bT = (long long)WD * sIc[(IPT + it) * NT + tid] + (imetaT[it] >> 8 & 255);
+#pragma unroll
+              for (int b = 0; b < NB; b++) {
+                const long long rb = (long long)sRow[b * 4 + 2] * W12 + bT;
+#pragma unroll
+                for (int a = 0; a < NB; a++) {
+                  if (a == 0 || b == 0) {
+                    const long long slot = rb + (P - b + a) * iwT;
+                    if (FK) prm.valK[slot] = accK[it][0][a][b];
+                    if (FM && prm.valM) prm.valM[slot] = accM[it][a][b] * prm.rho;
+                  }
+                }
+              }
+            }
           }
         } else if (imeta[it] >> 24 & 1) {
           const long long ic12 = sIc[it * NT + tid];
@@ -833,6 +879,25 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
             if (prm.has_f && (imeta[it] >> 25 & 1) && (a == 0 || last)) {
               const int il = imeta[it] >> 16 & 255;
               prm.rhs[(((long long)i0 * nd1 + i1lo + il / T2) * nd2 + i2lo + il % T2) * nc + prm.crow] = accF[it][a] * prm.vcoef;
+            }
+          }
+          if (SYM && (imetaT[it] >> 24 & 1)) {
+            const long long icT = sIc[(IPT + it) * NT + tid];
+            const int iwT = imetaT[it] & 255, ioT = imetaT[it] >> 8 & 255;
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+              const int j0 = e0 + b;
+              if (j0 < r0 || j0 >= r1) continue;
+              const int rlo = sRow[b * 4], rwid = sRow[b * 4 + 1], rcum = sRow[b * 4 + 2];
+              const long long rowslot = (long long)rcum * W12 + (long long)rwid * icT + ioT;
+#pragma unroll
+              for (int a = 0; a < NB; a++) {
+                if (a == 0 || b == 0 || last) {
+                  const long long slot = rowslot + (long long)(e0 + a - rlo) * iwT;
+                  if (FK) prm.valK[slot] = accK[it][0][a][b];
+                  if (FM && prm.valM) prm.valM[slot] = accM[it][a][b] * prm.rho;
+                }
+              }
             }
           }
         }
@@ -905,13 +970,13 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
         const int i1l = wj / C::WPI2, L = (wj % C::WPI2) * 32 + lane, i1 = i1lo + i1l;
         if (i1 < nd1 && L < L2S && (L % C::NP2P) < NP2) {
           if (uni1) {
-            if (NPARTS == 1) s2_item<C, FK, FM, 0, 1, true>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
-            else if (part == 0) s2_item<C, FK, FM, 0, 2, true>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
-            else s2_item<C, FK, FM, 1, 2, true>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+            if (NPARTS == 1) s2_item<C, FK, FM, 0, 1, true, SYM>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+            else if (part == 0) s2_item<C, FK, FM, 0, 2, true, SYM>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+            else s2_item<C, FK, FM, 1, 2, true, SYM>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
           } else {
-            if (NPARTS == 1) s2_item_tab<C, FK, FM, 0, 1>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
-            else if (part == 0) s2_item_tab<C, FK, FM, 0, 2>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
-            else s2_item_tab<C, FK, FM, 1, 2>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+            if (NPARTS == 1) s2_item_tab<C, FK, FM, 0, 1, SYM>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+            else if (part == 0) s2_item_tab<C, FK, FM, 0, 2, SYM>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
+            else s2_item_tab<C, FK, FM, 1, 2, SYM>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
           }
         }
       }
@@ -1018,9 +1083,9 @@ int prepare_geometry(b2_ctx* ctx, RowParams& prm, CUtensorMap* map) {
   return B2_OK;
 }
 
-template <class C, bool FK, bool FM, int NFORM = 1, bool VEC = false, bool GPRE = false>
+template <class C, bool FK, bool FM, int NFORM = 1, bool VEC = false, bool GPRE = false, bool SYM = false>
 int launch_rows_cfg(b2_ctx* ctx, RowParams& prm) {
-  auto kern = k_rows3d<C, FK, FM, NFORM, VEC, GPRE>;
+  auto kern = k_rows3d<C, FK, FM, NFORM, VEC, GPRE, SYM>;
   const size_t smem = sizeof(double) * C::TOTAL;
   static_assert(sizeof(double) * C::TOTAL <= 227 * 1024, "tile does not fit in shared memory");
   B2_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1067,11 +1132,12 @@ int launch_rows_cfg(b2_ctx* ctx, RowParams& prm) {
 template <class C, bool FK, bool FM>
 int launch_rows_scalar(b2_ctx* ctx, RowParams& prm) {
   const bool gpre = !(ctx->opts.count("rows_gpre") && ctx->opts["rows_gpre"] == 0);
+  const bool sym = !(ctx->opts.count("rows_sym") && ctx->opts["rows_sym"] == 0);  // the coefficient of a scalar form is symmetric (checked by the caller)
   if (gpre) {
-    const int rc = launch_rows_cfg<C, FK, FM, 1, false, true>(ctx, prm);
+    const int rc = sym ? launch_rows_cfg<C, FK, FM, 1, false, true, true>(ctx, prm) : launch_rows_cfg<C, FK, FM, 1, false, true, false>(ctx, prm);
     if (rc != B2_ENOMEM) return rc;
   }
-  return launch_rows_cfg<C, FK, FM, 1, false, false>(ctx, prm);
+  return launch_rows_cfg<C, FK, FM, 1, false, false, false>(ctx, prm);
 }
 
 // vector-valued launches: the same choice
@@ -1270,7 +1336,9 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
     // degree 4 (the high-order IGA case): 2 x 3 dof columns per CTA, one point-plane per pipeline step, S1/S2 items split
     // in term groups; K and M in separate launches (25 accumulators per dof pair and form, two dof pairs per thread)
     using C4 = RCfg<4, 2, 3, 1, 256, 3>;  // 2 x 3 dof columns: 486 of 512 accumulator slots used, halo 6 x 7 elements (48^3: 14.4 -> 13.7 ms against 2 x 2)
-    if (!(fk && fm)) return launch_rows_forms<C4>(ctx, prm, fk, fm);
+    const bool sym4 = !(ctx->opts.count("rows_sym") && ctx->opts["rows_sym"] == 0) && !(ctx->opts.count("rows_gpre") && ctx->opts["rows_gpre"] == 0);
+    // symmetric variant: one dof pair per thread (246 of 256), 2 x 25 accumulators: K and M in ONE launch
+    if (!(fk && fm) || (sym4 && !(ctx->opts.count("rows_split_forms") && ctx->opts["rows_split_forms"]))) return launch_rows_forms<C4>(ctx, prm, fk, fm);
     RowParams pk = prm;
     pk.valM = nullptr;
     int rc = launch_rows_scalar<C4, true, false>(ctx, pk);
@@ -1284,7 +1352,8 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
     // two chunks of two point-planes per layer
     using C3 = RCfg<3, 3, 3, 2, 256, 3>;
     // K and M together: 512 threads (one dof pair per thread: 2 x 16 accumulators, 128 registers) -- 96^3: 14.5 ms
-    if (fk && fm && !(ctx->opts.count("rows_split_forms") && ctx->opts["rows_split_forms"])) return launch_rows_scalar<RCfg<3, 3, 3, 2, 512, 3>, true, true>(ctx, prm);
+    // (the 512-thread one-pair-per-thread configuration of round 1 is what the symmetric variant gives with 256 threads)
+    if (fk && fm && (ctx->opts.count("rows_sym") && ctx->opts["rows_sym"] == 0) && !(ctx->opts.count("rows_split_forms") && ctx->opts["rows_split_forms"])) return launch_rows_cfg<RCfg<3, 3, 3, 2, 512, 3>, true, true, 1, false, true, false>(ctx, prm);
     // K and M in one launch (the geometry stage runs once; 2 x 2 x 16 accumulators per thread spill ~0.7 KB to L1, still
     // 10 % faster than two launches: 96^3 17.7 -> 15.9 ms); option "rows_split_forms" = 1 selects the two launches
     if (!(fk && fm) || !(ctx->opts.count("rows_split_forms") && ctx->opts["rows_split_forms"])) return launch_rows_forms<C3>(ctx, prm, fk, fm);
@@ -1313,6 +1382,8 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
     if (variant == 12) return launch_rows_cfg<RCfg<2, 4, 4, 3, 512, 0>, true, true>(ctx, prm);
     if (variant == 13) return launch_rows_cfg<RCfg<2, 4, 4, 3, 384, 1>, true, true>(ctx, prm);
     if (variant == 30) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 0>, true, true, 1, false, true>(ctx, prm);
+    if (variant == 40) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 0>, true, true, 1, false, true, true>(ctx, prm);
+    if (variant == 41) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 0>, true, true, 1, false, false, true>(ctx, prm);
     if (variant == 31) return launch_rows_cfg<RCfg<2, 4, 4, 3, 512, 1>, true, true, 1, false, true>(ctx, prm);
     if (variant == 20) return launch_rows_cfg<RCfg<2, 4, 4, 1, 256, 1, 7, 2>, true, true>(ctx, prm);
     if (variant == 21) return launch_rows_cfg<RCfg<2, 4, 4, 1, 256, 3, 7, 2>, true, true>(ctx, prm);
