@@ -65,7 +65,14 @@ class GpuBackend:
         plan = self._plans.get(key)
         if plan is None:
             ctx = engine.Context.get(self.device)
-            plan = self._plans[key] = engine.Plan(ctx, spec['bases'], spec['rules'], spec['nodes'], ncomp=spec['ncomp'])
+            if 'face' in spec:
+                ids, xi, w = spec['elem_ids'], spec['xi'], spec['weights']
+                plan = engine.ElemSetPlan(ctx, spec['bases'], nodes=spec['nodes'], ncomp=spec['ncomp'], elem_ids=ids,
+                                          qoff=numpy.arange(len(ids) + 1, dtype=numpy.int64) * len(w), qcoords=numpy.tile(xi, (len(ids), 1)), qweights=numpy.tile(w, len(ids)))
+                plan.set_faces(numpy.full(len(ids), spec['face']['dim'], dtype=numpy.int8))
+            else:
+                plan = engine.Plan(ctx, spec['bases'], spec['rules'], spec['nodes'], ncomp=spec['ncomp'])
+            self._plans[key] = plan
         return plan
 
     def pattern(self, spec):
@@ -85,9 +92,11 @@ def set_backend(backend):
 
 # ---- host-side jets of the local basis functions (recognition only; the assembly never runs on the host) ---------------
 
-def element_jets(bases, nodes, eidx, xi):
+def element_jets(bases, nodes, eidx, xi, nidx=None):
     '''Values and PHYSICAL gradients of the local functions of element `eidx` (index per dimension) at local points
-    xi[nq, nd] for a multilinear nodal geometry: returns (phi[nq, n_e, 1+nd], detJ[nq]); local functions in C order.'''
+    xi[nq, nd] for a multilinear nodal geometry: returns (phi[nq, n_e, 1+nd], |det J|[nq], J^-1[nq, nd, nd]); local functions in C
+    order.  `nidx` is the position of the element in `nodes` when that array covers only part of the grid (default: eidx).'''
+    nidx = eidx if nidx is None else nidx
     nd = len(bases)
     nq = len(xi)
     N = numpy.ones((nq, 1))
@@ -101,7 +110,7 @@ def element_jets(bases, nodes, eidx, xi):
         dN = [(dN[k][:, :, None] * (g if k == d else v)[:, None, :]).reshape(nq, -1) for k in range(nd)]
     J = numpy.zeros((nq, nd, nd))
     for corner in itertools.product((0, 1), repeat=nd):
-        X = nodes[(slice(None),) + tuple(e + c for e, c in zip(eidx, corner))]
+        X = nodes[(slice(None),) + tuple(e + c for e, c in zip(nidx, corner))]
         for k in range(nd):
             dphi = numpy.ones(nq)
             for d in range(nd):
@@ -112,7 +121,7 @@ def element_jets(bases, nodes, eidx, xi):
     phi = numpy.empty((nq, N.shape[1], 1 + nd))
     phi[:, :, 0] = N
     phi[:, :, 1:] = numpy.einsum('kqa,qkj->qaj', numpy.stack(dN), Jinv)
-    return phi, det
+    return phi, det, Jinv
 
 
 def element_dofs(bases, eidx):
@@ -126,9 +135,14 @@ def element_dofs(bases, eidx):
 # ---- python-side state of one intercepted integral ---------------------------------------------------------------------
 
 class _Info:
-    def __init__(self, sample, integrand, shape, coords, weights, rules):
+    def __init__(self, sample, integrand, shape, coords, weights, rules, face=None):
         self.sample = sample
         self.integrand = integrand
+        self.face = face            # None: volume sample; dict(dim, side, index): a side of the topology, `shape` holds the tangential dimensions
+        if face is not None:
+            # points in the coordinates of the adjacent VOLUME element: the fixed coordinate is 0 or 1 (the order of the tangential
+            # points does not matter for a sum)
+            coords = numpy.insert(coords, face['dim'], float(face['side']), axis=1)
         self.shape = shape          # elements per dimension
         self.coords = coords        # points of one element [nq, nd]
         self.weights = weights
@@ -167,12 +181,26 @@ class _Info:
             self._tree = bases, geoms
         return self._tree
 
+    def volume_shape(self, nfixed=1):
+        'elements per dimension of the volume grid the element indices refer to (for a side: `nfixed` elements along the fixed dimension)'
+        if self.face is None:
+            return self.shape
+        return self.shape[:self.face['dim']] + (nfixed,) + self.shape[self.face['dim']:]
+
     def corner_sample(self):
-        'a sample on the same transforms whose points are the 2^nd corners of every element'
-        nd = len(self.shape)
+        'a sample whose points are the 2^nd corners of every (adjacent volume) element'
+        trans = self.sample.transforms
+        if self.face is not None:
+            # the layer of volume elements behind the side: the fixed axis becomes a dimension axis of length one
+            tseq = importlib.import_module(_NT['nutils'].__name__ + '.transformseq')
+            t0 = trans[0]
+            axes = tuple(tseq.DimAxis(a.i, a.j, a.mod, False) if not a.isdim else a for a in t0._axes)
+            slab = tseq.StructuredTransforms(t0._root, axes, t0._nrefine)
+            trans = (slab, slab)
+        nd = len(self.volume_shape())
         corners = numpy.array(list(itertools.product((0., 1.), repeat=nd)))
         pts = _NT['pointsseq'].PointsSequence.uniform(_NT['points'].CoordsPoints(_NT['types'].arraydata(corners)), self.sample.nelems)
-        return _NT['sample'].Sample.new(self.sample.spaces[0], self.sample.transforms, pts)
+        return _NT['sample'].Sample.new(self.sample.spaces[0], trans, pts)
 
     def nodes(self):
         '''nodal coordinates float64[nd, n0+1, ...] of the geometry of the integrand, evaluated by the reference at the
@@ -182,7 +210,8 @@ class _Info:
             bases, geoms = self.tree()
             if not geoms:
                 raise Declined('no geometry in the integrand')
-            nd = len(self.shape)
+            vshape = self.volume_shape()
+            nd = len(vshape)
             cs = self.corner_sample()
             vals = []
             for g in geoms:
@@ -196,10 +225,10 @@ class _Info:
             scale = abs(vals[0]).max() or 1.
             if any(abs(v - vals[0]).max() > 1e-13 * scale for v in vals[1:]):
                 raise Declined('more than one geometry in the integrand')
-            x = vals[0].reshape(self.shape + (2,) * nd + (nd,))
-            nodes = numpy.full((nd,) + tuple(n + 1 for n in self.shape), numpy.nan)
+            x = vals[0].reshape(vshape + (2,) * nd + (nd,))
+            nodes = numpy.full((nd,) + tuple(n + 1 for n in vshape), numpy.nan)
             for corner in itertools.product((0, 1), repeat=nd):
-                sl = tuple(slice(c, n + c) for c, n in zip(corner, self.shape))
+                sl = tuple(slice(c, n + c) for c, n in zip(corner, vshape))
                 v = numpy.moveaxis(x[(Ellipsis,) + corner + (slice(None),)], -1, 0)
                 old = nodes[(slice(None),) + sl]
                 if (abs(numpy.where(numpy.isnan(old), v, old) - v) > 1e-12 * scale).any():
@@ -220,9 +249,20 @@ def _sample_info(sample):
     if type(sample).__name__ != '_DefaultIndex' or len(sample.spaces) != 1:
         raise Declined('sample type {}'.format(type(sample).__name__))
     trans = sample.transforms[0]
-    if type(trans).__name__ != 'StructuredTransforms' or not all(getattr(a, 'isdim', False) and not a.isperiodic for a in trans._axes):
-        raise Declined('not a volume sample of a non-periodic structured topology')
-    shape = tuple(len(a) for a in trans._axes)
+    if type(trans).__name__ != 'StructuredTransforms':
+        raise Declined('not a sample of a structured topology')
+    axes = trans._axes
+    fixed = [k for k, a in enumerate(axes) if not getattr(a, 'isdim', False)]
+    if any(getattr(a, 'isperiodic', False) for a in axes) or len(fixed) > 1 or (fixed and type(axes[fixed[0]]).__name__ != 'IntAxis'):
+        raise Declined('not a volume or boundary sample of a non-periodic structured topology')
+    face = None
+    if fixed:
+        # a side of the topology (topology.py:2049-2057): the elements are the faces of the adjacent volume elements
+        a = axes[fixed[0]]
+        if len(a) != 1:
+            raise Declined('interfaces are not boundary sides')
+        face = dict(dim=fixed[0], side=int(bool(a.side)), index=int(a.map(0)))
+    shape = tuple(len(a) for k, a in enumerate(axes) if k not in fixed)
     if type(sample.points).__name__ != '_Uniform' or sample.nelems == 0:
         raise Declined('points differ per element')
     pts = sample.points.get(0)
@@ -232,7 +272,7 @@ def _sample_info(sample):
     except Exception:
         raise Declined('points without weights')
     nd = len(shape)
-    if coords.ndim != 2 or coords.shape[1] != nd or not 1 <= nd <= 3:
+    if coords.ndim != 2 or coords.shape[1] != nd or not (1 <= nd <= 3 or (face and nd == 0)) or len(axes) > 3:
         raise Declined('dimension')
     # tensor rule?  per-dimension points ascending, C-order outer product (points.py:144-164)
     rules = []
@@ -248,10 +288,12 @@ def _sample_info(sample):
         w = W.sum(axis=tuple(k for k in range(nd) if k != d))
         rules.append((numpy.array(x), numpy.array(w)))
     from . import points as _points
+    if nd == 0:
+        return shape, coords, weights, rules, face
     tc, tw = _points.tensor_points(rules)
     if abs(tc - coords).max() > 1e-14 or abs(tw - weights).max() > 1e-14 * abs(weights).max() or any(len(r[0]) > 5 for r in rules):
         raise Declined('points are not a tensor rule')
-    return shape, coords, weights, rules
+    return shape, coords, weights, rules, face
 
 
 # ---- dispatch ----------------------------------------------------------------------------------------------------------
@@ -264,7 +306,7 @@ def _dispatch(cls, func, args, kwargs):
     sample, integrand = args
     STATS['offered'] += 1
     try:
-        shape, coords, weights, rules = _sample_info(sample)
+        shape, coords, weights, rules, face = _sample_info(sample)
     except Declined as e:
         _note_declined(str(e))
         return NotImplemented
@@ -273,7 +315,7 @@ def _dispatch(cls, func, args, kwargs):
         _note_declined('complex integrand')
         return NotImplemented
     token = next(_COUNTER)
-    _REGISTRY[token] = _Info(sample, integrand, shape, coords, weights, rules)
+    _REGISTRY[token] = _Info(sample, integrand, shape, coords, weights, rules, face)
     return _NT['Integral'](integrand, sample, token)
 
 
@@ -335,7 +377,7 @@ def _recognise(node):
     if len(groups) not in (1, 2) or any(g not in (1, 2) for g in groups):
         raise Declined('{} array axes groups'.format(len(groups)))
     dims = [int(n.__index__()) for n in node.shape]
-    nd = len(info.shape)
+    nd = len(info.volume_shape())
     na = nd + 1
     # axes of every group: basis axis [, component axis]
     pos = 0
@@ -350,7 +392,13 @@ def _recognise(node):
     if nc > 3:
         raise Declined('more than three components')
     fbases, _ = info.tree()
-    cands = [b for b in fbases if hasattr(b, '_start_dofs') and tuple(b._transforms_shape) == info.shape and all(len(b) == dims[ax[0]] for ax in gaxes)]
+    def on_topology(b):
+        bshape = tuple(b._transforms_shape)
+        if info.face is None:
+            return bshape == info.shape
+        f = info.face
+        return len(bshape) == nd and bshape == info.volume_shape(bshape[f['dim']]) and f['index'] == (bshape[f['dim']] - 1 if f['side'] else 0)
+    cands = [b for b in fbases if hasattr(b, '_start_dofs') and on_topology(b) and all(len(b) == dims[ax[0]] for ax in gaxes)]
     if not cands:
         raise Declined('no structured basis of the topology matches the array axes')
     nodes = info.nodes()
@@ -362,10 +410,10 @@ def _recognise(node):
         raise Declined('integrand is identically zero')
     f = ev.compile(chunks)
     rng = numpy.random.RandomState(len(dims) * 7919 + info.sample.nelems)
-    elems = _probe_elements(info.shape, rng, 10 + 2 * nd)
+    elems = _probe_elements(info.shape, rng, 10 + 2 * nd) if info.shape else [()]
     data = []
     for e in elems:
-        ielem = int(numpy.ravel_multi_index(e, info.shape))
+        ielem = int(numpy.ravel_multi_index(e, info.shape)) if info.shape else 0
         data.append([tuple(numpy.asarray(a).ravel() for a in chunk) for chunk in f({'_b200_ielem': ielem})])
     last = None
     for basis in cands:
@@ -377,13 +425,18 @@ def _recognise(node):
 
 
 def _fit(node, info, basis, nodes, elems, data, gaxes, nc):
-    nd = len(info.shape)
+    nd = len(info.volume_shape())
     na = nd + 1
     bases = adapter.bases1d_from_structured_basis(basis)
     k = len(gaxes)
+    face = info.face
     A_rows, rhs = [], []
     blocks = []
     for e, chunks in zip(elems, data):
+        nidx = e
+        if face is not None:   # tangential index -> index of the adjacent volume element (in the grid / in the one-layer node array)
+            nidx = e[:face['dim']] + (0,) + e[face['dim']:]
+            e = e[:face['dim']] + (face['index'],) + e[face['dim']:]
         ldofs = element_dofs(bases, e)
         lookup = {int(d): a for a, d in enumerate(ldofs)}
         ne = len(ldofs)
@@ -405,8 +458,10 @@ def _fit(node, info, basis, nodes, elems, data, gaxes, nc):
                 where.append(numpy.array([lookup[int(i)] for i in idx[ax[0]]], dtype=int))
                 where.append(idx[ax[1]] if len(ax) == 2 else numpy.zeros(len(vals), dtype=int))
             numpy.add.at(T, tuple(where), vals)
-        phi, det = element_jets(bases, nodes, e, info.coords)
+        phi, det, Jinv = element_jets(bases, nodes, e, info.coords, nidx)
         wdet = info.weights * det
+        if face is not None:   # surface measure |det J| |J^-T e_k| (function.py:2291-2316 on a boundary sample)
+            wdet = wdet * numpy.linalg.norm(Jinv[:, face['dim'], :], axis=1)
         if k == 2:
             E = numpy.einsum('q,qax,qby->xyab', wdet, phi, phi).reshape(na * na, ne * ne)
         else:
@@ -445,6 +500,17 @@ def _fit(node, info, basis, nodes, elems, data, gaxes, nc):
         C[abs(C) < 1e-13 * abs(C).max()] = 0.
         coef = C
     spec = dict(bases=bases, rules=info.rules, nodes=nodes, ncomp=nc, key=(id(basis), id(info.sample), nc, info.nodes_digest()))
+    if face is not None:
+        # the adjacent volume elements as an element set with points on their faces (b2_elemset_set_faces)
+        vshape = tuple(b.nelems for b in bases)
+        full = numpy.zeros((nd,) + tuple(n + 1 for n in vshape))
+        lo = face['index']
+        sl = (slice(None),) * (1 + face['dim']) + (slice(lo, lo + 2),)
+        full[sl] = nodes
+        grids = [numpy.arange(n) for n in vshape]
+        grids[face['dim']] = numpy.array([lo])
+        elem_ids = numpy.sort(numpy.ravel_multi_index(numpy.stack(numpy.meshgrid(*grids, indexing='ij'), -1).reshape(-1, nd).T, vshape)).astype(numpy.int64)
+        spec.update(nodes=full, face=dict(face), elem_ids=elem_ids, xi=numpy.array(info.coords), weights=numpy.array(info.weights))
     plan = dict(spec=spec, kind='matrix' if k == 2 else 'vector', coef=coef, nc=nc, nbasis=len(basis), gaxes=gaxes, keep=(basis, info), id=next(_COUNTER))
     _PLANS[plan['id']] = plan
     return plan

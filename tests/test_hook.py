@@ -101,6 +101,34 @@ def test_system_elasticity(hooked):
     assert util.relerr(gv, rv) <= 1e-12 and util.relerr(gres, rres) <= 1e-12
 
 
+@pytest.mark.parametrize('shape,side', [((4, 3, 3), 'right'), ((5, 4), 'top'), ((5, 4), 'left'), ((3, 3, 2), 'front'), ((6,), 'right')])
+def test_boundary_side_hooked_equals_stock(hooked, shape, side):
+    'boundary mass matrix and load of one side of the topology (topology.py:2049-2057): the faces of the adjacent elements, surface measure'
+    nutils = util_ref.reference()
+    from nutils import mesh, function
+
+    def run():
+        rng = numpy.random.RandomState(5)
+        verts = [numpy.linspace(0, 1, n + 1) ** (1. + .3 * k) for k, n in enumerate(shape)]
+        topo, geom0 = mesh.rectilinear(verts)
+        X = numpy.stack(numpy.meshgrid(*verts, indexing='ij'))
+        X = X + .1 / max(shape) * (rng.rand(*X.shape) - .5)
+        geom = (topo.basis('spline', degree=1) * X.reshape(len(shape), -1)).sum(-1)
+        basis = topo.basis('spline', degree=2)
+        J = function.J(geom)
+        btopo = topo.boundary[side]
+        M = btopo.integral(basis[:, None] * basis[None, :] * J, degree=4)
+        F = btopo.integral(2.5 * basis * J, degree=4)
+        return function.eval((function.as_csr(M), F))
+    ref = run()
+    hooked.install()
+    be = util_ref.OracleBackend()
+    hooked.set_backend(be)
+    got = run()
+    assert hooked.STATS['accelerated'] == 2 and be.calls == 2, hooked.STATS
+    _compare(ref, got)
+
+
 def test_declines_position_dependent_coefficient(hooked):
     'an integrand outside the closed form falls through to the stock evaluable: same numbers, no backend call'
     nutils = util_ref.reference()
@@ -121,7 +149,7 @@ def test_declines_position_dependent_coefficient(hooked):
 
 
 def test_reference_laplace_example(hooked):
-    'examples/laplace.py of the reference, unmodified: the domain integral is assembled by the backend, the rest declines'
+    'examples/laplace.py of the reference, unmodified: the domain integral and the constant-coefficient boundary matrices are assembled by the backend, the rest declines'
     util_ref.reference()
     import laplace
     cons0, u0, err0 = laplace.main(nelems=6)
@@ -129,7 +157,7 @@ def test_reference_laplace_example(hooked):
     be = util_ref.OracleBackend()
     hooked.set_backend(be)
     cons1, u1, err1 = laplace.main(nelems=6)
-    assert be.calls >= 1 and hooked.STATS['accelerated'] >= 1
+    assert be.calls >= 3 and hooked.STATS['accelerated'] >= 3, hooked.STATS
     assert numpy.array_equal(numpy.isnan(cons0), numpy.isnan(cons1))
     assert numpy.nanmax(abs(cons0 - cons1)) <= 1e-13 and abs(u0 - u1).max() <= 1e-12 and abs(err0 - err1) <= 1e-12
 
@@ -147,7 +175,7 @@ def test_gpu_reference_laplace_example(hooked):
     n0 = ctx.launch_count
     cons, u, err = laplace.main(nelems=32)
     assert ctx.launch_count > n0, 'no kernel was launched: the integrals did not run on the GPU'
-    assert hooked.STATS['accelerated'] >= 1
+    assert hooked.STATS['accelerated'] >= 3, hooked.STATS   # the domain integral and the two constant-coefficient boundary matrices
     assert abs(err - 2.496e-05) <= 5e-9
     assert len(u) == 33 * 33 and int((~numpy.isnan(cons)).sum()) == 65
 

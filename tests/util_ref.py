@@ -36,8 +36,15 @@ class OracleBackend:
     def _problem(self, spec):
         from oracle import fem_oracle
         b1, rules = spec['bases'], spec['rules']
+        kw = {}
+        if 'face' in spec:   # a side of the topology: the adjacent elements as an element set with points on their faces
+            from nutils_b200 import points
+            ids, xi, w = spec['elem_ids'], spec['xi'], spec['weights']
+            kw = dict(elem_ids=ids, qoff=numpy.arange(len(ids) + 1) * len(w), qcoords=numpy.tile(xi, (len(ids), 1)), qweights=numpy.tile(w, len(ids)),
+                      face_dim=numpy.full(len(ids), spec['face']['dim'], dtype=numpy.int8))
+            rules = points.tensor_gauss(len(b1), 2)
         return fem_oracle.Problem(tuple(b.nelems for b in b1), [b.degree for b in b1], [b.coeffs for b in b1], [b.setidx for b in b1], [b.start for b in b1],
-                                  [b.ndofs for b in b1], [r[0] for r in rules], [r[1] for r in rules], spec['nodes'], ncomp=spec['ncomp'])
+                                  [b.ndofs for b in b1], [r[0] for r in rules], [r[1] for r in rules], spec['nodes'], ncomp=spec['ncomp'], **kw)
 
     def pattern(self, spec):
         from oracle import fem_oracle
