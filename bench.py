@@ -316,6 +316,57 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
 
 
+# ---- host placement of a rank (e2e over PCIe) ----------------------------------------------------------------------------------
+
+def numa_nodes():
+    'cpu lists of the NUMA nodes of this host: {node: [cpus]}'
+    out = {}
+    base = '/sys/devices/system/node'
+    try:
+        for name in sorted(os.listdir(base)):
+            if name.startswith('node') and name[4:].isdigit():
+                cpus = []
+                for part in open(os.path.join(base, name, 'cpulist')).read().strip().split(','):
+                    if part:
+                        a, _, b = part.partition('-')
+                        cpus.extend(range(int(a), int(b or a) + 1))
+                if cpus:
+                    out[int(name[4:])] = cpus
+    except OSError:
+        pass
+    return out
+
+
+def place_rank(local, world, policy):
+    '''Pin this rank's threads -- and with them the first-touch placement of its pinned host buffers -- to a NUMA node before
+    anything is allocated.  policy 'gpu': the node the GPU's PCIe root reports (sysfs numa_node); 'spread': ranks round-robin over
+    the nodes (all GPUs of these boxes report node 0, whose memory controllers then take the D2H traffic of every rank); 'none'.
+    Returns a description for the JSON line.'''
+    nodes = numa_nodes()
+    allowed = set(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else set()
+    if policy == 'none' or len(nodes) < 2 or not allowed:
+        return {'policy': 'none', 'nodes': len(nodes)}
+    node = None
+    if policy == 'gpu':
+        try:
+            import torch
+            pr = torch.cuda.get_device_properties(local)
+            bdf = '{:04x}:{:02x}:{:02x}.0'.format(pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            node = int(open('/sys/bus/pci/devices/{}/numa_node'.format(bdf)).read())
+        except Exception:
+            node = None
+        if node is None or node < 0:
+            policy = 'spread'
+    if policy == 'spread':
+        keys = sorted(nodes)
+        node = keys[local * len(keys) // max(world, 1)] if world > 1 else keys[0]
+    cpus = sorted(set(nodes.get(node, [])) & allowed)
+    if not cpus:
+        return {'policy': 'none', 'nodes': len(nodes), 'note': 'no allowed cpu on node {}'.format(node)}
+    os.sched_setaffinity(0, cpus)
+    return {'policy': policy, 'node': node, 'cpus': len(cpus), 'nodes': len(nodes)}
+
+
 # ---- clocks ----------------------------------------------------------------------------------------------------------------
 
 class ClockSampler:
@@ -614,6 +665,7 @@ def run_b200(args):
     local = int(os.environ.get('LOCAL_RANK', 0))
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit('launch with torchrun --nproc-per-node {} for --gpus {}'.format(args.gpus, args.gpus))
+    placement = place_rank(local, world, args.numa if world > 1 else 'none')
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
@@ -739,6 +791,8 @@ def run_b200(args):
                       'element ranges per rank, ONE neighbour exchange (NCCL send/recv) of the shared dof rows'))}
         if getattr(W, 'halo_bytes', 0):
             config['halo_bytes_per_rank'] = W.halo_bytes
+        if world > 1:
+            config['host_placement_rank0'] = placement
         if check is not None:
             config['check_sumM_minus_sumf'] = check
         if hasattr(W, 'plan_seconds'):
@@ -781,6 +835,7 @@ def main():
     ap.add_argument('--fcm-depth', type=int, default=2)
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
     ap.add_argument('--path', default='rows', choices=['rows', 'scatter'], help='structured workloads: rows = owner-computes kernel (default); scatter = element-scatter kernels + exchange')
+    ap.add_argument('--numa', default='spread', choices=['none', 'gpu', 'spread'], help='N > 1: NUMA placement of a rank (and of its pinned host buffers)')
     ap.add_argument('--cpu-n', type=int, default=40, help='elements per direction of the parity / C-port sample')
     ap.add_argument('--ref-n', type=int, default=0, help='size of the reference sample (0: fitted to the time budget)')
     ap.add_argument('--ref-budget', type=float, default=150.)

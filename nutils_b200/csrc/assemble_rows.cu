@@ -63,6 +63,7 @@ struct RowParams {
   double* valM;
   double* rhs;
   int g_ebeg;  // first element layer held by the precomputed geometry array (GPRE launches)
+  int dbg;  // B2_EXPERIMENT builds: skip stages to measure their share of the critical path (1 stores, 2 S3, 4 S1, 8 S2)
   void* host_gcache;  // host only: GeomCache shared by the launches of one b2_assemble_rows_device call
 };
 
@@ -777,6 +778,9 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
         }
 #pragma unroll
         for (int it = 0; it < IPT; it++) {
+#ifdef B2_EXPERIMENT
+          if (prm.dbg & 2) continue;
+#endif
           if (SYM ? (imeta[it] >> 24 & 1) : (tid + it * NT < N12)) {
             const double* x = sT2 + q0l * C::T2QS + t2idx[it];
             double gDD = 0., gDV = 0., gVD = 0., gVV = 0., gM = 0.;
@@ -811,6 +815,10 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
       const bool interior = !VEC && e0 >= P && e0 <= n0 - 1 - P && e0 >= r0 && e0 + P < r1;
 #pragma unroll
       for (int it = 0; it < IPT; it++) {
+#ifdef B2_EXPERIMENT
+        if (prm.dbg & 1) {
+        } else
+#endif
         if (interior) {
           if (imeta[it] >> 24 & 1) {
             const int iw12 = imeta[it] & 255;
@@ -917,7 +925,11 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
       }
     }
     if (s < nstep) {
-      if (GPRE) {  // the box of this step has landed in sG
+      if (GPRE
+#ifdef B2_EXPERIMENT
+          && !(prm.dbg & 16)
+#endif
+      ) {  // the box of this step has landed in sG
         mbar_wait(gbar, gphase);
         gphase ^= 1;
       }
@@ -926,6 +938,10 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
         const int part = wi % NPARTS1, wj = wi / NPARTS1;
         const int i2l = wj / C::WPI1, L = (wj % C::WPI1) * 32 + lane, i2 = i2lo + i2l;
         const int e1 = e1base + (L % NQ1) / NQ;
+#ifdef B2_EXPERIMENT
+        if (prm.dbg & 4) {
+        } else
+#endif
         if (i2 < nd2 && L < LS && e1 >= 0 && e1 < n1) {
           if (uni2) {
             if (NPARTS1 == 1) s1_item<C, FK, FM, 0, 1, true>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
@@ -954,7 +970,11 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
     if (tid == 0) sCnt[0] = NW;
     const int ngc = (!GPRE && s + 1 < nstep) ? NGC : 0;
     const int ln = ebeg + (s + 1) / NSUB, qcn = ((s + 1) % NCH) * QC, formn = ((s + 1) % NSUB) / NCH;
-    if (GPRE && s + 1 < nstep && tid == 0) {
+    if (GPRE && s + 1 < nstep && tid == 0
+#ifdef B2_EXPERIMENT
+        && !(prm.dbg & 16)
+#endif
+    ) {
       // sG was last read by S1 of step s (phase X, generic proxy): order those reads before the async-proxy writes
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(gbar, (unsigned)(sizeof(double) * C::SZ_G));
@@ -968,6 +988,10 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
       } else {
         const int part = wi % NPARTS, wj = wi / NPARTS;
         const int i1l = wj / C::WPI2, L = (wj % C::WPI2) * 32 + lane, i1 = i1lo + i1l;
+#ifdef B2_EXPERIMENT
+        if (prm.dbg & 8) {
+        } else
+#endif
         if (i1 < nd1 && L < L2S && (L % C::NP2P) < NP2) {
           if (uni1) {
             if (NPARTS == 1) s2_item<C, FK, FM, 0, 1, true, SYM>(prm, sT1, sTb1, sL1, sT2, sL2, i1, i1l, L, n1, prm.has_f);
@@ -1132,7 +1156,10 @@ int launch_rows_cfg(b2_ctx* ctx, RowParams& prm) {
 template <class C, bool FK, bool FM>
 int launch_rows_scalar(b2_ctx* ctx, RowParams& prm) {
   const bool gpre = !(ctx->opts.count("rows_gpre") && ctx->opts["rows_gpre"] == 0);
-  const bool sym = !(ctx->opts.count("rows_sym") && ctx->opts["rows_sym"] == 0);  // the coefficient of a scalar form is symmetric (checked by the caller)
+  // the coefficient of a scalar form is symmetric (checked by the caller).  Measured (profiles/r02/README.md): the symmetric variant
+  // wins at degree 2 (-1 %: half the S3 and two thirds of the S2 work against scattered transposed stores) and at degree 4 (K and M in
+  // one launch: -30 %), and loses 2 % at degree 3; degree 1 is indifferent
+  const bool sym = ctx->opts.count("rows_sym") ? ctx->opts["rows_sym"] != 0 : (C::P == 2 || C::P == 4);
   if (gpre) {
     const int rc = sym ? launch_rows_cfg<C, FK, FM, 1, false, true, true>(ctx, prm) : launch_rows_cfg<C, FK, FM, 1, false, true, false>(ctx, prm);
     if (rc != B2_ENOMEM) return rc;
@@ -1140,10 +1167,12 @@ int launch_rows_scalar(b2_ctx* ctx, RowParams& prm) {
   return launch_rows_cfg<C, FK, FM, 1, false, false, false>(ctx, prm);
 }
 
-// vector-valued launches: the same choice
+// vector-valued launches: the precomputed geometry (10 components per column component) is available but NOT the default -- measured
+// on 96^3 p=2 elasticity it changes nothing (31.2 against 30.5 ms: with 16 warps the in-kernel geometry already runs in the shadow of
+// S2) and costs 5.7 GB; option "rows_gpre_vec" = 1 selects it
 template <class C, bool FK, bool FM, int NFORM>
 int launch_rows_vec(b2_ctx* ctx, RowParams& prm) {
-  const bool gpre = !(ctx->opts.count("rows_gpre") && ctx->opts["rows_gpre"] == 0);
+  const bool gpre = ctx->opts.count("rows_gpre_vec") && ctx->opts["rows_gpre_vec"] != 0;
   if (gpre) {
     const int rc = launch_rows_cfg<C, FK, FM, NFORM, true, true>(ctx, prm);
     if (rc != B2_ENOMEM) return rc;
@@ -1263,6 +1292,7 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
   prm.rho = 1.;
   prm.kc[0] = prm.kc[3] = prm.kc[5] = 1.;
   prm.ncomp = B.ncomp;
+  prm.dbg = ctx->opts.count("rows_dbg") ? (int)ctx->opts["rows_dbg"] : 0;
   GeomCache gcache;
   prm.host_gcache = &gcache;
   // dominant coefficient set per dimension and its table at the 1-D points (host copy of what get_tabs uploaded)
@@ -1353,7 +1383,7 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
     using C3 = RCfg<3, 3, 3, 2, 256, 3>;
     // K and M together: 512 threads (one dof pair per thread: 2 x 16 accumulators, 128 registers) -- 96^3: 14.5 ms
     // (the 512-thread one-pair-per-thread configuration of round 1 is what the symmetric variant gives with 256 threads)
-    if (fk && fm && (ctx->opts.count("rows_sym") && ctx->opts["rows_sym"] == 0) && !(ctx->opts.count("rows_split_forms") && ctx->opts["rows_split_forms"])) return launch_rows_cfg<RCfg<3, 3, 3, 2, 512, 3>, true, true, 1, false, true, false>(ctx, prm);
+    if (fk && fm && !(ctx->opts.count("rows_sym") && ctx->opts["rows_sym"] != 0) && !(ctx->opts.count("rows_gpre") && ctx->opts["rows_gpre"] == 0) && !(ctx->opts.count("rows_split_forms") && ctx->opts["rows_split_forms"])) return launch_rows_cfg<RCfg<3, 3, 3, 2, 512, 3>, true, true, 1, false, true, false>(ctx, prm);
     // K and M in one launch (the geometry stage runs once; 2 x 2 x 16 accumulators per thread spill ~0.7 KB to L1, still
     // 10 % faster than two launches: 96^3 17.7 -> 15.9 ms); option "rows_split_forms" = 1 selects the two launches
     if (!(fk && fm) || !(ctx->opts.count("rows_split_forms") && ctx->opts["rows_split_forms"])) return launch_rows_forms<C3>(ctx, prm, fk, fm);

@@ -70,6 +70,10 @@ class GpuBackend:
                 plan = engine.ElemSetPlan(ctx, spec['bases'], nodes=spec['nodes'], ncomp=spec['ncomp'], elem_ids=ids,
                                           qoff=numpy.arange(len(ids) + 1, dtype=numpy.int64) * len(w), qcoords=numpy.tile(xi, (len(ids), 1)), qweights=numpy.tile(w, len(ids)))
                 plan.set_faces(numpy.full(len(ids), spec['face']['dim'], dtype=numpy.int8))
+            elif 'elemset' in spec:
+                es = spec['elemset']
+                plan = engine.ElemSetPlan(ctx, spec['bases'], nodes=spec['nodes'], ncomp=spec['ncomp'], elem_ids=es['elem_ids'], qoff=es['qoff'], qcoords=es['qcoords'],
+                                          qweights=es['qweights'], renumber=spec['renumber'], nbasis_new=spec['nbasis_new'])
             else:
                 plan = engine.Plan(ctx, spec['bases'], spec['rules'], spec['nodes'], ncomp=spec['ncomp'])
             self._plans[key] = plan
@@ -138,6 +142,9 @@ class _Info:
     def __init__(self, sample, integrand, shape, coords, weights, rules, face=None):
         self.sample = sample
         self.integrand = integrand
+        self.elemset = None         # dict(elem_ids, qoff, qcoords, qweights): a subset of the elements and / or per-element point sets
+        if face is not None and 'elemset' in face:
+            self.elemset, face = face['elemset'], None
         self.face = face            # None: volume sample; dict(dim, side, index): a side of the topology, `shape` holds the tangential dimensions
         if face is not None:
             # points in the coordinates of the adjacent VOLUME element: the fixed coordinate is 0 or 1 (the order of the tangential
@@ -222,20 +229,56 @@ class _Info:
                 x = numpy.asarray(cs.eval(g))
                 x = x.reshape(x.shape[0], -1, nd)[:, 0, :]   # broadcast copies of the geometry carry leading axes
                 vals.append(x)
-            scale = abs(vals[0]).max() or 1.
+            scale = numpy.nanmax(abs(vals[0])) or 1.
             if any(abs(v - vals[0]).max() > 1e-13 * scale for v in vals[1:]):
                 raise Declined('more than one geometry in the integrand')
+            if self.elemset is not None:
+                # only the kept elements have corners: scatter them into the full node grid (the rest is never read)
+                ids = self.elemset['elem_ids']
+                full = numpy.full(vshape + (2,) * nd + (nd,), numpy.nan)
+                full.reshape((-1,) + (2,) * nd + (nd,))[ids] = vals[0].reshape((len(ids),) + (2,) * nd + (nd,))
+                vals[0] = full
             x = vals[0].reshape(vshape + (2,) * nd + (nd,))
             nodes = numpy.full((nd,) + tuple(n + 1 for n in vshape), numpy.nan)
             for corner in itertools.product((0, 1), repeat=nd):
                 sl = tuple(slice(c, n + c) for c, n in zip(corner, vshape))
                 v = numpy.moveaxis(x[(Ellipsis,) + corner + (slice(None),)], -1, 0)
                 old = nodes[(slice(None),) + sl]
-                if (abs(numpy.where(numpy.isnan(old), v, old) - v) > 1e-12 * scale).any():
+                if (abs(numpy.where(numpy.isnan(old) | numpy.isnan(v), 0., old - v)) > 1e-12 * scale).any():
                     raise Declined('geometry is discontinuous across elements')
-                nodes[(slice(None),) + sl] = v
+                nodes[(slice(None),) + sl] = numpy.where(numpy.isnan(v), old, v)
+            if self.elemset is not None:
+                nodes = numpy.nan_to_num(nodes)
             self._nodes = nodes
         return self._nodes
+
+    def probes(self, rng):
+        'elements (positions in the sample) on which the integrand is probed: corners, centre and pseudo-random ones'
+        nd = len(self.volume_shape())
+        if self.elemset is not None:
+            n = self.sample.nelems
+            picks = [0, n - 1, n // 2, n // 3, (2 * n) // 3] + [int(rng.randint(n)) for _ in range(12)]
+            out = []
+            for k in picks:
+                if k not in out:
+                    out.append(k)
+            return out[:14]
+        if not self.shape:
+            return [0]
+        return [int(numpy.ravel_multi_index(e, self.shape)) for e in _probe_elements(self.shape, rng, 10 + 2 * nd)]
+
+    def element(self, k):
+        '(index of the volume element per dimension, its position in the node array, local points, weights) of sample element k'
+        if self.elemset is not None:
+            es = self.elemset
+            e = tuple(int(i) for i in numpy.unravel_index(int(es['elem_ids'][k]), self.shape))
+            sl = slice(int(es['qoff'][k]), int(es['qoff'][k + 1]))
+            return e, e, es['qcoords'][sl], es['qweights'][sl]
+        t = tuple(int(i) for i in numpy.unravel_index(k, self.shape)) if self.shape else ()
+        if self.face is None:
+            return t, t, self.coords, self.weights
+        f = self.face
+        return t[:f['dim']] + (f['index'],) + t[f['dim']:], t[:f['dim']] + (0,) + t[f['dim']:], self.coords, self.weights
 
     def nodes_digest(self):
         if self._digest is None:
@@ -249,6 +292,11 @@ def _sample_info(sample):
     if type(sample).__name__ != '_DefaultIndex' or len(sample.spaces) != 1:
         raise Declined('sample type {}'.format(type(sample).__name__))
     trans = sample.transforms[0]
+    elem_ids = None
+    if type(trans).__name__ == 'MaskedTransforms' and type(trans._parent).__name__ == 'StructuredTransforms':
+        # a subset of the elements of a structured topology: trimmed / subset topologies (topology.py:2615-2740)
+        elem_ids = numpy.asarray(trans._indices, dtype=numpy.int64)
+        trans = trans._parent
     if type(trans).__name__ != 'StructuredTransforms':
         raise Declined('not a sample of a structured topology')
     axes = trans._axes
@@ -263,8 +311,27 @@ def _sample_info(sample):
             raise Declined('interfaces are not boundary sides')
         face = dict(dim=fixed[0], side=int(bool(a.side)), index=int(a.map(0)))
     shape = tuple(len(a) for k, a in enumerate(axes) if k not in fixed)
-    if type(sample.points).__name__ != '_Uniform' or sample.nelems == 0:
-        raise Declined('points differ per element')
+    if sample.nelems == 0:
+        raise Declined('empty sample')
+    if type(sample.points).__name__ != '_Uniform' or elem_ids is not None:
+        # cut cells carry their own point sets (pointsseq.py:324-332, points.py:257-337): ragged tables of an element set
+        if face is not None:
+            raise Declined('ragged points on a boundary side')
+        nd = len(shape)
+        if not 1 <= nd <= 3:
+            raise Declined('dimension')
+        qc, qw, qoff = [], [], [0]
+        try:
+            for i in range(sample.nelems):
+                p = sample.points.get(i)
+                qc.append(numpy.asarray(p.coords, dtype=float).reshape(-1, nd))
+                qw.append(numpy.asarray(p.weights, dtype=float))
+                qoff.append(qoff[-1] + len(qw[-1]))
+        except Exception:
+            raise Declined('points without weights')
+        es = dict(elem_ids=numpy.arange(sample.nelems, dtype=numpy.int64) if elem_ids is None else elem_ids, qoff=numpy.array(qoff, dtype=numpy.int64),
+                  qcoords=numpy.concatenate(qc), qweights=numpy.concatenate(qw))
+        return shape, None, None, None, dict(elemset=es)
     pts = sample.points.get(0)
     try:
         coords = numpy.asarray(pts.coords, dtype=float)
@@ -393,12 +460,17 @@ def _recognise(node):
         raise Declined('more than three components')
     fbases, _ = info.tree()
     def on_topology(b):
+        if info.elemset is not None:   # the basis of a trimmed / subset topology is a PrunedBasis of a structured one (function.py:3103-3133)
+            parent = getattr(b, '_parent', None)
+            if parent is None:
+                return hasattr(b, '_start_dofs') and tuple(b._transforms_shape) == info.shape and len(info.elemset['elem_ids']) == int(numpy.prod(info.shape))
+            return hasattr(parent, '_start_dofs') and tuple(parent._transforms_shape) == info.shape and numpy.array_equal(numpy.asarray(b._transmap), info.elemset['elem_ids'])
         bshape = tuple(b._transforms_shape)
         if info.face is None:
             return bshape == info.shape
         f = info.face
         return len(bshape) == nd and bshape == info.volume_shape(bshape[f['dim']]) and f['index'] == (bshape[f['dim']] - 1 if f['side'] else 0)
-    cands = [b for b in fbases if hasattr(b, '_start_dofs') and on_topology(b) and all(len(b) == dims[ax[0]] for ax in gaxes)]
+    cands = [b for b in fbases if (hasattr(b, '_start_dofs') or hasattr(getattr(b, '_parent', None), '_start_dofs')) and on_topology(b) and all(len(b) == dims[ax[0]] for ax in gaxes)]
     if not cands:
         raise Declined('no structured basis of the topology matches the array axes')
     nodes = info.nodes()
@@ -410,10 +482,9 @@ def _recognise(node):
         raise Declined('integrand is identically zero')
     f = ev.compile(chunks)
     rng = numpy.random.RandomState(len(dims) * 7919 + info.sample.nelems)
-    elems = _probe_elements(info.shape, rng, 10 + 2 * nd) if info.shape else [()]
+    elems = info.probes(rng)
     data = []
-    for e in elems:
-        ielem = int(numpy.ravel_multi_index(e, info.shape)) if info.shape else 0
+    for ielem in elems:
         data.append([tuple(numpy.asarray(a).ravel() for a in chunk) for chunk in f({'_b200_ielem': ielem})])
     last = None
     for basis in cands:
@@ -427,17 +498,18 @@ def _recognise(node):
 def _fit(node, info, basis, nodes, elems, data, gaxes, nc):
     nd = len(info.volume_shape())
     na = nd + 1
-    bases = adapter.bases1d_from_structured_basis(basis)
+    parent = getattr(basis, '_parent', basis)
+    bases = adapter.bases1d_from_structured_basis(parent)
+    renumber = numpy.asarray(basis._renumber, dtype=numpy.int64) if parent is not basis else None
     k = len(gaxes)
     face = info.face
     A_rows, rhs = [], []
     blocks = []
-    for e, chunks in zip(elems, data):
-        nidx = e
-        if face is not None:   # tangential index -> index of the adjacent volume element (in the grid / in the one-layer node array)
-            nidx = e[:face['dim']] + (0,) + e[face['dim']:]
-            e = e[:face['dim']] + (face['index'],) + e[face['dim']:]
+    for ielem, chunks in zip(elems, data):
+        e, nidx, xi, wq = info.element(ielem)
         ldofs = element_dofs(bases, e)
+        if renumber is not None:
+            ldofs = renumber[ldofs]
         lookup = {int(d): a for a, d in enumerate(ldofs)}
         ne = len(ldofs)
         T = numpy.zeros((ne, nc) * k)
@@ -458,8 +530,8 @@ def _fit(node, info, basis, nodes, elems, data, gaxes, nc):
                 where.append(numpy.array([lookup[int(i)] for i in idx[ax[0]]], dtype=int))
                 where.append(idx[ax[1]] if len(ax) == 2 else numpy.zeros(len(vals), dtype=int))
             numpy.add.at(T, tuple(where), vals)
-        phi, det, Jinv = element_jets(bases, nodes, e, info.coords, nidx)
-        wdet = info.weights * det
+        phi, det, Jinv = element_jets(bases, nodes, e, xi, nidx)
+        wdet = wq * det
         if face is not None:   # surface measure |det J| |J^-T e_k| (function.py:2291-2316 on a boundary sample)
             wdet = wdet * numpy.linalg.norm(Jinv[:, face['dim'], :], axis=1)
         if k == 2:
@@ -511,7 +583,9 @@ def _fit(node, info, basis, nodes, elems, data, gaxes, nc):
         grids[face['dim']] = numpy.array([lo])
         elem_ids = numpy.sort(numpy.ravel_multi_index(numpy.stack(numpy.meshgrid(*grids, indexing='ij'), -1).reshape(-1, nd).T, vshape)).astype(numpy.int64)
         spec.update(nodes=full, face=dict(face), elem_ids=elem_ids, xi=numpy.array(info.coords), weights=numpy.array(info.weights))
-    plan = dict(spec=spec, kind='matrix' if k == 2 else 'vector', coef=coef, nc=nc, nbasis=len(basis), gaxes=gaxes, keep=(basis, info), id=next(_COUNTER))
+    if info.elemset is not None:
+        spec.update(elemset=info.elemset, renumber=renumber, nbasis_new=len(basis))
+    plan = dict(spec=spec, kind='matrix' if k == 2 else 'vector', coef=coef, nc=nc, nbasis=len(basis), gaxes=gaxes, keep=(basis, info), id=next(_COUNTER))   # nbasis: functions of the (pruned) basis
     _PLANS[plan['id']] = plan
     return plan
 

@@ -21,6 +21,9 @@ variant = int(os.environ.get('ROWS_VARIANT', 0))
 ctx.set_option('rows_variant', variant)
 ctx.set_option('rows_split_forms', int(os.environ.get('ROWS_SPLIT_FORMS', 0)))
 ctx.set_option('rows_gpre', int(os.environ.get('ROWS_GPRE', 1)))
+if 'ROWS_SYM' in os.environ:
+    ctx.set_option('rows_sym', int(os.environ['ROWS_SYM']))
+ctx.set_option('rows_dbg', int(os.environ.get('ROWS_DBG', 0)))
 for nseg in [int(a) for a in sys.argv[3:]] or [0]:
     ctx.set_option('rows_nseg', nseg)
     for _ in range(2):

@@ -43,6 +43,12 @@ class OracleBackend:
             kw = dict(elem_ids=ids, qoff=numpy.arange(len(ids) + 1) * len(w), qcoords=numpy.tile(xi, (len(ids), 1)), qweights=numpy.tile(w, len(ids)),
                       face_dim=numpy.full(len(ids), spec['face']['dim'], dtype=numpy.int8))
             rules = points.tensor_gauss(len(b1), 2)
+        if 'elemset' in spec:   # trimmed / subset topology: kept elements, ragged points, pruned numbering
+            from nutils_b200 import points
+            kw = dict(spec['elemset'])
+            if spec['renumber'] is not None:
+                kw.update(renumber=spec['renumber'], nbasis_new=spec['nbasis_new'])
+            rules = points.tensor_gauss(len(b1), 2)
         return fem_oracle.Problem(tuple(b.nelems for b in b1), [b.degree for b in b1], [b.coeffs for b in b1], [b.setidx for b in b1], [b.start for b in b1],
                                   [b.ndofs for b in b1], [r[0] for r in rules], [r[1] for r in rules], spec['nodes'], ncomp=spec['ncomp'], **kw)
 
