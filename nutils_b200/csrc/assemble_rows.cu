@@ -133,7 +133,8 @@ struct RCfg {
   static constexpr int MAXL = 512;                                                       // layers per marching segment (sSet0)
   static constexpr int OFF_SET = OFF_ROW + 2 * SZ_ROW;
   static constexpr int OFF_IC = OFF_SET + MAXL / 2 + 2;                                  // [IPT][NT] 64-bit row-start factors of the S3 items
-  static constexpr int TOTAL = OFF_IC + IPT * NT;
+  static constexpr int IPTS = (T1 * T2 * ((WD * WD + 1) / 2) + NT - 1) / NT;              // items per thread of the symmetric variant
+  static constexpr int TOTAL = OFF_IC + (IPT > 2 * IPTS ? IPT : 2 * IPTS) * NT;
   static constexpr int NPF = (SZ_NOD + NT - 1) / NT;                                     // node values prefetched per thread
   static_assert(SZ_TB0 <= NT && 4 * NB <= NT, "layer tables are prefetched by one pass of the CTA");
 };
@@ -580,7 +581,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
   // its entries twice, as (i, j) and transposed as (j, i): half the S3 work and two thirds of the S2 work of the full variant
   constexpr int NSYM = (WD * WD + 1) / 2, N12S = T1 * T2 * NSYM;
   constexpr int IPT = SYM ? (N12S + NT - 1) / NT : C::IPT;
-  static_assert(!SYM || 2 * IPT <= C::IPT || IPT * NT * 2 <= C::IPT * NT, "the transposed row-start factors share the sIc array");
+  static_assert(!SYM || IPT == C::IPTS, "the transposed row-start factors share the sIc array");
   constexpr int NGK = FK ? 4 : 0;  // S2 output groups: DD DV VD VV [M]
   constexpr int NPARTS1 = ((C::SPLIT & 1) && FK) ? 3 : 1, NPARTS = ((C::SPLIT & 2) && FK) ? 2 : 1;  // term groups of S1 / S2 items
   static_assert(NQ % QC == 0, "the points q0 of a layer are processed in NQ/QC chunks");
@@ -699,6 +700,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
   int imeta[IPT];
   int imetaT[SYM ? IPT : 1];   // SYM: the same for the transposed entry (row (j1, j2), column (i1, i2)); bit 24 = it exists (off-diagonal pair)
   int t2idx[IPT];              // index of the pair in the T2 arrays
+  long long ibase[IPT], ibaseT[SYM ? IPT : 1];  // thread part of the slot of an entry on interior layers (see the store)
   long long* sIc = reinterpret_cast<long long*>(smem + C::OFF_IC);  // [IPT][NT] (SYM: [2 IPT][NT], direct then transposed)
 #pragma unroll
   for (int it = 0; it < IPT; it++) {
@@ -721,22 +723,30 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
     const bool v = inrange && i1 < nd1 && i2 < nd2 && j1 >= 0 && j1 < nd1 && j2 >= 0 && j2 < nd2;
     imeta[it] = (i1l * T2 + i2l) << 16;
     sIc[it * NT + tid] = 0;
+    ibase[it] = 0;
     if (SYM) {
       imetaT[it] = 0;
+      ibaseT[it] = 0;
       sIc[(IPT + it) * NT + tid] = 0;
     }
     if (v) {
       const int w1 = B.wid[1][i1], w2 = B.wid[2][i2];
-      sIc[it * NT + tid] = (long long)B.cum[1][i1] * B.W[2] + (long long)w1 * B.cum[2][i2];
-      imeta[it] |= (w1 * w2) | ((j1 - B.lo[1][i1]) * w2 + (j2 - B.lo[2][i2])) << 8 | 1 << 24 | (d1 == P && d2 == P ? 1 << 25 : 0);
+      const long long ic = (long long)B.cum[1][i1] * B.W[2] + (long long)w1 * B.cum[2][i2];
+      const int io = (j1 - B.lo[1][i1]) * w2 + (j2 - B.lo[2][i2]);
+      sIc[it * NT + tid] = ic;
+      ibase[it] = (long long)WD * ic + io;
+      imeta[it] |= (w1 * w2) | io << 8 | 1 << 24 | (d1 == P && d2 == P ? 1 << 25 : 0);
       if (SYM && !(d1 == P && d2 == P)) {
         const int v1 = B.wid[1][j1], v2 = B.wid[2][j2];
-        sIc[(IPT + it) * NT + tid] = (long long)B.cum[1][j1] * B.W[2] + (long long)v1 * B.cum[2][j2];
-        imetaT[it] = (v1 * v2) | ((i1 - B.lo[1][j1]) * v2 + (i2 - B.lo[2][j2])) << 8 | 1 << 24;
+        const long long icT = (long long)B.cum[1][j1] * B.W[2] + (long long)v1 * B.cum[2][j2];
+        const int ioT = (i1 - B.lo[1][j1]) * v2 + (i2 - B.lo[2][j2]);
+        sIc[(IPT + it) * NT + tid] = icT;
+        ibaseT[it] = (long long)WD * icT + ioT;
+        imetaT[it] = (v1 * v2) | ioT << 8 | 1 << 24;
       }
     }
   }
-  const long long W12 = B.W[1] * B.W[2];
+  const long long W12 = B.W[1] * B.W[2], WDW12 = WD * W12;
 
   double accK[IPT][NFORM][NB][NB], accM[IPT][NB][NB], accF[IPT][NB];
 #pragma unroll
@@ -768,6 +778,17 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
       const int e0 = ebeg + (s - 1) / NSUB, qc = ((s - 1) % NCH) * QC, form = ((s - 1) % NSUB) / NCH;
       const double* sTb0 = sTb0B + (e0 & 1) * C::SZ_TB0;
       const int* sRow = sRowB + (e0 & 1) * 4 * NB;
+      // the S2 results of the whole chunk are fetched before the first use (one exposed shared-memory latency per step, not QC)
+      constexpr bool PRE3 = IPT == 1 && P <= 2;
+      double xpre[PRE3 ? QC : 1][5];
+      if (PRE3 && (SYM ? (imeta[0] >> 24 & 1) : (tid < N12))) {
+#pragma unroll
+        for (int q0l = 0; q0l < QC; q0l++) {
+          const double* x = sT2 + q0l * C::T2QS + t2idx[0];
+          if (FK) { xpre[q0l][0] = x[0]; xpre[q0l][1] = x[N12P]; xpre[q0l][2] = x[2 * N12P]; xpre[q0l][3] = x[3 * N12P]; }
+          if (FM) xpre[q0l][4] = x[NGK * N12P];
+        }
+      }
 #pragma unroll
       for (int q0l = 0; q0l < QC; q0l++) {
         double va[NB], da[NB];
@@ -784,8 +805,13 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
           if (SYM ? (imeta[it] >> 24 & 1) : (tid + it * NT < N12)) {
             const double* x = sT2 + q0l * C::T2QS + t2idx[it];
             double gDD = 0., gDV = 0., gVD = 0., gVV = 0., gM = 0.;
-            if (FK) { gDD = x[0]; gDV = x[N12P]; gVD = x[2 * N12P]; gVV = x[3 * N12P]; }
-            if (FM) gM = x[NGK * N12P];
+            if (PRE3) {
+              if (FK) { gDD = xpre[q0l][0]; gDV = xpre[q0l][1]; gVD = xpre[q0l][2]; gVV = xpre[q0l][3]; }
+              if (FM) gM = xpre[q0l][4];
+            } else {
+              if (FK) { gDD = x[0]; gDV = x[N12P]; gVD = x[2 * N12P]; gVV = x[3 * N12P]; }
+              if (FM) gM = x[NGK * N12P];
+            }
 #pragma unroll
             for (int b = 0; b < NB; b++) {
               const double ud = fma(da[b], gDD, va[b] * gDV), uv = fma(da[b], gVD, va[b] * gVV), um = va[b] * gM;
@@ -820,18 +846,21 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
         } else
 #endif
         if (interior) {
+          // rows e0 .. e0+P have the full width WD, so cum0[e0 + a] = cum0[e0] + WD a: the slot of entry (a, b) is
+          // cum0[e0] W12 [layer, CTA-uniform] + ibase [thread, fixed] + a WD W12 [uniform] + (P - a + b) w12 [thread, small]
           if (imeta[it] >> 24 & 1) {
             const int iw12 = imeta[it] & 255;
-            const long long b12 = (long long)WD * sIc[it * NT + tid] + (imeta[it] >> 8 & 255);
+            const long long lbase = (long long)sRow[2] * W12;
+            double* __restrict__ pK = prm.valK + (lbase + ibase[it]);
+            double* __restrict__ pM = prm.valM + (lbase + ibase[it]);
 #pragma unroll
             for (int a = 0; a < NB; a++) {
-              const long long ra = (long long)sRow[a * 4 + 2] * W12 + b12;
 #pragma unroll
               for (int b = 0; b < NB; b++) {
                 if (a == 0 || b == 0) {
-                  const long long slot = ra + (P - a + b) * iw12;
-                  if (FK) prm.valK[slot] = accK[it][0][a][b];
-                  if (FM && prm.valM) prm.valM[slot] = accM[it][a][b] * prm.rho;
+                  const long long off = (long long)a * WDW12 + (P - a + b) * iw12;
+                  if (FK) pK[off] = accK[it][0][a][b];
+                  if (FM && prm.valM) pM[off] = accM[it][a][b] * prm.rho;
                 }
               }
             }
@@ -842,16 +871,16 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
             if (SYM && (imetaT[it] >> 24 & 1)) {
               // the transposed entries: row (e0 + b, j1, j2), column (e0 + a, i1, i2)
               const int iwT = imetaT[it] & 255;
-              const long long bT = (long long)WD * sIc[(IPT + it) * NT + tid] + (imetaT[it] >> 8 & 255);
+              double* __restrict__ qK = prm.valK + (lbase + ibaseT[it]);
+              double* __restrict__ qM = prm.valM + (lbase + ibaseT[it]);
 #pragma unroll
               for (int b = 0; b < NB; b++) {
-                const long long rb = (long long)sRow[b * 4 + 2] * W12 + bT;
 #pragma unroll
                 for (int a = 0; a < NB; a++) {
                   if (a == 0 || b == 0) {
-                    const long long slot = rb + (P - b + a) * iwT;
-                    if (FK) prm.valK[slot] = accK[it][0][a][b];
-                    if (FM && prm.valM) prm.valM[slot] = accM[it][a][b] * prm.rho;
+                    const long long off = (long long)b * WDW12 + (P - b + a) * iwT;
+                    if (FK) qK[off] = accK[it][0][a][b];
+                    if (FM && prm.valM) qM[off] = accM[it][a][b] * prm.rho;
                   }
                 }
               }
@@ -955,6 +984,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
             else s1_item_tab<C, FK, FM, 2, 3>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
           }
         }
+        if (NS1 <= NW) break;  // every warp has its one static item: no queue traffic
         __syncwarp();
         if (lane == 0) wi = atomicAdd(&sCnt[0], 1);
         wi = __shfl_sync(0xffffffffu, wi, 0);
@@ -1004,6 +1034,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
           }
         }
       }
+      if (GPRE && NS2 <= NW) break;  // one static S2 item per warp and no geometry items
       __syncwarp();
       if (lane == 0) wi = atomicAdd(&sCnt[1], 1);
       wi = __shfl_sync(0xffffffffu, wi, 0);
@@ -1414,6 +1445,11 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
     if (variant == 30) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 0>, true, true, 1, false, true>(ctx, prm);
     if (variant == 40) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 0>, true, true, 1, false, true, true>(ctx, prm);
     if (variant == 41) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 0>, true, true, 1, false, false, true>(ctx, prm);
+    if (variant == 42) return launch_rows_cfg<RCfg<2, 4, 4, 3, 512, 1>, true, true, 1, false, true, true>(ctx, prm);
+    if (variant == 43) return launch_rows_cfg<RCfg<2, 4, 4, 3, 384, 1>, true, true, 1, false, true, true>(ctx, prm);
+    if (variant == 44) return launch_rows_cfg<RCfg<2, 4, 4, 1, 256, 1, 7, 2>, true, true, 1, false, true, true>(ctx, prm);
+    if (variant == 45) return launch_rows_cfg<RCfg<2, 4, 4, 1, 256, 3, 7, 2>, true, true, 1, false, true, true>(ctx, prm);
+    if (variant == 46) return launch_rows_cfg<RCfg<2, 4, 4, 3, 512, 3>, true, true, 1, false, true, true>(ctx, prm);
     if (variant == 31) return launch_rows_cfg<RCfg<2, 4, 4, 3, 512, 1>, true, true, 1, false, true>(ctx, prm);
     if (variant == 20) return launch_rows_cfg<RCfg<2, 4, 4, 1, 256, 1, 7, 2>, true, true>(ctx, prm);
     if (variant == 21) return launch_rows_cfg<RCfg<2, 4, 4, 1, 256, 3, 7, 2>, true, true>(ctx, prm);
