@@ -700,7 +700,8 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
   int imeta[IPT];
   int imetaT[SYM ? IPT : 1];   // SYM: the same for the transposed entry (row (j1, j2), column (i1, i2)); bit 24 = it exists (off-diagonal pair)
   int t2idx[IPT];              // index of the pair in the T2 arrays
-  long long ibase[IPT], ibaseT[SYM ? IPT : 1];  // thread part of the slot of an entry on interior layers (see the store)
+  constexpr bool REGBASE = !VEC && (SYM || NT <= 256);
+  long long ibase[REGBASE ? IPT : 1], ibaseT[SYM ? IPT : 1];  // thread part of the slot of an entry on interior layers (see the store)
   long long* sIc = reinterpret_cast<long long*>(smem + C::OFF_IC);  // [IPT][NT] (SYM: [2 IPT][NT], direct then transposed)
 #pragma unroll
   for (int it = 0; it < IPT; it++) {
@@ -723,7 +724,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
     const bool v = inrange && i1 < nd1 && i2 < nd2 && j1 >= 0 && j1 < nd1 && j2 >= 0 && j2 < nd2;
     imeta[it] = (i1l * T2 + i2l) << 16;
     sIc[it * NT + tid] = 0;
-    ibase[it] = 0;
+    if (REGBASE) ibase[it] = 0;
     if (SYM) {
       imetaT[it] = 0;
       ibaseT[it] = 0;
@@ -734,7 +735,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
       const long long ic = (long long)B.cum[1][i1] * B.W[2] + (long long)w1 * B.cum[2][i2];
       const int io = (j1 - B.lo[1][i1]) * w2 + (j2 - B.lo[2][i2]);
       sIc[it * NT + tid] = ic;
-      ibase[it] = (long long)WD * ic + io;
+      if (REGBASE) ibase[it] = (long long)WD * ic + io;
       imeta[it] |= (w1 * w2) | io << 8 | 1 << 24 | (d1 == P && d2 == P ? 1 << 25 : 0);
       if (SYM && !(d1 == P && d2 == P)) {
         const int v1 = B.wid[1][j1], v2 = B.wid[2][j2];
@@ -779,7 +780,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
       const double* sTb0 = sTb0B + (e0 & 1) * C::SZ_TB0;
       const int* sRow = sRowB + (e0 & 1) * 4 * NB;
       // the S2 results of the whole chunk are fetched before the first use (one exposed shared-memory latency per step, not QC)
-      constexpr bool PRE3 = IPT == 1 && P <= 2;
+      constexpr bool PRE3 = IPT == 1 && P <= 2 && !VEC && NFORM == 1 && NT <= 256;  // register-rich configurations only
       double xpre[PRE3 ? QC : 1][5];
       if (PRE3 && (SYM ? (imeta[0] >> 24 & 1) : (tid < N12))) {
 #pragma unroll
@@ -848,11 +849,33 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
         if (interior) {
           // rows e0 .. e0+P have the full width WD, so cum0[e0 + a] = cum0[e0] + WD a: the slot of entry (a, b) is
           // cum0[e0] W12 [layer, CTA-uniform] + ibase [thread, fixed] + a WD W12 [uniform] + (P - a + b) w12 [thread, small]
-          if (imeta[it] >> 24 & 1) {
+          if (!REGBASE) {
+            // register-starved configurations (512 threads): the thread part of the slot comes from shared memory
+            if (imeta[it] >> 24 & 1) {
+              const int iw12 = imeta[it] & 255;
+              const long long b12 = (long long)WD * sIc[it * NT + tid] + (imeta[it] >> 8 & 255);
+#pragma unroll
+              for (int a = 0; a < NB; a++) {
+                const long long ra = (long long)sRow[a * 4 + 2] * W12 + b12;
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+                  if (a == 0 || b == 0) {
+                    const long long slot = ra + (P - a + b) * iw12;
+                    if (FK) prm.valK[slot] = accK[it][0][a][b];
+                    if (FM && prm.valM) prm.valM[slot] = accM[it][a][b] * prm.rho;
+                  }
+                }
+              }
+              if (prm.has_f && (imeta[it] >> 25 & 1)) {
+                const int il = imeta[it] >> 16 & 255;
+                prm.rhs[((long long)e0 * nd1 + i1lo + il / T2) * nd2 + i2lo + il % T2] = accF[it][0] * prm.vcoef;
+              }
+            }
+          } else if (imeta[it] >> 24 & 1) {
             const int iw12 = imeta[it] & 255;
             const long long lbase = (long long)sRow[2] * W12;
-            double* __restrict__ pK = prm.valK + (lbase + ibase[it]);
-            double* __restrict__ pM = prm.valM + (lbase + ibase[it]);
+            double* __restrict__ pK = prm.valK + (lbase + ibase[REGBASE ? it : 0]);
+            double* __restrict__ pM = prm.valM + (lbase + ibase[REGBASE ? it : 0]);
 #pragma unroll
             for (int a = 0; a < NB; a++) {
 #pragma unroll
@@ -984,7 +1007,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
             else s1_item_tab<C, FK, FM, 2, 3>(prm, sG, sTb2, sT1, sL1, i2, i2l, L, n2);
           }
         }
-        if (NS1 <= NW) break;  // every warp has its one static item: no queue traffic
+        if (P <= 2 && NS1 <= NW) break;  // every warp has its one static item: no queue traffic
         __syncwarp();
         if (lane == 0) wi = atomicAdd(&sCnt[0], 1);
         wi = __shfl_sync(0xffffffffu, wi, 0);
@@ -1034,7 +1057,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
           }
         }
       }
-      if (GPRE && NS2 <= NW) break;  // one static S2 item per warp and no geometry items
+      if (P <= 2 && GPRE && NS2 <= NW) break;  // one static S2 item per warp and no geometry items
       __syncwarp();
       if (lane == 0) wi = atomicAdd(&sCnt[1], 1);
       wi = __shfl_sync(0xffffffffu, wi, 0);
