@@ -31,6 +31,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "common.cuh"
@@ -50,6 +51,7 @@ struct RowParams {
   //   stiffness-like:  dm[e][x][y] = D[crow][1+x][e][1+y]  (any 3x3 block, not necessarily symmetric)
   //   mass-like:       rhoe[e]     = D[crow][0][e][0]
   int ncomp, crow;
+  int ecol0;  // column component of form 0 of a stiffness-like launch (forms = consecutive column components ecol0, ecol0 + 1, ..)
   double dm[3][9];
   double rhoe[3];
   // (value, derivative) of the local functions of the DOMINANT coefficient set of each dimension at the 1-D points,
@@ -134,7 +136,7 @@ struct RCfg {
   static constexpr int OFF_SET = OFF_ROW + 2 * SZ_ROW;
   static constexpr int OFF_IC = OFF_SET + MAXL / 2 + 2;                                  // [IPT][NT] 64-bit row-start factors of the S3 items
   static constexpr int IPTS = (T1 * T2 * ((WD * WD + 1) / 2) + NT - 1) / NT;              // items per thread of the symmetric variant
-  static constexpr int TOTAL = OFF_IC + (IPT > 2 * IPTS ? IPT : 2 * IPTS) * NT;
+  static constexpr int TOTAL = OFF_IC + (NG == 10 ? 2 * IPT : IPT > 2 * IPTS ? IPT : 2 * IPTS) * NT;  // NG == 10: off-diagonal blocks store every pair transposed as well
   static constexpr int NPF = (SZ_NOD + NT - 1) / NT;                                     // node values prefetched per thread
   static_assert(SZ_TB0 <= NT && 4 * NB <= NT, "layer tables are prefetched by one pass of the CTA");
 };
@@ -568,9 +570,13 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map
 //   phase X:  S3(l-1) + store(l-1)  [static: the thread owns its dof pair's accumulators]   ||   S1(l)   [queue]
 //   phase Y:  S2(l)  [queue]   ||   G(l+1)  [queue, 32 columns per item]
 // NFORM > 1: vector-valued stiffness-like launch, forms = column components, one pipeline step per (layer, form, chunk)
-template <class C, bool FK, bool FM, int NFORM, bool VEC, bool GPRE, bool SYM>
+// TRN (vector-valued spaces, off-diagonal block (crow, e > crow) of a SYMMETRIC form): every entry ((I, crow), (J, e)) is also stored
+// transposed as ((J, e), (I, crow)), so the blocks below the diagonal are never integrated
+template <class C, bool FK, bool FM, int NFORM, bool VEC, bool GPRE, bool SYM, bool TRN = false>
 __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __grid_constant__ CUtensorMap gmap) {
-  static_assert(!SYM || (!VEC && NFORM == 1 && C::NG == 7), "symmetric variant: scalar forms with a symmetric coefficient");
+  static_assert(!SYM || (NFORM == 1 && C::NG == 7), "symmetric variant: one form with a symmetric coefficient (scalar space, or a diagonal block of a vector-valued one)");
+  static_assert(!TRN || (VEC && !SYM && FK && !FM), "transposed stores: off-diagonal blocks of vector-valued stiffness-like forms");
+  constexpr bool TWO = SYM || TRN;  // the thread stores its entries twice: it keeps the slot data of the transposed entry as well
   static_assert(!GPRE || C::NG == 7 || C::NG == 10, "precomputed geometry: symmetric scalar forms or general forms");
   static_assert(NFORM == 1 || (FK && !FM && C::NG == 10), "several forms per launch: general stiffness-like forms only");
   constexpr int P = C::P, NB = C::NB, NQ = C::NQ, WD = C::WD, QC = C::QC, NT = C::NT, NW = C::NW;
@@ -582,6 +588,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
   constexpr int NSYM = (WD * WD + 1) / 2, N12S = T1 * T2 * NSYM;
   constexpr int IPT = SYM ? (N12S + NT - 1) / NT : C::IPT;
   static_assert(!SYM || IPT == C::IPTS, "the transposed row-start factors share the sIc array");
+  static_assert(!TRN || C::NG == 10, "sIc is sized for the transposed entries of general-coefficient configurations");
   constexpr int NGK = FK ? 4 : 0;  // S2 output groups: DD DV VD VV [M]
   constexpr int NPARTS1 = ((C::SPLIT & 1) && FK) ? 3 : 1, NPARTS = ((C::SPLIT & 2) && FK) ? 2 : 1;  // term groups of S1 / S2 items
   static_assert(NQ % QC == 0, "the points q0 of a layer are processed in NQ/QC chunks");
@@ -698,7 +705,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
   // packed per item: wid1*wid2 | position of (j1, j2) in that box << 8 | tile-local (i1, i2) << 16 | valid << 24 | diagonal << 25;
   // the 64-bit row-start factor lives in shared memory (read once per layer), the rest is re-derived when needed
   int imeta[IPT];
-  int imetaT[SYM ? IPT : 1];   // SYM: the same for the transposed entry (row (j1, j2), column (i1, i2)); bit 24 = it exists (off-diagonal pair)
+  int imetaT[TWO ? IPT : 1];   // SYM: the same for the transposed entry (row (j1, j2), column (i1, i2)); bit 24 = it exists (off-diagonal pair)
   int t2idx[IPT];              // index of the pair in the T2 arrays
   constexpr bool REGBASE = !VEC && (SYM || NT <= 256);
   long long ibase[REGBASE ? IPT : 1], ibaseT[SYM ? IPT : 1];  // thread part of the slot of an entry on interior layers (see the store)
@@ -725,9 +732,9 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
     imeta[it] = (i1l * T2 + i2l) << 16;
     sIc[it * NT + tid] = 0;
     if (REGBASE) ibase[it] = 0;
-    if (SYM) {
+    if (TWO) {
       imetaT[it] = 0;
-      ibaseT[it] = 0;
+      if (SYM) ibaseT[it] = 0;
       sIc[(IPT + it) * NT + tid] = 0;
     }
     if (v) {
@@ -737,12 +744,13 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
       sIc[it * NT + tid] = ic;
       if (REGBASE) ibase[it] = (long long)WD * ic + io;
       imeta[it] |= (w1 * w2) | io << 8 | 1 << 24 | (d1 == P && d2 == P ? 1 << 25 : 0);
-      if (SYM && !(d1 == P && d2 == P)) {
+      // SYM: the pair {i, i} holds both orders of its dimension-0 entries itself; TRN: its transposed entries lie in another block
+      if (TRN || (SYM && !(d1 == P && d2 == P))) {
         const int v1 = B.wid[1][j1], v2 = B.wid[2][j2];
         const long long icT = (long long)B.cum[1][j1] * B.W[2] + (long long)v1 * B.cum[2][j2];
         const int ioT = (i1 - B.lo[1][j1]) * v2 + (i2 - B.lo[2][j2]);
         sIc[(IPT + it) * NT + tid] = icT;
-        ibaseT[it] = (long long)WD * icT + ioT;
+        if (SYM) ibaseT[it] = (long long)WD * icT + ioT;
         imetaT[it] = (v1 * v2) | ioT << 8 | 1 << 24;
       }
     }
@@ -927,7 +935,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
                 const long long slot = rowslot + (long long)(e0 + b - rlo) * iw12 * nc;
                 if (FK) {
 #pragma unroll
-                  for (int f = 0; f < NFORM; f++) prm.valK[slot + f] = accK[it][f][a][b];
+                  for (int f = 0; f < NFORM; f++) prm.valK[slot + (VEC ? prm.ecol0 : 0) + f] = accK[it][f][a][b];
                 }
                 if (FM && prm.valM) {
                   if (nc == 1) prm.valM[slot] = accM[it][a][b] * prm.rho;
@@ -941,21 +949,27 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
               prm.rhs[(((long long)i0 * nd1 + i1lo + il / T2) * nd2 + i2lo + il % T2) * nc + prm.crow] = accF[it][a] * prm.vcoef;
             }
           }
-          if (SYM && (imetaT[it] >> 24 & 1)) {
+          if (TWO && (imetaT[it] >> 24 & 1)) {
+            // transposed entries: row (e0 + b, j1, j2) [component ecol0 + f], column (e0 + a, i1, i2) [component crow]
             const long long icT = sIc[(IPT + it) * NT + tid];
             const int iwT = imetaT[it] & 255, ioT = imetaT[it] >> 8 & 255;
+            const int nc = VEC ? prm.ncomp : 1;
 #pragma unroll
             for (int b = 0; b < NB; b++) {
               const int j0 = e0 + b;
               if (j0 < r0 || j0 >= r1) continue;
               const int rlo = sRow[b * 4], rwid = sRow[b * 4 + 1], rcum = sRow[b * 4 + 2];
-              const long long rowslot = (long long)rcum * W12 + (long long)rwid * icT + ioT;
 #pragma unroll
-              for (int a = 0; a < NB; a++) {
-                if (a == 0 || b == 0 || last) {
-                  const long long slot = rowslot + (long long)(e0 + a - rlo) * iwT;
-                  if (FK) prm.valK[slot] = accK[it][0][a][b];
-                  if (FM && prm.valM) prm.valM[slot] = accM[it][a][b] * prm.rho;
+              for (int f = 0; f < NFORM; f++) {
+                const long long rowslot = VEC ? (((long long)rcum * W12 + (long long)rwid * icT) * nc + (long long)(prm.ecol0 + f) * rwid * iwT) * nc + (long long)ioT * nc + prm.crow
+                                              : (long long)rcum * W12 + (long long)rwid * icT + ioT;
+#pragma unroll
+                for (int a = 0; a < NB; a++) {
+                  if (a == 0 || b == 0 || last) {
+                    const long long slot = rowslot + (long long)(e0 + a - rlo) * iwT * nc;
+                    if (FK) prm.valK[slot] = accK[it][f][a][b];
+                    if (FM && !VEC && prm.valM) prm.valM[slot] = accM[it][a][b] * prm.rho;
+                  }
                 }
               }
             }
@@ -1085,6 +1099,7 @@ struct GeomCache {
   bool valid = false;
   int box[4] = {0, 0, 0, 0};
   int g_ebeg = 0;
+  double kc[6] = {0, 0, 0, 0, 0, 0};  // the conductivity the array was computed with
   CUtensorMap map;
 };
 
@@ -1095,7 +1110,7 @@ int prepare_geometry(b2_ctx* ctx, RowParams& prm, CUtensorMap* map) {
   constexpr bool GEN = C::NG == 10;
   constexpr int NCOMP = C::NG * NFORM;
   GeomCache* gc = (GeomCache*)prm.host_gcache;
-  if (!GEN && gc && gc->valid && gc->box[0] == C::NQ1 && gc->box[1] == C::QC && gc->box[2] == C::NQ2 && gc->box[3] == C::NG) {
+  if (!GEN && gc && gc->valid && gc->box[0] == C::NQ1 && gc->box[1] == C::QC && gc->box[2] == C::NQ2 && gc->box[3] == C::NG && !memcmp(gc->kc, prm.kc, sizeof(prm.kc))) {
     *map = gc->map;
     prm.g_ebeg = gc->g_ebeg;
     return B2_OK;
@@ -1156,14 +1171,15 @@ int prepare_geometry(b2_ctx* ctx, RowParams& prm, CUtensorMap* map) {
     gc->valid = true;
     gc->box[0] = C::NQ1; gc->box[1] = C::QC; gc->box[2] = C::NQ2; gc->box[3] = C::NG;
     gc->g_ebeg = ebeg;
+    memcpy(gc->kc, prm.kc, sizeof(prm.kc));
     gc->map = *map;
   }
   return B2_OK;
 }
 
-template <class C, bool FK, bool FM, int NFORM = 1, bool VEC = false, bool GPRE = false, bool SYM = false>
+template <class C, bool FK, bool FM, int NFORM = 1, bool VEC = false, bool GPRE = false, bool SYM = false, bool TRN = false>
 int launch_rows_cfg(b2_ctx* ctx, RowParams& prm) {
-  auto kern = k_rows3d<C, FK, FM, NFORM, VEC, GPRE, SYM>;
+  auto kern = k_rows3d<C, FK, FM, NFORM, VEC, GPRE, SYM, TRN>;
   const size_t smem = sizeof(double) * C::TOTAL;
   static_assert(sizeof(double) * C::TOTAL <= 227 * 1024, "tile does not fit in shared memory");
   B2_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1224,14 +1240,26 @@ int launch_rows_scalar(b2_ctx* ctx, RowParams& prm) {
 // vector-valued launches: the precomputed geometry (10 components per column component) is available but NOT the default -- measured
 // on 96^3 p=2 elasticity it changes nothing (31.2 against 30.5 ms: with 16 warps the in-kernel geometry already runs in the shadow of
 // S2) and costs 5.7 GB; option "rows_gpre_vec" = 1 selects it
-template <class C, bool FK, bool FM, int NFORM>
+template <class C, bool FK, bool FM, int NFORM, bool TRN = false>
 int launch_rows_vec(b2_ctx* ctx, RowParams& prm) {
   const bool gpre = ctx->opts.count("rows_gpre_vec") && ctx->opts["rows_gpre_vec"] != 0;
   if (gpre) {
-    const int rc = launch_rows_cfg<C, FK, FM, NFORM, true, true>(ctx, prm);
+    const int rc = launch_rows_cfg<C, FK, FM, NFORM, true, true, false, TRN>(ctx, prm);
     if (rc != B2_ENOMEM) return rc;
   }
-  return launch_rows_cfg<C, FK, FM, NFORM, true, false>(ctx, prm);
+  return launch_rows_cfg<C, FK, FM, NFORM, true, false, false, TRN>(ctx, prm);
+}
+
+// diagonal block (crow, crow) of a symmetric vector-valued form: the symmetric scalar pipeline (precomputed geometry, unordered dof
+// pairs) writing into the slots of the vector-valued pattern
+template <class C>
+int launch_rows_vec_diag(b2_ctx* ctx, RowParams& prm) {
+  const bool gpre = !(ctx->opts.count("rows_gpre") && ctx->opts["rows_gpre"] == 0);
+  if (gpre) {
+    const int rc = launch_rows_cfg<C, true, false, 1, true, true, true>(ctx, prm);
+    if (rc != B2_ENOMEM) return rc;
+  }
+  return launch_rows_cfg<C, true, false, 1, true, false, true>(ctx, prm);
 }
 
 template <class C>
@@ -1249,6 +1277,7 @@ int launch_rows_vector(b2_ctx* ctx, RowParams& base, const FormView& F, const do
   if (P < 1 || P > 4) return B2_EUNSUPPORTED;
   if (F.nvec > 1 || (F.nmat == 0 && F.nvec == 0)) return B2_EUNSUPPORTED;
   int kind[B2_MAX_FORMS];  // 0 stiffness-like, 1 mass-like
+  bool symm[B2_MAX_FORMS];
   for (int m = 0; m < F.nmat; m++) {
     bool gg = false, mass = false, mixed = false;
     for (int c = 0; c < nc; c++)
@@ -1263,6 +1292,15 @@ int launch_rows_vector(b2_ctx* ctx, RowParams& base, const FormView& F, const do
           }
     if (mixed || (gg && mass) || (!gg && !mass)) return B2_EUNSUPPORTED;
     kind[m] = gg ? 0 : 1;
+    // D[c][x][e][y] == D[e][y][c][x]: the matrix is symmetric (elasticity and every form that derives from an energy)
+    symm[m] = gg && !(ctx->opts.count("rows_vecsym") && ctx->opts["rows_vecsym"] == 0);
+    double dmax = 0.;
+    for (int t = 0; t < nc * na * nc * na; t++) dmax = std::max(dmax, std::fabs(D_host[m][t]));
+    for (int c = 0; c < nc && symm[m]; c++)
+      for (int e = 0; e < nc; e++)
+        for (int x = 1; x < na; x++)
+          for (int y = 1; y < na; y++)
+            if (std::fabs(D_host[m][((c * na + x) * nc + e) * na + y] - D_host[m][((e * na + y) * nc + c) * na + x]) > 4e-16 * dmax) symm[m] = false;
   }
   if (F.nvec)
     for (int c = 0; c < nc; c++)
@@ -1281,7 +1319,42 @@ int launch_rows_vector(b2_ctx* ctx, RowParams& base, const FormView& F, const do
         want_f = false;
       }
       int rc;
-      if (m < F.nmat && kind[m] == 0) {
+      if (m < F.nmat && kind[m] == 0 && symm[m]) {
+        // symmetric form: the diagonal block (c, c) by the symmetric scalar pipeline, the blocks (c, e > c) by the general one with every
+        // entry stored transposed into block (e, c) as well -- 6 of the 9 blocks are integrated, 3 of them at the symmetric cost
+        auto blk = [&](int e, int x, int y) { return D_host[m][((c * na + 1 + x) * nc + e) * na + 1 + y]; };
+        RowParams pd = prm;
+        pd.ecol0 = c;
+        pd.valK = F.values[m];
+        const double kc[6] = {blk(c, 0, 0), blk(c, 0, 1), blk(c, 0, 2), blk(c, 1, 1), blk(c, 1, 2), blk(c, 2, 2)};
+        for (int t = 0; t < 6; t++) pd.kc[t] = kc[t];
+        pd.iso = kc[1] == 0. && kc[2] == 0. && kc[4] == 0. && kc[0] == kc[3] && kc[0] == kc[5];
+        rc = P == 1   ? launch_rows_vec_diag<RCfg<1, 9, 9, 2, 512, 0>>(ctx, pd)
+             : P == 2 ? launch_rows_vec_diag<RCfg<2, 4, 4, 3, 256, 0>>(ctx, pd)
+             : P == 3 ? launch_rows_vec_diag<RCfg<3, 3, 3, 2, 256, 3>>(ctx, pd)
+                      : launch_rows_vec_diag<RCfg<4, 2, 3, 1, 256, 3>>(ctx, pd);
+        const int nf = nc - 1 - c;  // column components e > c
+        if (rc == B2_OK && nf > 0) {
+          RowParams po = prm;
+          po.has_f = 0;
+          po.ecol0 = c + 1;
+          po.valK = F.values[m];
+          for (int f = 0; f < nf; f++)
+            for (int x = 0; x < 3; x++)
+              for (int y = 0; y < 3; y++) po.dm[f][x * 3 + y] = blk(c + 1 + f, x, y);
+          if (P <= 2) {
+            if (nf == 2) rc = P == 1 ? launch_rows_vec<RCfg<1, 8, 8, 2, 512, 0, 10>, true, false, 2, true>(ctx, po) : launch_rows_vec<RCfg<2, 4, 4, 3, 512, 1, 10>, true, false, 2, true>(ctx, po);
+            else rc = P == 1 ? launch_rows_vec<RCfg<1, 8, 8, 2, 512, 0, 10>, true, false, 1, true>(ctx, po) : launch_rows_vec<RCfg<2, 4, 4, 3, 512, 1, 10>, true, false, 1, true>(ctx, po);
+          } else {
+            for (int f = 0; f < nf && rc == B2_OK; f++) {
+              RowParams pe = po;
+              for (int t = 0; t < 9; t++) pe.dm[0][t] = po.dm[f][t];
+              pe.ecol0 = c + 1 + f;
+              rc = P == 3 ? launch_rows_vec<RCfg<3, 3, 3, 2, 256, 3, 10>, true, false, 1, true>(ctx, pe) : launch_rows_vec<RCfg<4, 2, 2, 1, 256, 3, 10>, true, false, 1, true>(ctx, pe);
+            }
+          }
+        }
+      } else if (m < F.nmat && kind[m] == 0) {
         for (int e = 0; e < nc; e++)
           for (int x = 0; x < 3; x++)
             for (int y = 0; y < 3; y++) prm.dm[e][x * 3 + y] = D_host[m][((c * na + 1 + x) * nc + e) * na + 1 + y];
@@ -1296,7 +1369,7 @@ int launch_rows_vector(b2_ctx* ctx, RowParams& base, const FormView& F, const do
           for (int e = 0; e < nc && rc == B2_OK; e++) {
             RowParams pe = prm;
             for (int t = 0; t < 9; t++) pe.dm[0][t] = prm.dm[e][t];
-            pe.valK = F.values[m] + e;
+            pe.ecol0 = e;
             if (e) pe.has_f = 0;
             rc = P == 3 ? launch_rows_vec<RCfg<3, 3, 3, 2, 256, 3, 10>, true, false, 1>(ctx, pe) : launch_rows_vec<RCfg<4, 2, 2, 1, 256, 3, 10>, true, false, 1>(ctx, pe);
           }
