@@ -210,6 +210,58 @@ def test_rows_plane_ranges(ctx, case, nseg):
     assert util.relerr(rhs[0].cpu().numpy(), vecs[0]) <= TOL
 
 
+VEC_CASES = [dict(nelems=(6, 7, 5), degree=2), dict(nelems=(9, 4, 9), degree=1), dict(nelems=(1, 1, 1), degree=2), dict(nelems=(2, 1, 3), degree=1),
+             dict(nelems=(5, 4, 4), degree=3), dict(nelems=(4, 3, 3), degree=4), dict(nelems=(1, 1, 1), degree=4), dict(nelems=(11, 5, 6), degree=2)]
+
+
+@pytest.mark.parametrize('form', ['elasticity', 'symmetric', 'general'])
+@pytest.mark.parametrize('case', VEC_CASES, ids=lambda c: 'x'.join(map(str, c['nelems'])) + 'p{}'.format(c['degree']))
+def test_rows_vector_blocks(ctx, case, form):
+    '''Vector-valued (3-component) stiffness-like forms through the owner-computes kernel ITSELF (context option kernel = 2: the
+    specialised kernel or an error; one matrix form per call, as the kernel takes at most two).  Symmetric forms (D[c][x][e][y] =
+    D[e][y][c][x]: elasticity, a random symmetrised coupling) are integrated by blocks -- diagonal blocks on the symmetric scalar
+    pipeline, blocks above the diagonal with transposed stores, blocks below never; a non-symmetric coupling takes all nine
+    blocks.  Against the oracle, over disjoint plane ranges written into one poisoned array, and symmetric route against the
+    nine-block route (rows_vecsym = 0).'''
+    import torch
+    prob = _random_problem(seed=hash(str(case) + form) % 2**31, ncomp=3, **case)
+    rng = numpy.random.RandomState(5)
+    Dgg = numpy.zeros((3, 4, 3, 4))
+    Dgg[:, 1:, :, 1:] = rng.rand(3, 3, 3, 3) - .5
+    D = {'elasticity': engine.form_elasticity(3, 1.3, .7), 'symmetric': Dgg + Dgg.transpose(2, 3, 0, 1) + 2 * engine.form_elasticity(3, .1, 1.), 'general': Dgg}[form]
+    Cs = [engine.form_load(3, 3, f=[.3, -1.1, 2.])]
+    mats, vecs = c_oracle.assemble(prob, [('generic', D)], [('generic', C) for C in Cs])
+    plan = _plan(ctx, prob)
+    rowptr, _ = plan.csr_pattern()
+    ndof0 = prob.ndofs_d[0]
+    dev = torch.device('cuda', 0)
+    poison = -7.25
+    cuts = sorted(set([0, ndof0 // 3, ndof0 // 3 + 1, ndof0]))
+    per_plane = plan.ndofs // ndof0
+    results = []
+    ctx.set_option('kernel', 2)
+    try:
+        for vecsym in (1, 0):
+            ctx.set_option('rows_vecsym', vecsym)
+            vals = [torch.full((plan.nnz,), poison, dtype=torch.float64, device=dev)]
+            rhs = [torch.full((plan.ndofs,), poison, dtype=torch.float64, device=dev)]
+            for i, (p0, p1) in enumerate(zip(cuts[:-1], cuts[1:])):
+                plan.assemble_rows_device([D], Cs, vals, rhs, plane_range=(p0, p1))
+                ctx.synchronize()
+                if i == 0 and p1 < ndof0:
+                    assert bool((vals[0][int(rowptr[p1 * per_plane]):] == poison).all())
+                    assert bool((rhs[0][p1 * per_plane:] == poison).all())
+            v = vals[0].cpu().numpy()
+            assert util.relerr(v, mats[0][0]) <= TOL
+            assert util.rowsum_relerr(v, mats[0][0], rowptr) <= TOL
+            assert util.relerr(rhs[0].cpu().numpy(), vecs[0]) <= TOL
+            results.append(v)
+    finally:
+        ctx.set_option('kernel', 0)
+        ctx.set_option('rows_vecsym', 1)
+    assert util.relerr(results[0], results[1]) <= TOL
+
+
 def test_rows_nonuniform_knots_and_long_march(ctx):
     '''Graded knot vectors give every element its own coefficient set (the kernel's table-driven variants instead of the
     constant-bank fast path), and 700 element layers exceed one marching segment (512 layers), forcing a split.'''
