@@ -576,6 +576,7 @@ template <class C, bool FK, bool FM, int NFORM, bool VEC, bool GPRE, bool SYM, b
 __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __grid_constant__ CUtensorMap gmap) {
   static_assert(!SYM || (NFORM == 1 && C::NG == 7), "symmetric variant: one form with a symmetric coefficient (scalar space, or a diagonal block of a vector-valued one)");
   static_assert(!TRN || (VEC && !SYM && FK && !FM), "transposed stores: off-diagonal blocks of vector-valued stiffness-like forms");
+  constexpr int NCV = VEC ? 3 : 1;  // components of a vector-valued space (the launcher admits 3 only)
   constexpr bool TWO = SYM || TRN;  // the thread stores its entries twice: it keeps the slot data of the transposed entry as well
   static_assert(!GPRE || C::NG == 7 || C::NG == 10, "precomputed geometry: symmetric scalar forms or general forms");
   static_assert(NFORM == 1 || (FK && !FM && C::NG == 10), "several forms per launch: general stiffness-like forms only");
@@ -707,8 +708,8 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
   int imeta[IPT];
   int imetaT[TWO ? IPT : 1];   // SYM: the same for the transposed entry (row (j1, j2), column (i1, i2)); bit 24 = it exists (off-diagonal pair)
   int t2idx[IPT];              // index of the pair in the T2 arrays
-  constexpr bool REGBASE = !VEC && (SYM || NT <= 256);
-  long long ibase[REGBASE ? IPT : 1], ibaseT[SYM ? IPT : 1];  // thread part of the slot of an entry on interior layers (see the store)
+  constexpr bool REGBASE = SYM || NT <= 256;
+  long long ibase[REGBASE ? IPT : 1], ibaseT[TWO && REGBASE ? IPT : 1];  // thread part of the slot of an entry on interior layers (see the store)
   long long* sIc = reinterpret_cast<long long*>(smem + C::OFF_IC);  // [IPT][NT] (SYM: [2 IPT][NT], direct then transposed)
 #pragma unroll
   for (int it = 0; it < IPT; it++) {
@@ -734,7 +735,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
     if (REGBASE) ibase[it] = 0;
     if (TWO) {
       imetaT[it] = 0;
-      if (SYM) ibaseT[it] = 0;
+      if (REGBASE) ibaseT[it] = 0;
       sIc[(IPT + it) * NT + tid] = 0;
     }
     if (v) {
@@ -742,7 +743,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
       const long long ic = (long long)B.cum[1][i1] * B.W[2] + (long long)w1 * B.cum[2][i2];
       const int io = (j1 - B.lo[1][i1]) * w2 + (j2 - B.lo[2][i2]);
       sIc[it * NT + tid] = ic;
-      if (REGBASE) ibase[it] = (long long)WD * ic + io;
+      if (REGBASE) ibase[it] = VEC ? ((long long)WD * ic * NCV + (long long)prm.crow * WD * (w1 * w2)) * NCV + io * NCV + prm.ecol0 : (long long)WD * ic + io;
       imeta[it] |= (w1 * w2) | io << 8 | 1 << 24 | (d1 == P && d2 == P ? 1 << 25 : 0);
       // SYM: the pair {i, i} holds both orders of its dimension-0 entries itself; TRN: its transposed entries lie in another block
       if (TRN || (SYM && !(d1 == P && d2 == P))) {
@@ -750,12 +751,12 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
         const long long icT = (long long)B.cum[1][j1] * B.W[2] + (long long)v1 * B.cum[2][j2];
         const int ioT = (i1 - B.lo[1][j1]) * v2 + (i2 - B.lo[2][j2]);
         sIc[(IPT + it) * NT + tid] = icT;
-        if (SYM) ibaseT[it] = (long long)WD * icT + ioT;
+        if (REGBASE) ibaseT[it] = VEC ? ((long long)WD * icT * NCV + (long long)prm.ecol0 * WD * (v1 * v2)) * NCV + ioT * NCV + prm.crow : (long long)WD * icT + ioT;
         imetaT[it] = (v1 * v2) | ioT << 8 | 1 << 24;
       }
     }
   }
-  const long long W12 = B.W[1] * B.W[2], WDW12 = WD * W12;
+  const long long W12 = B.W[1] * B.W[2], W12N = W12 * (NCV * NCV), WDW12 = WD * W12N;
 
   double accK[IPT][NFORM][NB][NB], accM[IPT][NB][NB], accF[IPT][NB];
 #pragma unroll
@@ -847,7 +848,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
       const bool last = e0 == n0 - 1;
       // interior layer of a scalar space (the common case): all P+1 rows have the full width 2P+1, their first coupled dof is
       // i0-P and they all lie in the planes of this launch -- the slot arithmetic collapses to one 64-bit base per row
-      const bool interior = !VEC && e0 >= P && e0 <= n0 - 1 - P && e0 >= r0 && e0 + P < r1;
+      const bool interior = (!VEC || (REGBASE && !FM)) && e0 >= P && e0 <= n0 - 1 - P && e0 >= r0 && e0 + P < r1;
 #pragma unroll
       for (int it = 0; it < IPT; it++) {
 #ifdef B2_EXPERIMENT
@@ -880,8 +881,10 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
               }
             }
           } else if (imeta[it] >> 24 & 1) {
-            const int iw12 = imeta[it] & 255;
-            const long long lbase = (long long)sRow[2] * W12;
+            // (vector-valued spaces: W12 and w12 carry the factors ncomp^2 and ncomp of the component-interleaved slots, the
+            // component offsets are part of ibase; form f = column component ecol0 + f)
+            const int iw12 = (imeta[it] & 255) * NCV;
+            const long long lbase = (long long)sRow[2] * W12N;
             double* __restrict__ pK = prm.valK + (lbase + ibase[REGBASE ? it : 0]);
             double* __restrict__ pM = prm.valM + (lbase + ibase[REGBASE ? it : 0]);
 #pragma unroll
@@ -890,28 +893,34 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
               for (int b = 0; b < NB; b++) {
                 if (a == 0 || b == 0) {
                   const long long off = (long long)a * WDW12 + (P - a + b) * iw12;
-                  if (FK) pK[off] = accK[it][0][a][b];
-                  if (FM && prm.valM) pM[off] = accM[it][a][b] * prm.rho;
+                  if (FK) {
+#pragma unroll
+                    for (int f = 0; f < NFORM; f++) pK[off + f] = accK[it][f][a][b];
+                  }
+                  if (FM && !VEC && prm.valM) pM[off] = accM[it][a][b] * prm.rho;
                 }
               }
             }
             if (prm.has_f && (imeta[it] >> 25 & 1)) {
               const int il = imeta[it] >> 16 & 255;
-              prm.rhs[((long long)e0 * nd1 + i1lo + il / T2) * nd2 + i2lo + il % T2] = accF[it][0] * prm.vcoef;
+              prm.rhs[(((long long)e0 * nd1 + i1lo + il / T2) * nd2 + i2lo + il % T2) * NCV + (VEC ? prm.crow : 0)] = accF[it][0] * prm.vcoef;
             }
-            if (SYM && (imetaT[it] >> 24 & 1)) {
-              // the transposed entries: row (e0 + b, j1, j2), column (e0 + a, i1, i2)
-              const int iwT = imetaT[it] & 255;
-              double* __restrict__ qK = prm.valK + (lbase + ibaseT[it]);
-              double* __restrict__ qM = prm.valM + (lbase + ibaseT[it]);
+            if (TWO && (imetaT[it] >> 24 & 1)) {
+              // the transposed entries: row (e0 + b, j1, j2) [component ecol0 + f], column (e0 + a, i1, i2) [component crow]
+              const int iwT = (imetaT[it] & 255) * NCV;
+              double* __restrict__ qK = prm.valK + (lbase + ibaseT[REGBASE ? it : 0]);
+              double* __restrict__ qM = prm.valM + (lbase + ibaseT[REGBASE ? it : 0]);
 #pragma unroll
               for (int b = 0; b < NB; b++) {
 #pragma unroll
                 for (int a = 0; a < NB; a++) {
                   if (a == 0 || b == 0) {
                     const long long off = (long long)b * WDW12 + (P - b + a) * iwT;
-                    if (FK) qK[off] = accK[it][0][a][b];
-                    if (FM && prm.valM) qM[off] = accM[it][a][b] * prm.rho;
+                    if (FK) {
+#pragma unroll
+                      for (int f = 0; f < NFORM; f++) qK[off + (long long)f * WD * iwT] = accK[it][f][a][b];
+                    }
+                    if (FM && !VEC && prm.valM) qM[off] = accM[it][a][b] * prm.rho;
                   }
                 }
               }
@@ -1342,7 +1351,16 @@ int launch_rows_vector(b2_ctx* ctx, RowParams& base, const FormView& F, const do
           for (int f = 0; f < nf; f++)
             for (int x = 0; x < 3; x++)
               for (int y = 0; y < 3; y++) po.dm[f][x * 3 + y] = blk(c + 1 + f, x, y);
-          if (P <= 2) {
+          const int64_t ovar = ctx->opts.count("rows_vec_offdiag") ? ctx->opts["rows_vec_offdiag"] : 0;
+          if (P == 2 && ovar != 2) {
+            // one launch per block on the register-rich 256-thread configuration
+            for (int f = 0; f < nf && rc == B2_OK; f++) {
+              RowParams pe = po;
+              for (int t = 0; t < 9; t++) pe.dm[0][t] = po.dm[f][t];
+              pe.ecol0 = c + 1 + f;
+              rc = launch_rows_vec<RCfg<2, 4, 4, 3, 256, 0, 10>, true, false, 1, true>(ctx, pe);
+            }
+          } else if (P <= 2) {
             if (nf == 2) rc = P == 1 ? launch_rows_vec<RCfg<1, 8, 8, 2, 512, 0, 10>, true, false, 2, true>(ctx, po) : launch_rows_vec<RCfg<2, 4, 4, 3, 512, 1, 10>, true, false, 2, true>(ctx, po);
             else rc = P == 1 ? launch_rows_vec<RCfg<1, 8, 8, 2, 512, 0, 10>, true, false, 1, true>(ctx, po) : launch_rows_vec<RCfg<2, 4, 4, 3, 512, 1, 10>, true, false, 1, true>(ctx, po);
           } else {

@@ -10,7 +10,7 @@ ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 dev = torch.device('cuda', 0)
 ctx.set_option('rows_variant', int(os.environ.get('ROWS_VARIANT', 0)))
 ctx.set_option('rows_dbg', int(os.environ.get('ROWS_DBG', 0)))
-for k in ('rows_gpre_vec', 'rows_sym', 'rows_vecsym'):
+for k in ('rows_gpre_vec', 'rows_sym', 'rows_vecsym', 'rows_vec_offdiag'):
     if k.upper() in os.environ:
         ctx.set_option(k, int(os.environ[k.upper()]))
 cases = [dict(n=64, p=1), dict(n=64, p=2), dict(n=48, p=3), dict(n=32, p=4), dict(n=32, p=2, ncomp=3), dict(n=48, p=2, ncomp=3), dict(n=24, p=3, ncomp=3)]
