@@ -1236,9 +1236,10 @@ template <class C, bool FK, bool FM>
 int launch_rows_scalar(b2_ctx* ctx, RowParams& prm) {
   const bool gpre = !(ctx->opts.count("rows_gpre") && ctx->opts["rows_gpre"] == 0);
   // the coefficient of a scalar form is symmetric (checked by the caller).  Measured (profiles/r02/README.md): the symmetric variant
-  // wins at degree 2 (-1 %: half the S3 and two thirds of the S2 work against scattered transposed stores) and at degree 4 (K and M in
-  // one launch: -30 %), and loses 2 % at degree 3; degree 1 is indifferent
-  const bool sym = ctx->opts.count("rows_sym") ? ctx->opts["rows_sym"] != 0 : (C::P == 2 || C::P == 4);
+  // (half the S3 and two thirds of the S2 work against scattered transposed stores) wins at degree 4 (K and M in one launch: -30 %);
+  // at degree 2 the full variant is 3 % faster since its interior store takes the slot bases from registers (4.95 against 5.09 ms
+  // at 128^3), at degree 3 2 %; degree 1 is indifferent
+  const bool sym = ctx->opts.count("rows_sym") ? ctx->opts["rows_sym"] != 0 : C::P == 4;
   if (gpre) {
     const int rc = sym ? launch_rows_cfg<C, FK, FM, 1, false, true, true>(ctx, prm) : launch_rows_cfg<C, FK, FM, 1, false, true, false>(ctx, prm);
     if (rc != B2_ENOMEM) return rc;
