@@ -473,6 +473,9 @@ class Structured:
         # algorithmic bytes of this rank: 8 B per stored value and rhs entry + 24 B per node of the layers it integrates
         self.alg_bytes = 8. * (len(self.Ds) * self.nvalues + len(self.Cs) * self.nrows + 3 * (self.nlayers + 1) * (self.shape[1] + 1) * (self.shape[2] + 1))
         self.kernel = ('k_rows3d (owner-computes tile kernel; its geometry comes from k_geom3d by TMA)' if self.rows_path else 'k_assemble_scalar3d (element scatter; zero-fill and exchange excluded)')
+        if self.elast and self.rows_path:
+            self.kernel = ('k_rows3d, 6 of the 9 component blocks of the symmetric form: 3 diagonal blocks on the symmetric scalar pipeline (k_geom3d + TMA), '
+                           '3 blocks above the diagonal on the general pipeline with transposed stores; figure = all launches of a step together')
         self.ncu_key = '{}_n{}_p{}'.format(args.workload, args.n, p) if (world == 1 and self.rows_path) else None
 
     def sums(self):
@@ -706,7 +709,7 @@ def run_b200(args):
     # context recording the maximum single-launch time instead of the sum
     dominant_ms = dominant_kernel_time(ctx, W, torch) if kernel_launches > args.steps else kernel_ms / max(args.steps, 1)
     if getattr(W, 'elast', False):
-        dominant_ms = kernel_ms / max(args.steps, 1)   # vector-valued: one launch of the SAME kernel per row component, each writes a third of the rows
+        dominant_ms = kernel_ms / max(args.steps, 1)   # vector-valued: the launches of the tile kernel per component block each write a part of the rows: taken together
     if world > 1:
         t = torch.tensor([ms, kernel_ms, dominant_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

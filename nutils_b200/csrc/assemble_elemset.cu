@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512, TCMAX == 4 ? 4 : 1) k_
   double* sW = sJ + qc * JS;                            // [qc][NA]  W, dW/dxi (rational functions)
   double* sK = sW + qc * NA;                            // [qc][2 B2_MAX_FORMS] pointwise coefficient of every form (1 if none)
   double* sB = sK + qc * 2 * B2_MAX_FORMS;              // [qc][nb][NA]
+  sB += (reinterpret_cast<unsigned long long>(sB) >> 3) & 1;  // 16-byte aligned (the launch reserves the slack): 3-D entries move as 128-bit vectors
   double* sV = sB + qc * nb * NA;                       // [nvec][ne]
   long long* sRow = reinterpret_cast<long long*>(sV + B2_MAX_FORMS * ne);  // [nb] first slot of the basis row
   int* sLen = reinterpret_cast<int*>(sRow + nb);        // [nb] columns of the basis row
@@ -454,13 +455,22 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512, TCMAX == 4 ? 4 : 1) k_
             for (int k = 0; k < DIM; k++) dxi[k] = (dxi[k] - N * sW[ql * NA + 1 + k]) * rW;
           }
           double* b = sB + (ql * nb + a) * NA;
-          b[0] = N;
+          double gph[DIM];
 #pragma unroll
           for (int i = 0; i < DIM; i++) {
             double s = 0.;
 #pragma unroll
             for (int k = 0; k < DIM; k++) s += dxi[k] * sJ[ql * JS + k * DIM + i];
-            b[1 + i] = s;
+            gph[i] = s;
+          }
+          if constexpr (NA == 4) {
+            // one entry = 32 aligned bytes: two 128-bit stores (four 64-bit stores at stride 32 bytes across the lanes are an 8-way bank conflict)
+            reinterpret_cast<double2*>(b)[0] = make_double2(N, gph[0]);
+            reinterpret_cast<double2*>(b)[1] = make_double2(gph[1], gph[2]);
+          } else {
+            b[0] = N;
+#pragma unroll
+            for (int i = 0; i < DIM; i++) b[1 + i] = gph[i];
           }
         }
         __syncthreads();
@@ -546,8 +556,13 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512, TCMAX == 4 ? 4 : 1) k_
                       if (arow_ok && ql < nqc) {
                         const double* Ba = sB + (ql * nb + arow) * NA;
                         double t = 0.;
+                        if constexpr (NA == 4) {
+                          const double2 b01 = reinterpret_cast<const double2*>(Ba)[0], b23 = reinterpret_cast<const double2*>(Ba)[1];
+                          t = fma(b23.y, dcol[3], fma(b23.x, dcol[2], fma(b01.y, dcol[1], b01.x * dcol[0])));
+                        } else {
 #pragma unroll
-                        for (int x = 0; x < NA; x++) t = fma(Ba[x], dcol[x], t);
+                          for (int x = 0; x < NA; x++) t = fma(Ba[x], dcol[x], t);
+                        }
                         af[u] = t * sJ[ql * JS + DIM * DIM] * sK[ql * 2 * B2_MAX_FORMS + fm];
                       }
                     }
@@ -625,19 +640,24 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512, TCMAX == 4 ? 4 : 1) k_
         }
         }
         // linear forms: thread r owns sV[.][r]
-        if (pass0 == 0) {
-          for (int r = tid; r < ne; r += T) {
+        if (pass0 == 0 && P.F.nvec) {
+          // the points are dealt to T / ne groups of threads (an element with few functions would leave most warps waiting at the
+          // barrier); partial sums meet in shared memory
+          const int nparts = max(1, T / ne);
+          for (int it = tid; it < ne * nparts; it += T) {
+            const int r = it % ne, part = it / ne;
             const int a = r / nc, ci = r % nc;
             for (int v = 0; v < P.F.nvec; v++) {
               double s = 0.;
-              for (int ql = 0; ql < nqc; ql++) {
+              for (int ql = part; ql < nqc; ql += nparts) {
                 const double* Ba = sB + (ql * nb + a) * NA;
                 double t = 0.;
 #pragma unroll
                 for (int x = 0; x < NA; x++) t += P.F.vcoef[(v * nc + ci) * NA + x] * Ba[x];
                 s += t * sJ[ql * JS + DIM * DIM] * sK[ql * 2 * B2_MAX_FORMS + B2_MAX_FORMS + v];
               }
-              sV[v * ne + r] += s;
+              if (nparts > 1) atomicAdd(&sV[v * ne + r], s);
+              else sV[v * ne + r] += s;
             }
           }
         }
@@ -653,6 +673,13 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512, TCMAX == 4 ? 4 : 1) k_
           if (In >= 0) {
             const int len = sLen[a];
             const int* cols = E.colidx_b + sRow[a];
+            // a row that kept its whole box of (2p+1)^DIM coupled functions (the rule away from trimmed cells and domain boundaries)
+            // holds function b at the analytic position sum_d (b_d - a_d + p_d) stride_d: one load confirms it, the bisection
+            // (log2(len) DEPENDENT global loads) is the fallback
+            int full = 1;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) full *= 2 * B.p[d] + 1;
+            const int mia = sMi[a];
 #pragma unroll
             for (int tc = 0; tc < TCMAX; tc++) {
               if (tc < ntr) {
@@ -661,11 +688,22 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512, TCMAX == 4 ? 4 : 1) k_
                   const int b = tc * 8 + (lane & 3) * 2 + i;
                   const int Jn = b < nb ? sDof[b] : -1;
                   if (Jn < 0) continue;
-                  int lo = 0, hi = len;
-                  while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (cols[mid] < Jn) lo = mid + 1;
-                    else hi = mid;
+                  int lo = -1;
+                  if (len == full) {
+                    const int mib = sMi[b];
+                    int pos = 0;
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) pos = pos * (2 * B.p[d] + 1) + ((mib >> (8 * d)) & 255) - ((mia >> (8 * d)) & 255) + B.p[d];
+                    if (cols[pos] == Jn) lo = pos;
+                  }
+                  if (lo < 0) {
+                    int hi = len;
+                    lo = 0;
+                    while (lo < hi) {
+                      const int mid = (lo + hi) >> 1;
+                      if (cols[mid] < Jn) lo = mid + 1;
+                      else hi = mid;
+                    }
                   }
                   if (lo < len && cols[lo] == Jn) {
 #pragma unroll
