@@ -308,7 +308,9 @@ int b2_assemble_general_host(b2_ctx* ctx, const b2_pattern* pattern, int ndims, 
  * B2_EUNSUPPORTED.  "path": 0 = b2_assemble_host uses the owner-computes rows path for the whole topology, 1 = always
  * the element-scatter path.  "rows_nseg": force the number of marching segments of the rows kernel (0 = automatic).
  * "time_kernels": see b2_ctx_kernel_time (2: report the longest launch instead of the sum).  "rows_gpre": 0 = the rows
- * kernel evaluates the geometry itself instead of fetching the precomputed array by TMA. */
+ * kernel evaluates the geometry itself instead of fetching the precomputed array by TMA.  "rows_sym": 1 / 0 = scalar forms
+ * on unordered / ordered dof pairs (default: per degree).  "rows_vecsym": 0 = symmetric vector-valued forms integrate all
+ * nine component blocks instead of the six on and above the diagonal.  "elemset_mma": 0 = scalar FMA block loop. */
 int b2_ctx_set_option(b2_ctx* ctx, const char* name, int64_t value);
 
 #if defined(__GNUC__)
