@@ -13,7 +13,7 @@ import bench
 
 rep, key, workload = sys.argv[1:4]
 want = sys.argv[4] if len(sys.argv) > 4 else ''
-out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+out = open(rep).read() if rep.endswith('.csv') else subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout  # a report, or its exported raw page
 rows = list(csv.reader(io.StringIO(out)))
 hdr, units = rows[0], rows[1]
 col = {name: i for i, name in enumerate(hdr)}
