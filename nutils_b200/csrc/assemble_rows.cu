@@ -708,7 +708,7 @@ __global__ void __maxnreg__(C::MAXREG) k_rows3d(const RowParams prm, const __gri
   int imeta[IPT];
   int imetaT[TWO ? IPT : 1];   // SYM: the same for the transposed entry (row (j1, j2), column (i1, i2)); bit 24 = it exists (off-diagonal pair)
   int t2idx[IPT];              // index of the pair in the T2 arrays
-  constexpr bool REGBASE = SYM || NT <= 256;
+  constexpr bool REGBASE = SYM || NT <= 256;  // (512-thread ordered-pair configurations: the two extra registers per pair cost more in spills than the rebuilt base: p=3 13.5 -> 13.9 ms)
   long long ibase[REGBASE ? IPT : 1], ibaseT[TWO && REGBASE ? IPT : 1];  // thread part of the slot of an entry on interior layers (see the store)
   long long* sIc = reinterpret_cast<long long*>(smem + C::OFF_IC);  // [IPT][NT] (SYM: [2 IPT][NT], direct then transposed)
 #pragma unroll
@@ -1238,8 +1238,8 @@ int launch_rows_scalar(b2_ctx* ctx, RowParams& prm) {
   // the coefficient of a scalar form is symmetric (checked by the caller).  Measured (profiles/r02/README.md): the symmetric variant
   // (half the S3 and two thirds of the S2 work against scattered transposed stores) wins at degree 4 (K and M in one launch: -30 %);
   // at degree 2 the full variant is 3 % faster since its interior store takes the slot bases from registers (4.95 against 5.09 ms
-  // at 128^3), at degree 3 2 %; degree 1 is indifferent
-  const bool sym = ctx->opts.count("rows_sym") ? ctx->opts["rows_sym"] != 0 : C::P == 4;
+  // at 128^3), at degree 3 2 %; at degree 1 the symmetric variant wins (128^3: 1.33 against 1.55 ms)
+  const bool sym = ctx->opts.count("rows_sym") ? ctx->opts["rows_sym"] != 0 : (C::P == 4 || C::P == 1);
   if (gpre) {
     const int rc = sym ? launch_rows_cfg<C, FK, FM, 1, false, true, true>(ctx, prm) : launch_rows_cfg<C, FK, FM, 1, false, true, false>(ctx, prm);
     if (rc != B2_ENOMEM) return rc;
@@ -1560,6 +1560,9 @@ int launch_assemble_rows(b2_ctx* ctx, const b2_basis* basis, const b2_quad* quad
     if (variant == 30) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 0>, true, true, 1, false, true>(ctx, prm);
     if (variant == 40) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 0>, true, true, 1, false, true, true>(ctx, prm);
     if (variant == 41) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 0>, true, true, 1, false, false, true>(ctx, prm);
+    if (variant == 47) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 1>, true, true, 1, false, true, false>(ctx, prm);
+    if (variant == 48) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 3>, true, true, 1, false, true, false>(ctx, prm);
+    if (variant == 49) return launch_rows_cfg<RCfg<2, 4, 4, 3, 256, 2>, true, true, 1, false, true, false>(ctx, prm);
     if (variant == 42) return launch_rows_cfg<RCfg<2, 4, 4, 3, 512, 1>, true, true, 1, false, true, true>(ctx, prm);
     if (variant == 43) return launch_rows_cfg<RCfg<2, 4, 4, 3, 384, 1>, true, true, 1, false, true, true>(ctx, prm);
     if (variant == 44) return launch_rows_cfg<RCfg<2, 4, 4, 1, 256, 1, 7, 2>, true, true, 1, false, true, true>(ctx, prm);
