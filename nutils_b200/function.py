@@ -336,9 +336,15 @@ class Array:
     __rmul__ = __mul__
 
     def dot(self, other, axes=None):
+        '''Inner product with the reference's semantics (function.py:484-524): without `axes` the second argument must be a vector
+        and is contracted with the FIRST axis of self.'''
         other = Array.cast(other)
         if axes is None:
-            return (self * other).sum(-1) if other.ndim == self.ndim else (self * other[(None,) * (self.ndim - other.ndim)]).sum(-1)
+            if other.ndim != 1 or other.shape[0] != self.shape[0]:
+                raise ValueError('dot without axes: the second argument must be a vector matching the first axis')
+            if self.ndim > 1:
+                other = other[(slice(None),) + (None,) * (self.ndim - 1)]
+            axes = 0
         return (self * other).sum(axes)
 
     # -- integration-time views --------------------------------------------------------------------

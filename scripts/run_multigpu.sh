@@ -5,7 +5,7 @@ MAXN=${1:-8}
 mkdir -p gpurun_out/mg
 run() { # N tag extra-args
   N=$1; shift; TAG=$1; shift
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 30 --warmup 3 --no-cpu "$@" > gpurun_out/mg/$TAG.json 2> gpurun_out/mg/$TAG.err
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 --no-cpu "$@" > gpurun_out/mg/$TAG.json 2> gpurun_out/mg/$TAG.err
   tail -c 300 gpurun_out/mg/$TAG.err | tail -1
   cut -c1-180 gpurun_out/mg/$TAG.json
 }
