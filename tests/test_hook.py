@@ -129,6 +129,46 @@ def test_boundary_side_hooked_equals_stock(hooked, shape, side):
     _compare(ref, got)
 
 
+def _trimmed(nutils, n=4, degree=2, maxrefine=1):
+    'finite-cell Poisson forms on a ball trimmed out of a box (topology.py:1598-1660): PrunedBasis, ragged cut-cell points'
+    from nutils import mesh, function
+    topo0, geom = mesh.rectilinear([numpy.linspace(-1, 1, n + 1)] * 3)
+    topo = topo0.trim(.77 - (geom ** 2).sum(), maxrefine=maxrefine)
+    basis = topo.basis('spline', degree=degree)
+    g = basis.grad(geom)
+    J = function.J(geom)
+    K = topo.integral((g[:, None, :] * g[None, :, :]).sum(-1) * J, degree=2 * degree)
+    M = topo.integral(basis[:, None] * basis[None, :] * J, degree=2 * degree)
+    F = topo.integral(basis * J, degree=2 * degree)
+    return function.eval((function.as_csr(K), function.as_csr(M), F))
+
+
+def test_trimmed_topology_hooked_equals_stock(hooked):
+    'a trimmed topology arrives as an element set: the reference\'s own cut-cell points and pruned numbering, element-set kernels'
+    nutils = util_ref.reference()
+    ref = _trimmed(nutils)
+    hooked.install()
+    be = util_ref.OracleBackend()
+    hooked.set_backend(be)
+    got = _trimmed(nutils)
+    assert hooked.STATS['accelerated'] >= 1 and be.calls >= 1, hooked.STATS
+    _compare(ref, got)
+
+
+@pytest.mark.gpu
+def test_gpu_trimmed_topology_hooked_equals_stock(hooked):
+    nutils = util_ref.reference()
+    from nutils_b200 import engine
+    ref = _trimmed(nutils)
+    hooked.install()
+    ctx = engine.Context.get(0)
+    n0 = ctx.launch_count
+    got = _trimmed(nutils)
+    assert hooked.STATS['accelerated'] >= 1, hooked.STATS
+    assert ctx.launch_count > n0, 'the integrals did not run on the GPU'
+    _compare(ref, got)
+
+
 def test_declines_position_dependent_coefficient(hooked):
     'an integrand outside the closed form falls through to the stock evaluable: same numbers, no backend call'
     nutils = util_ref.reference()
