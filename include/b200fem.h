@@ -310,7 +310,8 @@ int b2_assemble_general_host(b2_ctx* ctx, const b2_pattern* pattern, int ndims, 
  * "time_kernels": see b2_ctx_kernel_time (2: report the longest launch instead of the sum).  "rows_gpre": 0 = the rows
  * kernel evaluates the geometry itself instead of fetching the precomputed array by TMA.  "rows_sym": 1 / 0 = scalar forms
  * on unordered / ordered dof pairs (default: per degree).  "rows_vecsym": 0 = symmetric vector-valued forms integrate all
- * nine component blocks instead of the six on and above the diagonal.  "elemset_mma": 0 = scalar FMA block loop. */
+ * nine component blocks instead of the six on and above the diagonal.  "elemset_mma": 0 = scalar FMA block loop.
+ * "elemset_queue": 0 = elements of ragged sets dealt round robin to the CTAs instead of the dynamic longest-first queue. */
 int b2_ctx_set_option(b2_ctx* ctx, const char* name, int64_t value);
 
 #if defined(__GNUC__)

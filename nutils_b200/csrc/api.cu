@@ -87,6 +87,7 @@ extern "C" int b2_ctx_destroy(b2_ctx* ctx) {
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->gbuf) cudaFree(ctx->gbuf);
+  if (ctx->queue) cudaFree(ctx->queue);
   if (ctx->formbuf) cudaFree(ctx->formbuf);
   if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->copy_event); }
   for (auto* v : {&ctx->kernel_events, &ctx->event_pool})

@@ -71,6 +71,13 @@ extern "C" int b2_elemset_create(b2_ctx* ctx, const b2_basis* basis, int64_t nse
       rc = upload_n(ctx, (const long long*)qoff, (size_t)nsel + 1, &es->d_qoff);
       if (rc == B2_OK) rc = upload_n(ctx, qcoords, (size_t)es->npoints * basis->ndims, &es->d_qcoords);
       if (rc == B2_OK) rc = upload_n(ctx, qweights, (size_t)es->npoints, &es->d_qweights);
+      if (rc == B2_OK) {
+        // longest-processing-time-first: the element queue of the kernel starts with the cells that carry the most points
+        std::vector<long long> order((size_t)nsel);
+        for (int64_t k = 0; k < nsel; k++) order[(size_t)k] = k;
+        std::stable_sort(order.begin(), order.end(), [&](long long a, long long b) { return qoff[a + 1] - qoff[a] > qoff[b + 1] - qoff[b]; });
+        rc = upload_n(ctx, order.data(), order.size(), &es->d_order);
+      }
     }
   }
   if (rc == B2_OK && renumber) {
@@ -162,7 +169,7 @@ extern "C" int b2_elemset_destroy(b2_elemset* es) {
   if (es->d_normals) cudaFree(es->d_normals);
   for (double* p : es->d_coef)
     if (p) cudaFree(p);
-  void* ptrs[] = {es->d_elem_ids, es->d_qoff, es->d_qcoords, es->d_qweights, es->d_renumber, es->d_scale, es->d_selmask, es->d_dofmap,
+  void* ptrs[] = {es->d_order, es->d_elem_ids, es->d_qoff, es->d_qcoords, es->d_qweights, es->d_renumber, es->d_scale, es->d_selmask, es->d_dofmap,
                   es->d_coeffs[0], es->d_coeffs[1], es->d_coeffs[2], es->d_efirst[0], es->d_efirst[1], es->d_efirst[2], es->d_elast[0], es->d_elast[1], es->d_elast[2]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -286,6 +293,7 @@ static int build_views(b2_ctx* ctx, const b2_pattern* pattern, const b2_elemset*
   E.nsel = es->nsel;
   E.elem_ids = es->d_elem_ids;
   E.qoff = es->d_qoff;
+  E.order = es->d_order;
   E.qcoords = es->d_qcoords;
   E.qweights = es->d_qweights;
   E.renumber = es->d_renumber;

@@ -59,6 +59,7 @@ struct ESParams {
   ElemSetView E;
   FormView F;
   long long sel_begin, sel_end;
+  unsigned long long* queue;  // next element to hand out (zeroed before the launch); null: static round robin
   int qchunk;  // points per chunk
   int pm1;     // max(p)+1 of the solution basis
   int pgm1;    // max(p)+1 of the geometry basis (spline geometry)
@@ -164,7 +165,18 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512, TCMAX == 4 ? 4 : 1) k_
     (geo ? sMg : sMi)[geo ? a - nb : a] = mi;
   }
 
-  for (long long sel = P.sel_begin + blockIdx.x; sel < P.sel_end; sel += gridDim.x) {
+  // Elements differ in cost by two orders of magnitude (27 points in an uncut cell, thousands in a cut one): they are handed out
+  // one at a time from a global counter instead of round robin, so that no CTA is left with a tail of expensive cells
+  __shared__ long long s_sel;
+  const bool use_order = E.order && P.sel_begin == 0 && P.sel_end == E.nsel;  // (a partial range keeps the order of the set)
+  for (long long sel = P.sel_begin + blockIdx.x;; sel += gridDim.x) {
+    if (P.queue) {
+      if (tid == 0) s_sel = P.sel_begin + (long long)atomicAdd(P.queue, 1ULL);
+      __syncthreads();   // (the next write of s_sel lies behind the barriers of this element)
+      sel = s_sel;
+    }
+    if (sel >= P.sel_end) break;
+    if (P.queue && use_order) sel = E.order[sel];
     const long long elem = E.elem_ids ? E.elem_ids[sel] : sel;
     int ie[3] = {0, 0, 0};
     {
@@ -756,6 +768,9 @@ __global__ void __launch_bounds__(TCMAX == 4 ? 128 : 512, TCMAX == 4 ? 4 : 1) k_
   }
 }
 
+// per-element point sets of different length: the case the element queue is for
+static inline bool E_ragged(const ESParams& P) { return P.E.qoff != nullptr; }
+
 template <int DIM, int TCMAX, int NJ>
 int launch_cfg(b2_ctx* ctx, ESParams& P, int max_nq) {
   const int nb = P.B.nb, ne = P.ne, ne2 = ne * ne;
@@ -781,6 +796,17 @@ int launch_cfg(b2_ctx* ctx, ESParams& P, int max_nq) {
   B2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   per_sm = std::max(per_sm, 1);
   const long long nel = P.sel_end - P.sel_begin;
+  P.queue = nullptr;
+  if (E_ragged(P) && !(ctx->opts.count("elemset_queue") && ctx->opts["elemset_queue"] == 0)) {
+    if (!ctx->queue && cudaMalloc(&ctx->queue, sizeof(unsigned long long)) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->queue = nullptr;
+    }
+    if (ctx->queue) {
+      B2_CUDA(ctx, cudaMemsetAsync(ctx->queue, 0, sizeof(unsigned long long), ctx->stream));
+      P.queue = ctx->queue;
+    }
+  }
   const int blocks = (int)std::min<long long>(nel, (long long)ctx->sm_count * per_sm * 4);
   {
     KernelTimer timer(ctx);

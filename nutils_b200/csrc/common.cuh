@@ -63,6 +63,7 @@ struct ElemSetView {
   long long nsel;
   const long long* elem_ids;   // [nsel] or null (all elements)
   const long long* qoff;       // [nsel+1] or null (tensor rule)
+  const long long* order;      // [nsel] elements by decreasing cost, or null
   const double* qcoords;       // [npoints][ndims]
   const double* qweights;      // [npoints]
   const int* renumber;         // [nbasis_parent] -> new index, < 0: dropped; null = identity
@@ -126,6 +127,8 @@ struct b2_ctx {
   void* formbuf = nullptr;
   size_t formbuf_bytes = 0;
   int64_t serial = 0;
+  // element queue head of the element-set kernel (dynamic hand-out of elements of very different cost)
+  unsigned long long* queue = nullptr;
   // optional per-kernel timing (option "time_kernels")
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
@@ -198,6 +201,7 @@ struct b2_elemset {
   std::vector<int> renumber;       // host copy (empty = identity)
   long long* d_elem_ids = nullptr;
   long long* d_qoff = nullptr;
+  long long* d_order = nullptr;   // ragged point sets: the elements by decreasing number of points (hand-out order of the element queue)
   double* d_qcoords = nullptr;
   double* d_qweights = nullptr;
   int* d_renumber = nullptr;

@@ -23,6 +23,7 @@ if __name__ == '__main__':
     ctx = engine.Context.get(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_option('elemset_mma', mma)
+    ctx.set_option('elemset_queue', int(os.environ.get('ES_QUEUE', 1)))
     t0 = time.perf_counter()
     elem_ids, qoff, qc, qw, ren, nbn = octree_ball(n, p, L)
     t1 = time.perf_counter()
